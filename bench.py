@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the geometry hot path (BASELINE.json metric) on N B200 GPUs of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path on the box's host cores
+
+One "step" = the reference's ChamferEMD reconstruction loss (src/train/metrics_and_losses.py:70-79) forward AND
+backward w.r.t. the reconstruction on one batch of B=32 cloud pairs of 2048 points per GPU (BASELINE.json configs
+[0]+[2], "Chamfer+EMD fwd/bwd clouds/sec (B=32,N=2048)").  The batch is sharded over ranks (weak scaling: 32 clouds
+per GPU); the only collective is one all-reduce of the loss.  The kNN graph throughput (configs[1]) and the
+Chamfer-only / EMD-only throughputs are reported in the same JSON line under "sub_metrics" with their rooflines.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+B_PER_GPU = 32
+N_POINTS = 2048
+KNN_N, KNN_K, KNN_C = 1024, 20, 64
+METRIC = "chamfer_emd_fwd_bwd_clouds_per_sec"
+WORKLOAD = ("ChamferEMD recon loss fwd+bwd (pykeops_chamfer + match_cost), B=32 x 2048 xyz points per GPU, "
+            "S1 synthetic ShapeNet-shaped clouds (BASELINE configs[0]+[2]); kNN k=20 N=1024 C=3/64 in sub_metrics (configs[1])")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--no-sub", action="store_true", help="skip sub-metrics (Chamfer-only, EMD-only, kNN)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows: list[list[str]] = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks() -> dict:
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            d = json.loads(f.read_text())
+            peaks.update(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], sm_max_mhz=d.get("sm_max_mhz"),
+                         source="measured (MEASURED_PEAKS.json)")
+        except Exception:
+            pass
+    return peaks
+
+
+def measure_pipe_peaks() -> dict:
+    """FP32 / MUFU pipe peaks measured on this box by tools/pipe_peaks (built in-tree); derived figures otherwise."""
+    derived = {"ffma_tflops": 148 * 128 * 2 * 1.965e9 / 1e12, "mufu_ex2_gops": 148 * 16 * 1.965e9 / 1e9,
+               "source": "derived: 148 SM x 128 FMA lanes (16 SFU lanes) x 1.965 GHz"}
+    exe = ROOT / "tools" / "pipe_peaks"
+    if not exe.exists():
+        return derived
+    try:
+        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout.strip().splitlines()[-1]
+        d = json.loads(out)
+        d["ffma_tflops"] = max(d["ffma_tflops"], d.get("ffma2_tflops", 0.0))
+        d["source"] = "measured on this GPU by tools/pipe_peaks (FFMA/FFMA2 and MUFU.EX2 saturation loops)"
+        return d
+    except Exception:
+        return derived
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from pointcloudcounterfactual_b200 import _lib, losses, neighbour_ops, sharding, synthetic
+    from pointcloudcounterfactual_b200.structural_losses import match_cost, nn_distance
+    from pointcloudcounterfactual_b200.structural_losses.structural_losses_backend import NNDistance
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl b200) needs CUDA GPUs; there is no CPU fallback")
+    rank, world, local = sharding.init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    K, W = args.steps, max(args.warmup, 3)
+
+    # identical bits on CPU and GPU: generated on the CPU, this rank's slice of the global batch
+    recon_h, ref_h = synthetic.s1_near(B_PER_GPU, N_POINTS, first=rank * B_PER_GPU)
+    recon_h, ref_h = recon_h.pin_memory(), ref_h.pin_memory()
+    recon_d, ref_d = recon_h.to(dev), ref_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        r = recon_d.detach().requires_grad_(True)
+        loss = losses.chamfer_emd(r, ref_d)
+        (grad,) = torch.autograd.grad(loss.sum(), r)
+        mean = sharding.global_mean_loss(loss)
+        return loss, grad, mean
+
+    def step_e2e():
+        r = recon_h.to(dev, non_blocking=True).requires_grad_(True)
+        t = ref_h.to(dev, non_blocking=True)
+        loss = losses.chamfer_emd(r, t)
+        (grad,) = torch.autograd.grad(loss.sum(), r)
+        mean = sharding.global_mean_loss(loss)
+        return loss.cpu(), float(mean.cpu()), grad
+
+    def timed(fn, steps, warm):
+        """per-step CUDA events on the launching stream; L2 flushed between steps outside the events."""
+        for _ in range(warm):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for e0, e1 in evs:
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+        barrier()
+        return [e0.elapsed_time(e1) for e0, e1 in evs]
+
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pipe = measure_pipe_peaks() if rank == 0 else {}
+    peaks = load_peaks()
+    barrier()
+
+    # ---- headline: device-resident ------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    times = timed(step_device, K, W)
+    launches = (_lib.launch_count() - l0) * K // (K + W)
+    total_ms = reduce_max(sum(times))
+    value = world * B_PER_GPU * K / (total_ms * 1e-3)
+
+    # ---- e2e: pinned host inputs -> device -> loss back on the host, every step ------------------------------
+    for _ in range(W):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    barrier()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else {}
+    e2e_value = world * B_PER_GPU * K / e2e_s
+    h2d = recon_h.numel() * 4 + ref_h.numel() * 4
+    d2h = B_PER_GPU * 4 + 4
+
+    # ---- dominant kernel: one approxmatch sweep (27 of them per step) --------------------------------------
+    def ev_time(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ones = torch.ones(B_PER_GPU, N_POINTS, device=dev)
+    ratio = torch.empty(B_PER_GPU, N_POINTS, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def sweep():
+        _lib.check(lib.pcc_approxmatch_sweep(B_PER_GPU, N_POINTS, N_POINTS, recon_d.data_ptr(), ref_d.data_ptr(),
+                                             ones.data_ptr(), ones.data_ptr(), ratio.data_ptr(), -16.0, st), "sweep")
+
+    sweep_ms = ev_time(sweep, 50)
+    pairs = B_PER_GPU * N_POINTS * N_POINTS
+    mufu_peak = pipe.get("mufu_ex2_gops", 148 * 16 * 1.965) if rank == 0 else 1.0
+    fp32_peak = pipe.get("ffma_tflops", 74.4) if rank == 0 else 1.0
+    roofline = {
+        "kernel": "am_rowsum_kernel (approxmatch sweep; 27 launches per step)",
+        "bound": "sfu", "unit": "Gexp/s", "achieved": pairs / (sweep_ms * 1e-3) / 1e9, "peak": mufu_peak,
+        "frac": pairs / (sweep_ms * 1e-3) / 1e9 / mufu_peak, "traffic": None,
+        "peak_source": pipe.get("source", ""), "launch_ms": sweep_ms,
+        "fp32_tflops": 11 * pairs / (sweep_ms * 1e-3) / 1e12, "fp32_frac": 11 * pairs / (sweep_ms * 1e-3) / 1e12 / fp32_peak,
+        "share_of_step": 27 * sweep_ms / (sum(times) / K),
+        "note": "1 MUFU.EX2 + 11 flop per pair; the SFU pipe (16 lanes/SM) bounds the kernel, not HBM or tensor cores",
+    }
+
+    # ---- sub-metrics ----------------------------------------------------------------------------------------
+    sub = {}
+    if not args.no_sub:
+        def graph_or_eager(fn, reps=50):
+            """CUDA-graph replay of one op (removes Python launch latency); eager if capture is refused."""
+            try:
+                fn()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                ms = ev_time(g.replay, reps)
+                return ms, True
+            except Exception as e:  # noqa: BLE001
+                torch.cuda.synchronize()
+                print(f"[bench] graph capture refused ({type(e).__name__}); eager timing", file=sys.stderr)
+                return ev_time(fn, reps), False
+
+        rr = recon_d.detach().requires_grad_(True)
+
+        def chamfer_fb():
+            loss = losses.pykeops_chamfer(rr, ref_d)
+            torch.autograd.grad(loss.sum(), rr)
+
+        def chamfer_f():
+            NNDistance(recon_d, ref_d)
+
+        def emd_fb():
+            loss = match_cost(rr, ref_d)
+            torch.autograd.grad(loss.sum(), rr)
+
+        x3 = synthetic.knn_xyz(B_PER_GPU, KNN_N, first=rank * B_PER_GPU).to(dev)
+        xf = synthetic.knn_features(B_PER_GPU, KNN_C, KNN_N, seed=2000 + rank).to(dev)
+        x25 = synthetic.knn_xyz(B_PER_GPU, N_POINTS, first=rank * B_PER_GPU).to(dev)
+
+        ms, gr = graph_or_eager(chamfer_f)
+        flops = 8.0 * 2 * B_PER_GPU * N_POINTS * N_POINTS
+        sub["chamfer_fwd"] = {"ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
+                              "roofline": {"bound": "fp32", "unit": "TFLOP/s", "achieved": flops / (ms * 1e-3) / 1e12,
+                                           "peak": fp32_peak, "frac": flops / (ms * 1e-3) / 1e12 / fp32_peak,
+                                           "gpairs_per_s": flops / 8 / (ms * 1e-3) / 1e9}}
+        ms, gr = graph_or_eager(chamfer_fb)
+        sub["chamfer_fwd_bwd"] = {"ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
+                                  "roofline": {"bound": "fp32", "unit": "TFLOP/s", "achieved": flops / (ms * 1e-3) / 1e12,
+                                               "peak": fp32_peak, "frac": flops / (ms * 1e-3) / 1e12 / fp32_peak}}
+        ms, gr = graph_or_eager(emd_fb, reps=10)
+        sub["emd_fwd_bwd"] = {"ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr}
+        for name, x, k, c in (("knn_xyz_k20_n1024", x3, KNN_K, 3), ("knn_feat64_k20_n1024", xf, KNN_K, KNN_C),
+                              ("knn_xyz_k25_n2048", x25, 25, 3), ("knn_xyz_k4_n2048", x25, 4, 3)):
+            ms, gr = graph_or_eager(lambda x=x, k=k: neighbour_ops.knn(x, k))
+            n = x.shape[2]
+            fl = (8.0 if c == 3 else 3.0 * c) * B_PER_GPU * n * n
+            sub[name] = {"ms": ms, "graphs_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
+                         "roofline": {"bound": "fp32", "unit": "TFLOP/s", "achieved": fl / (ms * 1e-3) / 1e12,
+                                      "peak": fp32_peak, "frac": fl / (ms * 1e-3) / 1e12 / fp32_peak,
+                                      "note": "exact fp32 direct-difference path (sub+fma per channel); "
+                                              "tcgen05 candidate-generator path not yet enabled"}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_reference_value(sample_clouds=4, reps=2)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "points": N_POINTS,
+                       "parallelism": f"batch-sharded x{world}, one all-reduce of the loss per step",
+                       "l2": "flushed between steps (256 MiB memset outside the per-step CUDA events); inputs are 1.5 MB",
+                       "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "pinned host clouds -> H2D -> chamfer_emd fwd+bwd -> loss D2H each step, host wall clock"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "peaks": {**peaks, "pipe": pipe},
+            "sub_metrics": sub,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_value(sample_clouds: int, reps: int) -> dict:
+    """The reference's CPU path on the host cores, bounded sample of the same workload.
+
+    Chamfer: the reference's torch CPU path (torch_chamfer, metrics_and_losses.py:44-47) forward+backward, restated
+    in oracle/torch_ref.py.  EMD: the reference has NO CPU implementation of match_cost (it is CUDA-only,
+    metrics_and_losses.py:76-79), so its algorithm is timed through the C restatement oracle/geom_oracle.c
+    (approxmatch + matchcost + matchcostgrad, OpenMP over all cores)."""
+    import torch
+
+    import oracle
+    from oracle import torch_ref
+    from pointcloudcounterfactual_b200 import synthetic
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle.set_num_threads(cores)
+    recon, ref = synthetic.s1_near(sample_clouds, N_POINTS)
+    torch_ref.chamfer_fwd_bwd(recon, ref)  # warm-up
+    oracle.approxmatch(recon[:1].numpy(), ref[:1].numpy(), want_match=False)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        torch_ref.chamfer_fwd_bwd(recon, ref)
+        match, _ = oracle.approxmatch(recon.numpy(), ref.numpy())
+        oracle.matchcost(recon.numpy(), ref.numpy(), match)
+        oracle.matchcostgrad(recon.numpy(), ref.numpy(), match)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": sample_clouds / dt, "unit": "clouds/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_clouds} clouds x {N_POINTS} points, {reps} repetitions: torch CPU torch_chamfer fwd+bwd "
+                      f"(reference path) + C oracle approxmatch/matchcost/matchcostgrad (no CPU EMD exists in the reference)"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    sample = 2  # clouds per step: ~0.5 s of host work per step
+    base = None
+    t_all0 = time.perf_counter()
+    vals = []
+    for i in range(W + K):
+        r = cpu_reference_value(sample_clouds=sample, reps=1)
+        if i >= W:
+            vals.append(r["value"])
+        base = r
+    total = sum(sample / v for v in vals)
+    value = sample * K / total
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": total / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "points": N_POINTS,
+                   "sample": f"each step = {sample} clouds of the workload (bounded sample)"},
+        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": base["cores"], "kind": "port", "sample": base["sample"]},
+        "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all0,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

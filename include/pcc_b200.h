@@ -1,0 +1,115 @@
+/*
+ * pcc_b200.h -- C ABI of libpcc_b200.so, the B200 (sm_100a) geometry hot path for
+ * nverchev/PointCloudCounterfactual.
+ *
+ * Drop-in boundary: every entry point below replaces one native launcher that the reference's
+ * pybind11 bindings call (paths relative to /root/reference).  Same argument lists and meaning;
+ * differences from the reference launchers:
+ *   - `extern "C"`, returns an int status (0 = ok, otherwise a cudaError_t value or a PCC_E* code)
+ *     instead of void / throwing std::runtime_error (approxmatch.cu:303-306) / printf (emd_cuda.cu:236-248);
+ *   - all pointers are DEVICE pointers on the current device unless the name ends in `_host`;
+ *   - all work is enqueued on `stream` (the reference's emd kernels ignore the current stream,
+ *     emd_cuda.cu:256-268, and nndistancegrad memsets on the legacy stream, nndistance.cu:150-151);
+ *     no entry point synchronises the host;
+ *   - no torch / ATen types anywhere in the signatures.
+ */
+#ifndef PCC_B200_H_
+#define PCC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *pcc_stream_t; /* a cudaStream_t */
+
+#define PCC_OK 0
+#define PCC_EINVAL (-1)    /* shape rule violated (mirrors emd_cuda_forward's -1, emd_cuda.cu:235-248) */
+#define PCC_ENOTSUP (-2)   /* configuration outside what the kernels support (e.g. k > PCC_KNN_MAX_K) */
+#define PCC_KNN_MAX_K 128
+
+/* Library / build identification. */
+const char *pcc_version(void);
+/* Text for a status returned by any entry point (cudaGetErrorString for CUDA codes). */
+const char *pcc_status_string(int status);
+/* Number of kernels this library has launched since it was loaded (all entry points; for bench.py's gpu_launches). */
+uint64_t pcc_launch_count(void);
+
+/* ---- Chamfer nearest-neighbour distance -------------------------------------------------------------
+ * Replaces `void nndistance(int b,int n,const float*xyz,int m,const float*xyz2,float*result,int*result_i,
+ *                           float*result2,int*result2_i,cudaStream_t)`
+ *   declared external/pytorch_structural_losses/src/structural_loss.cpp:13, defined src/nndistance.cu:125-128.
+ * xyz (b,n,3), xyz2 (b,m,3) fp32 contiguous.  result[b,n] = min_k |xyz[j]-xyz2[k]|^2 with the arithmetic
+ * d = fma(dz,dz,fma(dx,dx,dy*dy)); result_i[b,n] = LOWEST k attaining it (int32).  result2/result2_i: roles swapped.
+ * One fused launch covers both directions. */
+int pcc_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *result, int *result_i,
+                   float *result2, int *result2_i, pcc_stream_t stream);
+
+/* Replaces `void nndistancegrad(...)` (structural_loss.cpp:14, nndistance.cu:149-154).
+ * grad_xyz1 (b,n,3) / grad_xyz2 (b,m,3) are fully written (no memset needed).  Deterministic: per target point
+ * the own term is added first, then the scatter terms in ascending source index (the reference uses float
+ * atomics in arbitrary order). */
+int pcc_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2, const float *grad_dist1,
+                       const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
+                       float *grad_xyz2, pcc_stream_t stream);
+
+/* ---- Approximate-matching EMD -----------------------------------------------------------------------
+ * Replaces `void approxmatch(int b,int n,int m,const float*xyz1,const float*xyz2,float*match,float*temp,
+ *                            cudaStream_t)` (structural_loss.cpp:10, approxmatch.cu:299-307).
+ * match (b,m,n) is fully written; temp (b, 2(n+m)) is scratch = [remainL|remainR|ratioL|ratioR] per cloud. */
+int pcc_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp,
+                    pcc_stream_t stream);
+/* Replaces `void matchcost(...)` (structural_loss.cpp:11, approxmatch.cu:309-316): out[b] = sum match*|x1-x2|. */
+int pcc_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *out,
+                  pcc_stream_t stream);
+/* Replaces `void matchcostgrad(...)` (structural_loss.cpp:12, approxmatch.cu:318-326). */
+int pcc_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match,
+                      float *grad1, float *grad2, pcc_stream_t stream);
+/* Fused replacement for the ApproxMatch -> MatchCost -> MatchCostGrad chain behind
+ * structural_losses.match_cost (structural_losses/match_cost.py:14-42): same cost and gradients, but the
+ * (b,m,n) match matrix is never materialised (O(b(n+m)) memory).  grad1 / grad2 may be NULL.
+ * temp: (b, 2(n+m)) floats of scratch, as for pcc_approxmatch. */
+int pcc_matchcost_fused(int b, int n, int m, const float *xyz1, const float *xyz2, float *cost, float *grad1,
+                        float *grad2, float *temp, pcc_stream_t stream);
+
+/* Measurement hook (bench.py's roofline leg): ONE sweep of the approxmatch solver -- the kernel that dominates the
+ * EMD path -- exactly as pcc_approxmatch / pcc_matchcost_fused launch it for sweep 1 of a level
+ * (approxmatch.cu:29-62): ratio[b,n] = remain[b,n] / (1e-9 + sum_l exp(level*|x1_k-x2_l|^2) * weight[b,l]). */
+int pcc_approxmatch_sweep(int b, int n, int m, const float *xyz1, const float *xyz2, const float *weight,
+                          const float *remain, float *ratio, float level, pcc_stream_t stream);
+
+/* ---- kNN graph (DGCNN) ------------------------------------------------------------------------------
+ * Replaces the KeOps reduction behind `pykeops_knn` / `knn` (src/utils/neighbour_ops.py:63-82):
+ * x (b,c,n) channels-first fp32 -> idx (b,n,k) int64, the k smallest squared distances per point INCLUDING the
+ * point itself, ascending by (distance, index); distance = sum_c (x_i-x_j)^2 accumulated with fma over c in order.
+ * dist (b,n,k) may be NULL.  Requires 1 <= k <= min(n, PCC_KNN_MAX_K). */
+int pcc_knn(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, pcc_stream_t stream);
+
+/* General argKmin between two point sets, point-major layout (the LazyTensor patterns of
+ * neighbour_ops.py:35-40,81; metrics_and_losses.py:33,36; quantize.py:28):
+ * q (b,nq,c), r (b,nr,c) -> idx (b,nq,k) int64 ascending by (distance, index).  k=1 is argmin. */
+int pcc_argkmin(int b, int nq, int nr, int c, int k, const float *q, const float *r, int64_t *idx, float *dist,
+                pcc_stream_t stream);
+
+/* ---- Auction EMD ------------------------------------------------------------------------------------
+ * Replaces `int emd_cuda_forward(at::Tensor xyz1, ..., float eps, int iters)` (external/emd/src/emd.cpp:14-21,
+ * emd_cuda.cu:227-281) with the tensors passed as raw pointers in the same order.  The caller allocates and
+ * initialises the work buffers exactly as emd/emd_module.py:34-45 does (assignment = assignment_inv = -1, the rest 0;
+ * unass_cnt / unass_cnt_sum / cnt_tmp are 512 ints).  Returns 1 on success and -1 on a shape error, like the
+ * reference (n must be a multiple of 1024, b <= 512); other values are CUDA errors.
+ * One persistent CTA per cloud runs all `iters` rounds (the reference launches 7 kernels per round). */
+int pcc_emd_forward(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *assignment,
+                    float *price, int *assignment_inv, int *bid, float *bid_increments, float *max_increments,
+                    int *unass_idx, int *unass_cnt, int *unass_cnt_sum, int *cnt_tmp, int *max_idx, float eps,
+                    int iters, pcc_stream_t stream);
+/* Replaces `int emd_cuda_backward(xyz1, xyz2, gradxyz, graddist, idx)` (emd.cpp:23-26, emd_cuda.cu:301-315):
+ * gradxyz (b,n,3) is overwritten with 2*graddist*(xyz1 - xyz2[idx]).  Returns 1 on success. */
+int pcc_emd_backward(int b, int n, const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist,
+                     const int *idx, pcc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCC_B200_H_ */

@@ -1,0 +1,574 @@
+// Approximate-matching EMD (approxmatch + match cost + gradients) for sm_100a.
+//
+// Replaces external/pytorch_structural_losses/src/approxmatch.cu (approxmatchkernel :3-182, matchcostkernel
+// :184-224, matchcostgrad{1,2}kernel :229-291).  Same algorithm -- 9 annealing levels -4^j (j = 7..-1), each made of
+// three all-pairs sweeps with E(k,l) = exp(level * |x1_k - x2_l|^2) -- restructured for B200:
+//
+//   phase A  "solve": every sweep is one instance of the same row-sum kernel
+//                S[p] = sum_q E(p,q) * w[q]
+//            with a per-sweep epilogue (ratioL / ratioR+remainR / remainL update).  All clouds and all row blocks
+//            run in parallel over the 148 SMs (the reference runs one 512-thread CTA per cloud), two partner
+//            points per step with packed FADD2/FMUL2/FFMA2 and one MUFU.EX2 each.  The per-level scaling vectors
+//            ratioL_j, ratioR_j (9 x (n+m) floats per cloud) are kept.
+//   phase B  "apply": match[l][k] = sum_j E_j(k,l) ratioL_j[k] ratioR_j[l] is evaluated ONCE per pair
+//            (5 exponentials per pair: levels j+1 are obtained from level j by two squarings) and either written
+//            to the (b,m,n) matrix (pcc_approxmatch; one 0.5 GiB write instead of nine read-modify-writes) or
+//            consumed on the fly into cost and gradients (pcc_matchcost_fused; the matrix never exists).
+#include "common.cuh"
+
+namespace pcc {
+
+constexpr int AM_LEVELS = 9;  // j = 7, 6, ..., -1  (approxmatch.cu:24; the j == -2 / level 0 sweep is dead code)
+constexpr int AM_THREADS = 128;
+constexpr int AM_QTILE = 1024;  // partner points per shared-memory tile in the row-sum kernel
+constexpr float AM_LOG2E = 1.4426950408889634f;
+
+enum { EPI_RATIO_L = 0, EPI_RATIO_R = 1, EPI_REMAIN_L = 2 };
+
+__global__ void am_init_kernel(int n, int m, float *__restrict__ temp, float multiL, float multiR) {
+  // temp per cloud: [remainL(n) | remainR(m) | ratioL(n) | ratioR(m)]   (approxmatch.cu:4,19-21)
+  float *t = temp + (size_t)blockIdx.y * (size_t)(n + m) * 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x)
+    t[i] = i < n ? multiL : multiR;
+}
+
+// S[p] = sum_q exp2(scale * |x_p - x_q|^2) * w[q], then the epilogue of the sweep.
+template <int EPI>
+__global__ void __launch_bounds__(AM_THREADS)
+am_rowsum_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
+                 const float *__restrict__ wQ, size_t wQ_stride, float scale, float *__restrict__ remainP,
+                 size_t remain_stride, float *__restrict__ ratioP, size_t ratio_stride,
+                 const float *__restrict__ ratioP_in) {
+  __shared__ float4 tile[AM_QTILE];  // per partner pair: (x0,x1,y0,y1) (z0,z1,w0,w1)
+  const size_t cloud = blockIdx.y;
+  xP += cloud * (size_t)nP * 3;
+  xQ += cloud * (size_t)nQ * 3;
+  wQ += cloud * wQ_stride;
+  const int p = blockIdx.x * AM_THREADS + threadIdx.x;
+  const int pc = min(p, nP - 1);
+  const float px = xP[pc * 3], py = xP[pc * 3 + 1], pz = xP[pc * 3 + 2];
+  const f32x2 npx = pack2(-px, -px), npy = pack2(-py, -py), npz = pack2(-pz, -pz);
+  const f32x2 sc2 = pack2(scale, scale);
+  f32x2 acc = 0ull, acc_b = 0ull;
+  float *tf = reinterpret_cast<float *>(tile);
+
+  for (int base = 0; base < nQ; base += AM_QTILE) {
+    const int cnt = min(AM_QTILE, nQ - base);
+    const int cnt4 = (cnt + 3) & ~3;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt4; i += AM_THREADS) {
+      float x = 0.f, y = 0.f, z = 0.f, w = 0.f;  // padding partner: weight 0
+      if (i < cnt) {
+        const float *q = xQ + (size_t)(base + i) * 3;
+        x = q[0];
+        y = q[1];
+        z = q[2];
+        w = wQ[base + i];
+      }
+      const int o = (i >> 1) * 8 + (i & 1);
+      tf[o] = x;
+      tf[o + 2] = y;
+      tf[o + 4] = z;
+      tf[o + 6] = w;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int pr = 0; pr < (cnt4 >> 1); pr += 2) {
+      const float4 a0 = tile[pr * 2], a1 = tile[pr * 2 + 1];
+      const float4 b0 = tile[pr * 2 + 2], b1 = tile[pr * 2 + 3];
+      const f32x2 da = mul2(sqdist2(pack2(a0.x, a0.y), pack2(a0.z, a0.w), pack2(a1.x, a1.y), npx, npy, npz), sc2);
+      const f32x2 db = mul2(sqdist2(pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), npx, npy, npz), sc2);
+      float e0, e1, e2, e3;
+      unpack2(da, e0, e1);
+      unpack2(db, e2, e3);
+      acc = fma2(pack2(ex2_ftz(e0), ex2_ftz(e1)), pack2(a1.z, a1.w), acc);
+      acc_b = fma2(pack2(ex2_ftz(e2), ex2_ftz(e3)), pack2(b1.z, b1.w), acc_b);
+    }
+  }
+  if (p >= nP) return;
+  float s0, s1, s2, s3;
+  unpack2(acc, s0, s1);
+  unpack2(acc_b, s2, s3);
+  const float S = (s0 + s1) + (s2 + s3);
+  float *rem = remainP + cloud * remain_stride;
+  float *rat = ratioP + cloud * ratio_stride;
+  if (EPI == EPI_RATIO_L) {  // approxmatch.cu:37,58-61: suml = 1e-9f + sum ; ratioL = remainL / suml
+    rat[p] = rem[p] / (1e-9f + S);
+  } else if (EPI == EPI_RATIO_R) {  // approxmatch.cu:104-109
+    const float r = rem[p];
+    const float sumr = S * r;
+    const float consumption = fminf(r / (sumr + 1e-9f), 1.0f);
+    rat[p] = consumption * r;
+    rem[p] = fmaxf(0.0f, r - sumr);
+  } else {  // approxmatch.cu:150-162: suml = sum_l E*ratioL[k]*ratioR[l] ; remainL = max(0, remainL - suml)
+    const float suml = (ratioP_in + cloud * ratio_stride)[p] * S;
+    rem[p] = fmaxf(0.0f, rem[p] - suml);
+  }
+}
+
+// ---- phase B -------------------------------------------------------------------------------------------------
+// match(p,q) = sum_t E_t(p,q) * a_t[p] * b_t[q],  t = 0..8  <->  j = 7..-1,  E_t = exp2(c_t * d2)
+struct AmScales {
+  float c[AM_LEVELS];
+};
+
+constexpr int AMF_QTILE = 256;                      // partner points per tile in the phase-B kernels
+constexpr int AMF_F4_PER_PAIR = (3 + AM_LEVELS) / 2;  // 6 float4 per partner pair: 3 coords + 9 factors, 2 lanes each
+
+// evaluates the 9 level terms for two partner points at once (packed lanes = partners)
+__device__ __forceinline__ f32x2 am_match_pair(f32x2 d2, const f32x2 *bq /*9*/, const float *ap /*9*/,
+                                               const AmScales &sc) {
+  // anchors j = 7, 5, 3, 1, -1 (t = 0, 2, 4, 6, 8) by MUFU; j+1 from j by E^4 (t-1 from t)
+  float lo, hi;
+  f32x2 E[AM_LEVELS];
+#pragma unroll
+  for (int t = 0; t < AM_LEVELS; t += 2) {
+    const f32x2 a = mul2(d2, pack2(sc.c[t], sc.c[t]));
+    unpack2(a, lo, hi);
+    E[t] = pack2(ex2_ftz(lo), ex2_ftz(hi));
+  }
+#pragma unroll
+  for (int t = 2; t < AM_LEVELS; t += 2) {
+    const f32x2 s = mul2(E[t], E[t]);
+    E[t - 1] = mul2(s, s);
+  }
+  f32x2 mt = 0ull;
+#pragma unroll
+  for (int t = 0; t < AM_LEVELS; ++t)  // same level order as the reference's `match += w` sequence
+    mt = fma2(mul2(E[t], pack2(ap[t], ap[t])), bq[t], mt);
+  return mt;
+}
+
+// Loads partner points [base, base+cnt) with their 9 factors into the pair-packed tile.
+__device__ __forceinline__ void amf_fill_tile(float *tf, const float *__restrict__ xQ, const float *__restrict__ fQ,
+                                              size_t f_level_stride, int base, int cnt, int cnt2) {
+  for (int i = threadIdx.x; i < cnt2; i += AM_THREADS) {
+    float v[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) v[e] = 0.f;
+    if (i < cnt) {
+      const float *q = xQ + (size_t)(base + i) * 3;
+      v[0] = q[0];
+      v[1] = q[1];
+      v[2] = q[2];
+#pragma unroll
+      for (int t = 0; t < AM_LEVELS; ++t) v[3 + t] = fQ[(size_t)t * f_level_stride + base + i];
+    }
+    float *o = tf + (size_t)(i >> 1) * (AMF_F4_PER_PAIR * 4) + (i & 1);
+#pragma unroll
+    for (int e = 0; e < 12; ++e) o[e * 2] = v[e];
+  }
+}
+
+// MATERIALISE: thread = cloud-1 point k (coalesced along n), blockIdx.y = slab of cloud-2 points.
+__global__ void __launch_bounds__(AM_THREADS)
+am_materialize_kernel(int n, int m, int lslab, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                      const float *__restrict__ fL, const float *__restrict__ fR, size_t fL_level_stride,
+                      size_t fR_level_stride, AmScales sc, float *__restrict__ match) {
+  __shared__ float4 tile[AMF_QTILE / 2 * AMF_F4_PER_PAIR];
+  const size_t cloud = blockIdx.z;
+  xyz1 += cloud * (size_t)n * 3;
+  xyz2 += cloud * (size_t)m * 3;
+  fL += cloud * (size_t)n;
+  fR += cloud * (size_t)m;
+  match += cloud * (size_t)n * m;
+  const int k = blockIdx.x * AM_THREADS + threadIdx.x;
+  const int kc = min(k, n - 1);
+  const float px = xyz1[kc * 3], py = xyz1[kc * 3 + 1], pz = xyz1[kc * 3 + 2];
+  const f32x2 npx = pack2(-px, -px), npy = pack2(-py, -py), npz = pack2(-pz, -pz);
+  float ap[AM_LEVELS];
+#pragma unroll
+  for (int t = 0; t < AM_LEVELS; ++t) ap[t] = fL[(size_t)t * fL_level_stride + kc];
+  const int l_begin = blockIdx.y * lslab, l_end = min(m, l_begin + lslab);
+  for (int base = l_begin; base < l_end; base += AMF_QTILE) {
+    const int cnt = min(AMF_QTILE, l_end - base), cnt2 = (cnt + 1) & ~1;
+    __syncthreads();
+    amf_fill_tile(reinterpret_cast<float *>(tile), xyz2, fR, fR_level_stride, base, cnt, cnt2);
+    __syncthreads();
+    for (int pr = 0; pr < (cnt2 >> 1); ++pr) {
+      const float4 *T = tile + pr * AMF_F4_PER_PAIR;
+      const float4 c0 = T[0], c1 = T[1], c2 = T[2], c3 = T[3], c4 = T[4], c5 = T[5];
+      const f32x2 bq[AM_LEVELS] = {pack2(c1.z, c1.w), pack2(c2.x, c2.y), pack2(c2.z, c2.w),
+                                   pack2(c3.x, c3.y), pack2(c3.z, c3.w), pack2(c4.x, c4.y),
+                                   pack2(c4.z, c4.w), pack2(c5.x, c5.y), pack2(c5.z, c5.w)};
+      const f32x2 d2 = sqdist2(pack2(c0.x, c0.y), pack2(c0.z, c0.w), pack2(c1.x, c1.y), npx, npy, npz);
+      float m0, m1;
+      unpack2(am_match_pair(d2, bq, ap, sc), m0, m1);
+      const int l = base + pr * 2;
+      if (k < n) {
+        match[(size_t)l * n + k] = m0;
+        if (l + 1 < l_end) match[(size_t)(l + 1) * n + k] = m1;
+      }
+    }
+  }
+}
+
+// COST + GRADIENT of the point set P against Q without materialising match:
+//   cost_part[cloud][blockIdx.x] = sum_{p in block} sum_q match * |x_p - x_q|           (approxmatch.cu:184-224)
+//   gradP[p] = sum_q match * (x_p - x_q) * rsqrt(max(|x_p - x_q|^2, 1e-20))              (approxmatch.cu:229-291)
+__global__ void __launch_bounds__(AM_THREADS)
+am_costgrad_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
+                   const float *__restrict__ fP, const float *__restrict__ fQ, size_t fP_level_stride,
+                   size_t fQ_level_stride, AmScales sc, float *__restrict__ cost_part, float *__restrict__ gradP) {
+  __shared__ float4 tile[AMF_QTILE / 2 * AMF_F4_PER_PAIR];
+  __shared__ float red[AM_THREADS / 32];
+  const size_t cloud = blockIdx.y;
+  xP += cloud * (size_t)nP * 3;
+  xQ += cloud * (size_t)nQ * 3;
+  fP += cloud * (size_t)nP;
+  fQ += cloud * (size_t)nQ;
+  const int p = blockIdx.x * AM_THREADS + threadIdx.x;
+  const int pc = min(p, nP - 1);
+  const float px = xP[pc * 3], py = xP[pc * 3 + 1], pz = xP[pc * 3 + 2];
+  const f32x2 npx = pack2(-px, -px), npy = pack2(-py, -py), npz = pack2(-pz, -pz);
+  float ap[AM_LEVELS];
+#pragma unroll
+  for (int t = 0; t < AM_LEVELS; ++t) ap[t] = fP[(size_t)t * fP_level_stride + pc];
+  f32x2 cst = 0ull, gx = 0ull, gy = 0ull, gz = 0ull;
+  const f32x2 tiny = pack2(1e-20f, 1e-20f);
+  (void)tiny;
+  for (int base = 0; base < nQ; base += AMF_QTILE) {
+    const int cnt = min(AMF_QTILE, nQ - base), cnt2 = (cnt + 1) & ~1;
+    __syncthreads();
+    amf_fill_tile(reinterpret_cast<float *>(tile), xQ, fQ, fQ_level_stride, base, cnt, cnt2);
+    __syncthreads();
+    for (int pr = 0; pr < (cnt2 >> 1); ++pr) {
+      const float4 *T = tile + pr * AMF_F4_PER_PAIR;
+      const float4 c0 = T[0], c1 = T[1], c2 = T[2], c3 = T[3], c4 = T[4], c5 = T[5];
+      const f32x2 bq[AM_LEVELS] = {pack2(c1.z, c1.w), pack2(c2.x, c2.y), pack2(c2.z, c2.w),
+                                   pack2(c3.x, c3.y), pack2(c3.z, c3.w), pack2(c4.x, c4.y),
+                                   pack2(c4.z, c4.w), pack2(c5.x, c5.y), pack2(c5.z, c5.w)};
+      // dq = x_q - x_p (packed over the two partners); gradient uses x_p - x_q = -dq
+      const f32x2 dx = add2(pack2(c0.x, c0.y), npx), dy = add2(pack2(c0.z, c0.w), npy),
+                  dz = add2(pack2(c1.x, c1.y), npz);
+      const f32x2 d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+      const f32x2 mt = am_match_pair(d2, bq, ap, sc);
+      float d0, d1;
+      unpack2(d2, d0, d1);
+      const f32x2 rinv = pack2(rsqrt_ftz(fmaxf(d0, 1e-20f)), rsqrt_ftz(fmaxf(d1, 1e-20f)));
+      const f32x2 u = mul2(mt, rinv);       // match / dist
+      cst = fma2(u, d2, cst);               // match * dist   (dist = d2 * rsqrt(d2))
+      gx = fma2(u, dx, gx);                 // accumulates match * (x_q - x_p) / dist ; negated at the end
+      gy = fma2(u, dy, gy);
+      gz = fma2(u, dz, gz);
+    }
+  }
+  float c0, c1, x0, x1, y0, y1, z0, z1;
+  unpack2(cst, c0, c1);
+  unpack2(gx, x0, x1);
+  unpack2(gy, y0, y1);
+  unpack2(gz, z0, z1);
+  if (p < nP && gradP) {
+    float *g = gradP + (cloud * (size_t)nP + p) * 3;
+    g[0] = -(x0 + x1);
+    g[1] = -(y0 + y1);
+    g[2] = -(z0 + z1);
+  }
+  if (cost_part) {
+    float c = (p < nP) ? (c0 + c1) : 0.f;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < AM_THREADS / 32; ++w) s += red[w];
+      cost_part[cloud * gridDim.x + blockIdx.x] = s;
+    }
+  }
+}
+
+__global__ void am_cost_reduce_kernel(int b, int parts, const float *__restrict__ cost_part, float *__restrict__ cost) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  float s = 0.f;
+  for (int p = 0; p < parts; ++p) s += cost_part[(size_t)i * parts + p];  // fixed order: deterministic
+  cost[i] = s;
+}
+
+__global__ void am_export_temp_kernel(int n, int m, const float *__restrict__ fL_last, const float *__restrict__ fR_last,
+                                      float *__restrict__ temp) {
+  // temp's ratioL / ratioR slots receive the last level's vectors, as the reference leaves them (approxmatch.cu:4)
+  float *t = temp + (size_t)blockIdx.y * (size_t)(n + m) * 2 + (n + m);
+  const float *l = fL_last + (size_t)blockIdx.y * n, *r = fR_last + (size_t)blockIdx.y * m;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x)
+    t[i] = i < n ? l[i] : r[i - n];
+}
+
+// ---- match cost / gradient from a materialised match matrix (API parity with MatchCost / MatchCostGrad) --------
+constexpr int MC_THREADS = 256;
+constexpr int MC_ROWS = 16;  // cloud-2 rows per CTA
+
+// partial[cloud][blockIdx.x] = sum over rows l of this CTA, all k:  match[l][k] * sqrt(d2)
+__global__ void __launch_bounds__(MC_THREADS)
+matchcost_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                 const float *__restrict__ match, float *__restrict__ partial) {
+  __shared__ float red[MC_THREADS / 32];
+  const size_t cloud = blockIdx.y;
+  xyz1 += cloud * (size_t)n * 3;
+  xyz2 += cloud * (size_t)m * 3;
+  match += cloud * (size_t)n * m;
+  const int l0 = blockIdx.x * MC_ROWS, l1 = min(m, l0 + MC_ROWS);
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < n; k += MC_THREADS) {
+    const float x = xyz1[k * 3], y = xyz1[k * 3 + 1], z = xyz1[k * 3 + 2];
+    for (int l = l0; l < l1; ++l) {
+      const float d = sqdist1(x, y, z, xyz2[l * 3], xyz2[l * 3 + 1], xyz2[l * 3 + 2]);
+      acc = fmaf(match[(size_t)l * n + k], sqrtf(d), acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < MC_THREADS / 32; ++w) s += red[w];
+    partial[cloud * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// grad1[k] = sum_l match[l][k] (x1_k - x2_l) rsqrt(max(d2,1e-20)) : thread per k, rows streamed (coalesced over k)
+__global__ void __launch_bounds__(MC_THREADS)
+matchcostgrad1_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                      const float *__restrict__ match, float *__restrict__ grad1) {
+  __shared__ float4 xs[256];
+  const size_t cloud = blockIdx.y;
+  xyz1 += cloud * (size_t)n * 3;
+  xyz2 += cloud * (size_t)m * 3;
+  match += cloud * (size_t)n * m;
+  const int k = blockIdx.x * MC_THREADS + threadIdx.x;
+  const int kc = min(k, n - 1);
+  const float x = xyz1[kc * 3], y = xyz1[kc * 3 + 1], z = xyz1[kc * 3 + 2];
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  for (int base = 0; base < m; base += 256) {
+    const int cnt = min(256, m - base);
+    __syncthreads();
+    if ((int)threadIdx.x < cnt) {
+      const float *q = xyz2 + (size_t)(base + threadIdx.x) * 3;
+      xs[threadIdx.x] = make_float4(q[0], q[1], q[2], 0.f);
+    }
+    __syncthreads();
+    if (k < n) {
+#pragma unroll 4
+      for (int l = 0; l < cnt; ++l) {
+        const float4 q = xs[l];
+        const float dx = x - q.x, dy = y - q.y, dz = z - q.z;
+        const float d = match[(size_t)(base + l) * n + k] * rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-20f));
+        gx = fmaf(dx, d, gx);
+        gy = fmaf(dy, d, gy);
+        gz = fmaf(dz, d, gz);
+      }
+    }
+  }
+  if (k < n) {
+    float *g = grad1 + (cloud * (size_t)n + k) * 3;
+    g[0] = gx;
+    g[1] = gy;
+    g[2] = gz;
+  }
+}
+
+// grad2[l] = sum_k match[l][k] (x2_l - x1_k) rsqrt(.) : one warp per row l (coalesced over k), ordered shuffle reduce
+__global__ void __launch_bounds__(MC_THREADS)
+matchcostgrad2_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                      const float *__restrict__ match, float *__restrict__ grad2) {
+  const size_t cloud = blockIdx.y;
+  xyz1 += cloud * (size_t)n * 3;
+  xyz2 += cloud * (size_t)m * 3;
+  match += cloud * (size_t)n * m;
+  const int lane = threadIdx.x & 31;
+  const int l = blockIdx.x * (MC_THREADS / 32) + (threadIdx.x >> 5);
+  if (l >= m) return;
+  const float x = xyz2[l * 3], y = xyz2[l * 3 + 1], z = xyz2[l * 3 + 2];
+  const float *row = match + (size_t)l * n;
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  for (int k = lane; k < n; k += 32) {
+    const float dx = x - xyz1[k * 3], dy = y - xyz1[k * 3 + 1], dz = z - xyz1[k * 3 + 2];
+    const float d = row[k] * rsqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1e-20f));
+    gx = fmaf(dx, d, gx);
+    gy = fmaf(dy, d, gy);
+    gz = fmaf(dz, d, gz);
+  }
+  gx = warp_sum(gx);
+  gy = warp_sum(gy);
+  gz = warp_sum(gz);
+  if (lane == 0) {
+    float *g = grad2 + (cloud * (size_t)m + l) * 3;
+    g[0] = gx;
+    g[1] = gy;
+    g[2] = gz;
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+struct AmWorkspace {
+  float *base = nullptr;
+  float *fL = nullptr;  // [9][b][n]
+  float *fR = nullptr;  // [9][b][m]
+  float *cost_part = nullptr;
+  size_t fL_level_stride = 0, fR_level_stride = 0;
+};
+
+static AmScales am_scales() {
+  AmScales s;
+  for (int t = 0; t < AM_LEVELS; ++t) {
+    const int j = 7 - t;
+    const float level = -powf(4.0f, (float)j);  // approxmatch.cu:25
+    s.c[t] = level * AM_LOG2E;
+  }
+  return s;
+}
+
+// Phase A: runs the 27 sweeps; leaves remainL/remainR in temp and the per-level factors in ws.  Returns #launches.
+static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, float *temp, AmWorkspace &ws,
+                    size_t extra_floats, cudaStream_t st, int *launches) {
+  const size_t nfl = (size_t)AM_LEVELS * b * n, nfr = (size_t)AM_LEVELS * b * m;
+  cudaError_t e = cudaMallocAsync((void **)&ws.base, sizeof(float) * (nfl + nfr + extra_floats), st);
+  if (e != cudaSuccess) return (int)e;
+  ws.fL = ws.base;
+  ws.fR = ws.base + nfl;
+  ws.cost_part = ws.base + nfl + nfr;
+  ws.fL_level_stride = (size_t)b * n;
+  ws.fR_level_stride = (size_t)b * m;
+  float multiL, multiR;  // approxmatch.cu:6-12 (integer division)
+  if (n >= m) {
+    multiL = 1.f;
+    multiR = (float)(n / m);
+  } else {
+    multiL = (float)(m / n);
+    multiR = 1.f;
+  }
+  const AmScales sc = am_scales();
+  const size_t tstride = (size_t)(n + m) * 2;
+  float *remainL = temp, *remainR = temp + n;
+  am_init_kernel<<<dim3((n + m + 255) / 256, b), 256, 0, st>>>(n, m, temp, multiL, multiR);
+  const dim3 gk((n + AM_THREADS - 1) / AM_THREADS, b), gl((m + AM_THREADS - 1) / AM_THREADS, b);
+  for (int t = 0; t < AM_LEVELS; ++t) {
+    float *fLt = ws.fL + (size_t)t * ws.fL_level_stride, *fRt = ws.fR + (size_t)t * ws.fR_level_stride;
+    am_rowsum_kernel<EPI_RATIO_L><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, remainR, tstride, sc.c[t], remainL,
+                                                             tstride, fLt, (size_t)n, nullptr);
+    am_rowsum_kernel<EPI_RATIO_R><<<gl, AM_THREADS, 0, st>>>(m, n, xyz2, xyz1, fLt, (size_t)n, sc.c[t], remainR,
+                                                             tstride, fRt, (size_t)m, nullptr);
+    am_rowsum_kernel<EPI_REMAIN_L><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, fRt, (size_t)m, sc.c[t], remainL,
+                                                              tstride, fLt, (size_t)n, fLt);
+  }
+  am_export_temp_kernel<<<dim3((n + m + 255) / 256, b), 256, 0, st>>>(
+      n, m, ws.fL + (size_t)(AM_LEVELS - 1) * ws.fL_level_stride, ws.fR + (size_t)(AM_LEVELS - 1) * ws.fR_level_stride,
+      temp);
+  *launches += 2 + 3 * AM_LEVELS;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" __attribute__((visibility("default"))) int pcc_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp,
+                               pcc_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCC_EINVAL;
+  if (b == 0 || n == 0 || m == 0) return PCC_OK;
+  if (b > 65535) return PCC_ENOTSUP;
+  cudaStream_t st = (cudaStream_t)stream;
+  AmWorkspace ws;
+  int launches = 0;
+  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, 0, st, &launches);
+  if (rc == 0) {
+    const int lslab = 256;
+    dim3 grid((n + AM_THREADS - 1) / AM_THREADS, (m + lslab - 1) / lslab, b);
+    am_materialize_kernel<<<grid, AM_THREADS, 0, st>>>(n, m, lslab, xyz1, xyz2, ws.fL, ws.fR, ws.fL_level_stride,
+                                                       ws.fR_level_stride, am_scales(), match);
+    ++launches;
+    rc = (int)cudaGetLastError();
+  }
+  if (ws.base) cudaFreeAsync(ws.base, st);
+  g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
+  return rc;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_matchcost_fused(int b, int n, int m, const float *xyz1, const float *xyz2, float *cost,
+                                   float *grad1, float *grad2, float *temp, pcc_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCC_EINVAL;
+  if (b == 0) return PCC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0 || m == 0) {
+    if (cost) cudaMemsetAsync(cost, 0, sizeof(float) * b, st);
+    if (grad1 && n) cudaMemsetAsync(grad1, 0, sizeof(float) * (size_t)b * n * 3, st);
+    if (grad2 && m) cudaMemsetAsync(grad2, 0, sizeof(float) * (size_t)b * m * 3, st);
+    return (int)cudaGetLastError();
+  }
+  if (b > 65535) return PCC_ENOTSUP;
+  AmWorkspace ws;
+  int launches = 0;
+  const int parts = (n + AM_THREADS - 1) / AM_THREADS;
+  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, (size_t)b * parts, st, &launches);
+  if (rc == 0) {
+    const AmScales sc = am_scales();
+    am_costgrad_kernel<<<dim3(parts, b), AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, ws.fL, ws.fR, ws.fL_level_stride,
+                                                              ws.fR_level_stride, sc, cost ? ws.cost_part : nullptr,
+                                                              grad1);
+    ++launches;
+    if (cost) {
+      am_cost_reduce_kernel<<<(b + 127) / 128, 128, 0, st>>>(b, parts, ws.cost_part, cost);
+      ++launches;
+    }
+    if (grad2) {
+      am_costgrad_kernel<<<dim3((m + AM_THREADS - 1) / AM_THREADS, b), AM_THREADS, 0, st>>>(
+          m, n, xyz2, xyz1, ws.fR, ws.fL, ws.fR_level_stride, ws.fL_level_stride, sc, nullptr, grad2);
+      ++launches;
+    }
+    rc = (int)cudaGetLastError();
+  }
+  if (ws.base) cudaFreeAsync(ws.base, st);
+  g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
+  return rc;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match,
+                             float *out, pcc_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCC_EINVAL;
+  if (b == 0) return PCC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0 || m == 0) {
+    cudaMemsetAsync(out, 0, sizeof(float) * b, st);
+    return (int)cudaGetLastError();
+  }
+  if (b > 65535) return PCC_ENOTSUP;
+  const int parts = (m + MC_ROWS - 1) / MC_ROWS;
+  float *partial = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&partial, sizeof(float) * (size_t)b * parts, st);
+  if (e != cudaSuccess) return (int)e;
+  matchcost_kernel<<<dim3(parts, b), MC_THREADS, 0, st>>>(n, m, xyz1, xyz2, match, partial);
+  am_cost_reduce_kernel<<<(b + 127) / 128, 128, 0, st>>>(b, parts, partial, out);
+  cudaFreeAsync(partial, st);
+  return finish_launch(2);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match,
+                                 float *grad1, float *grad2, pcc_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCC_EINVAL;
+  if (b == 0) return PCC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0 || m == 0) {
+    if (n) cudaMemsetAsync(grad1, 0, sizeof(float) * (size_t)b * n * 3, st);
+    if (m) cudaMemsetAsync(grad2, 0, sizeof(float) * (size_t)b * m * 3, st);
+    return (int)cudaGetLastError();
+  }
+  if (b > 65535) return PCC_ENOTSUP;
+  matchcostgrad1_kernel<<<dim3((n + MC_THREADS - 1) / MC_THREADS, b), MC_THREADS, 0, st>>>(n, m, xyz1, xyz2, match,
+                                                                                          grad1);
+  matchcostgrad2_kernel<<<dim3((m + MC_THREADS / 32 - 1) / (MC_THREADS / 32), b), MC_THREADS, 0, st>>>(n, m, xyz1, xyz2,
+                                                                                                        match, grad2);
+  return finish_launch(2);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_approxmatch_sweep(int b, int n, int m, const float *xyz1,
+                                                                            const float *xyz2, const float *weight,
+                                                                            const float *remain, float *ratio,
+                                                                            float level, pcc_stream_t stream) {
+  if (b <= 0 || n <= 0 || m <= 0) return PCC_EINVAL;
+  if (b > 65535) return PCC_ENOTSUP;
+  am_rowsum_kernel<EPI_RATIO_L><<<dim3((n + AM_THREADS - 1) / AM_THREADS, b), AM_THREADS, 0, (cudaStream_t)stream>>>(
+      n, m, xyz1, xyz2, weight, (size_t)m, level * AM_LOG2E, const_cast<float *>(remain), (size_t)n, ratio, (size_t)n,
+      nullptr);
+  return finish_launch(1);
+}

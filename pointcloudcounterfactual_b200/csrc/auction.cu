@@ -1,0 +1,245 @@
+// Auction-algorithm EMD for sm_100a: one persistent CTA per cloud runs all rounds.
+//
+// Replaces external/emd/src/emd_cuda.cu: the reference launches 7 kernels per round (clear, calc_unass_cnt,
+// calc_unass_cnt_sum, calc_unass_idx, Bid, GetMax, Assign; :255-268) on the default stream, i.e. 350 launches for the
+// recommended 50 training rounds and 70 000 for the 10 000 test rounds.  Here every cloud is owned by one
+// 1024-thread CTA that keeps the target coordinates and prices in shared memory and loops over the rounds with
+// __syncthreads() in between -- one launch in total, on the caller's stream.
+//
+// Semantics follow emd_cuda.cu:94-225 round for round (synchronous bids on start-of-round prices, one winner per
+// target, forced assignment on the last round).  Where the reference is racy the result here is deterministic:
+// among bids within 1e-6 of the maximum the HIGHEST source index wins (reference: last writer, :187-190); the
+// compacted list of unassigned sources is in ascending order (reference: atomic order, :84-92).
+#include "common.cuh"
+
+namespace pcc {
+
+constexpr int AU_THREADS = 1024;
+
+// order-independent merge of (best value, lowest index attaining it, second-best value of the multiset)
+struct Bid3 {
+  float best, better;
+  int idx;
+};
+__device__ __forceinline__ Bid3 bid_merge(Bid3 a, Bid3 b) {
+  Bid3 r;
+  const bool a_wins = (a.best > b.best) || (a.best == b.best && (unsigned)a.idx < (unsigned)b.idx);
+  r.best = a_wins ? a.best : b.best;
+  r.idx = a_wins ? a.idx : b.idx;
+  r.better = fmaxf(fminf(a.best, b.best), fmaxf(a.better, b.better));
+  return r;
+}
+
+__global__ void __launch_bounds__(AU_THREADS, 1)
+auction_kernel(int n, const float *__restrict__ xyz1, const float *__restrict__ xyz2, float *__restrict__ dist,
+               int *__restrict__ assignment, float *__restrict__ price_g, int *__restrict__ assignment_inv,
+               int *__restrict__ bid, float *__restrict__ bid_inc, float *__restrict__ max_inc_g,
+               int *__restrict__ unass_idx, int *__restrict__ max_idx, float eps, int iters) {
+  extern __shared__ float sm[];
+  float *sx = sm, *sy = sm + n, *sz = sm + 2 * n;  // target coordinates, SoA
+  float *price = sm + 3 * n;
+  int *max_inc = reinterpret_cast<int *>(sm + 4 * n);  // float bits; bids are positive so signed-int max == float max
+  __shared__ int warp_cnt[AU_THREADS / 32];
+  __shared__ int n_unass;
+
+  const size_t cloud = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  xyz1 += cloud * (size_t)n * 3;
+  xyz2 += cloud * (size_t)n * 3;
+  int *asg = assignment + cloud * (size_t)n, *inv = assignment_inv + cloud * (size_t)n;
+  int *bd = bid + cloud * (size_t)n, *ulist = unass_idx + cloud * (size_t)n, *mxi = max_idx + cloud * (size_t)n;
+  float *binc = bid_inc + cloud * (size_t)n;
+
+  for (int k = tid; k < n; k += AU_THREADS) {
+    sx[k] = xyz2[k * 3];
+    sy[k] = xyz2[k * 3 + 1];
+    sz[k] = xyz2[k * 3 + 2];
+    price[k] = price_g[cloud * (size_t)n + k];
+    max_inc[k] = __float_as_int(max_inc_g[cloud * (size_t)n + k]);
+  }
+  __syncthreads();
+
+  const int per_thread = n / AU_THREADS;  // n is a multiple of 1024 (checked on the host, emd_cuda.cu:245-248)
+  for (int it = 0; it < iters; ++it) {
+    const bool last = (it == iters - 1);
+    // ---- ordered compaction of the unassigned sources (emd_cuda.cu:29-92) ---------------------------------
+    // thread t owns sources [t*per_thread, (t+1)*per_thread): ascending order is preserved
+    int mine = 0;
+    for (int e = 0; e < per_thread; ++e) mine += (asg[tid * per_thread + e] == -1);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_cnt[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_cnt[lane], s = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += u;
+      }
+      warp_cnt[lane] = s - t;
+      if (lane == 31) n_unass = s;
+    }
+    __syncthreads();
+    int pos = warp_cnt[warp] + incl - mine;
+    for (int e = 0; e < per_thread; ++e) {
+      const int j = tid * per_thread + e;
+      if (asg[j] == -1) ulist[pos++] = j;
+    }
+    __syncthreads();
+    const int U = n_unass;
+    if (U == 0) break;  // uniform: nothing left to assign, later rounds are no-ops (emd_cuda.cu:103-104)
+
+    // ---- Bid (emd_cuda.cu:94-178): `tpb` lanes cooperate on one bidder, strided over the targets -----------
+    int tpb = 1;
+    while (tpb < 32 && U * tpb * 2 <= AU_THREADS) tpb <<= 1;
+    const int bidders_per_pass = AU_THREADS / tpb;
+    for (int u0 = 0; u0 < U; u0 += bidders_per_pass) {
+      const int u = u0 + tid / tpb;
+      const int sub = tid % tpb;
+      Bid3 r;
+      r.best = -1e9f;
+      r.better = -1e9f;
+      r.idx = -1;
+      int i = -1;
+      if (u < U) {
+        i = ulist[u];
+        const float x1 = xyz1[i * 3], y1 = xyz1[i * 3 + 1], z1 = xyz1[i * 3 + 2];
+        for (int k = sub; k < n; k += tpb) {
+          const float x2 = sx[k] - x1, y2 = sy[k] - y1, z2 = sz[k] - z1;
+          const float s = __fmaf_rn(z2, z2, __fmaf_rn(x2, x2, __fmul_rn(y2, y2)));
+          // `3.0 - sqrtf(.) - price` with a double literal is evaluated in double by the reference (:145)
+          const float d = (float)(3.0 - (double)sqrtf(s) - (double)price[k]);
+          if (d > r.best) {
+            r.better = r.best;
+            r.best = d;
+            r.idx = k;
+          } else if (d > r.better) {
+            r.better = d;
+          }
+        }
+      }
+      for (int o = 1; o < tpb; o <<= 1) {  // groups are aligned sub-warps
+        Bid3 q;
+        q.best = __shfl_xor_sync(0xffffffffu, r.best, o);
+        q.better = __shfl_xor_sync(0xffffffffu, r.better, o);
+        q.idx = __shfl_xor_sync(0xffffffffu, r.idx, o);
+        r = bid_merge(r, q);
+      }
+      if (u < U && sub == 0) {
+        const float inc = r.best - r.better + eps;
+        bd[i] = r.idx;
+        binc[i] = inc;
+        atomicMax(&max_inc[r.idx], __float_as_int(inc));  // emd_cuda.cu:9-19,175
+      }
+    }
+    __syncthreads();
+    // ---- GetMax (emd_cuda.cu:180-193): winner = highest source index among the bids within 1e-6 of the
+    //      maximum; on the forced last round every bidder takes part -----------------------------------------
+    for (int u = tid; u < U; u += AU_THREADS) {
+      const int i = ulist[u], t = bd[i];
+      const double bi = (double)binc[i], mi = (double)__int_as_float(max_inc[t]);
+      if (last || (bi - 1e-6 <= mi && mi <= bi + 1e-6)) mxi[t] = -1;  // drop the stale winner of earlier rounds
+    }
+    __syncthreads();
+    for (int u = tid; u < U; u += AU_THREADS) {
+      const int i = ulist[u], t = bd[i];
+      const double bi = (double)binc[i], mi = (double)__int_as_float(max_inc[t]);
+      if (last || (bi - 1e-6 <= mi && mi <= bi + 1e-6)) atomicMax(&mxi[t], i);
+    }
+    __syncthreads();
+    // ---- Assign (emd_cuda.cu:195-214) ---------------------------------------------------------------------
+    for (int u = tid; u < U; u += AU_THREADS) {
+      const int i = ulist[u], t = bd[i];
+      if (last || mxi[t] == i) {
+        const float inc = binc[i];
+        if (!last) {
+          const int prev = inv[t];
+          if (prev != -1) asg[prev] = -1;
+          inv[t] = i;
+          price[t] += inc;
+        } else {  // several sources may be forced onto one target (:200): all keep it, the highest owns inv
+          if (mxi[t] == i) inv[t] = i;
+          atomicAdd(&price[t], inc);
+        }
+        asg[i] = t;
+        max_inc[t] = __float_as_int(-1e9f);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- CalcDist (emd_cuda.cu:216-225) + state write-back -------------------------------------------------------
+  for (int j = tid; j < n; j += AU_THREADS) {
+    const int k = asg[j];
+    float d = 0.f;
+    if (k >= 0) {
+      const float dx = xyz1[j * 3] - sx[k], dy = xyz1[j * 3 + 1] - sy[k], dz = xyz1[j * 3 + 2] - sz[k];
+      d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    }
+    dist[cloud * (size_t)n + j] = d;
+    price_g[cloud * (size_t)n + j] = price[j];
+    max_inc_g[cloud * (size_t)n + j] = __int_as_float(max_inc[j]);
+  }
+}
+
+__global__ void auction_grad_kernel(size_t total, int n, const float *__restrict__ xyz1,
+                                    const float *__restrict__ xyz2, const float *__restrict__ gdist,
+                                    const int *__restrict__ idx, float *__restrict__ grad) {
+  // emd_cuda.cu:283-299: grad1 = 2 g (x1 - x2[assignment])   (grad2 stays zero, emd_module.py:75-79)
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = t / n;
+    const int k = min(max(idx[t], 0), n - 1);
+    const float g = gdist[t] * 2.f;
+    const float *p = xyz1 + t * 3, *q = xyz2 + (i * n + k) * 3;
+    grad[t * 3] = g * (p[0] - q[0]);
+    grad[t * 3 + 1] = g * (p[1] - q[1]);
+    grad[t * 3 + 2] = g * (p[2] - q[2]);
+  }
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" __attribute__((visibility("default"))) int pcc_emd_forward(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist,
+                               int *assignment, float *price, int *assignment_inv, int *bid, float *bid_increments,
+                               float *max_increments, int *unass_idx, int *unass_cnt, int *unass_cnt_sum,
+                               int *cnt_tmp, int *max_idx, float eps, int iters, pcc_stream_t stream) {
+  (void)unass_cnt;  // the three 512-int counters of the reference API are not needed by the persistent kernel
+  (void)unass_cnt_sum;
+  (void)cnt_tmp;
+  if (n != m) return -1;          // emd_cuda.cu:235-238
+  if (b > 512) return -1;         // :240-243
+  if (n % 1024 != 0) return -1;   // :245-248
+  if (b <= 0 || n == 0) return 1;
+  const size_t smem = sizeof(float) * 5 * (size_t)n;
+  if (smem > 220 * 1024) return PCC_ENOTSUP;  // n <= 11264
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  auction_kernel<<<b, AU_THREADS, smem, (cudaStream_t)stream>>>(n, xyz1, xyz2, dist, assignment, price,
+                                                                 assignment_inv, bid, bid_increments, max_increments,
+                                                                 unass_idx, max_idx, eps, iters);
+  const int rc = finish_launch(1);
+  return rc == 0 ? 1 : rc;
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_emd_backward(int b, int n, const float *xyz1, const float *xyz2, float *gradxyz,
+                                const float *graddist, const int *idx, pcc_stream_t stream) {
+  if (b <= 0 || n <= 0) return 1;
+  const size_t total = (size_t)b * n;
+  const int threads = 256;
+  size_t blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  auction_grad_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(total, n, xyz1, xyz2, graddist, idx, gradxyz);
+  const int rc = finish_launch(1);
+  return rc == 0 ? 1 : rc;
+}

@@ -1,0 +1,364 @@
+// Chamfer nearest-neighbour distance, forward and backward, for sm_100a.
+//
+// Replaces external/pytorch_structural_losses/src/nndistance.cu (NmDistanceKernel :2-124 launched twice,
+// NmDistanceGradKernel :129-148 launched twice + 2 memsets) with
+//   * ONE forward launch covering both directions.  Reference points are staged in shared memory as groups of
+//     four (float4 X, Y, Z), distances are evaluated two at a time with packed FADD2/FMUL2/FFMA2 in the
+//     reference's rounding order, running minima use 3-input FMNMX, and the argmin is tracked per group of 8
+//     reference points and resolved exactly at the end (lowest index wins ties, like the reference's strict '<').
+//   * ONE deterministic backward launch (CTA per cloud and direction, counting sort of the nearest-neighbour
+//     lists in shared memory, ordered segmented sums) instead of float atomics.
+#include "common.cuh"
+
+namespace pcc {
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+constexpr int NN_THREADS = 128;
+constexpr int NN_TILE = 2048;  // reference points per shared-memory tile (24 KiB)
+
+template <int Q>
+__global__ void __launch_bounds__(NN_THREADS)
+nn_fwd_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2,
+              float *__restrict__ dist1, int *__restrict__ idx1, float *__restrict__ dist2,
+              int *__restrict__ idx2) {
+  __shared__ float4 tile[NN_TILE / 4 * 3];
+  const int dir = blockIdx.z;
+  const int nq = dir ? m : n, nr = dir ? n : m;
+  const int q0 = blockIdx.x * (NN_THREADS * Q);
+  if (q0 >= nq) return;  // grid.x is sized for max(n, m); uniform per CTA
+  const size_t cloud = blockIdx.y;
+  const float *__restrict__ qp = (dir ? xyz2 : xyz1) + cloud * (size_t)nq * 3;
+  const float *__restrict__ rp = (dir ? xyz1 : xyz2) + cloud * (size_t)nr * 3;
+  float *__restrict__ dout = (dir ? dist2 : dist1) + cloud * (size_t)nq;
+  int *__restrict__ iout = (dir ? idx2 : idx1) + cloud * (size_t)nq;
+
+  float qx[Q], qy[Q], qz[Q], best[Q];
+  int grp[Q];
+  f32x2 nqx[Q], nqy[Q], nqz[Q];
+#pragma unroll
+  for (int u = 0; u < Q; ++u) {
+    int j = min(q0 + u * NN_THREADS + (int)threadIdx.x, nq - 1);
+    qx[u] = qp[j * 3 + 0];
+    qy[u] = qp[j * 3 + 1];
+    qz[u] = qp[j * 3 + 2];
+    nqx[u] = pack2(-qx[u], -qx[u]);
+    nqy[u] = pack2(-qy[u], -qy[u]);
+    nqz[u] = pack2(-qz[u], -qz[u]);
+    best[u] = __int_as_float(0x7f800000);
+    grp[u] = 0;
+  }
+
+  float *tf = reinterpret_cast<float *>(tile);
+  for (int base = 0; base < nr; base += NN_TILE) {
+    const int cnt = min(NN_TILE, nr - base);
+    const int cnt8 = (cnt + 7) & ~7;
+    __syncthreads();  // previous tile fully consumed
+    for (int i = threadIdx.x; i < cnt8; i += NN_THREADS) {
+      float x, y, z;
+      if (i < cnt) {
+        const float *p = rp + (size_t)(base + i) * 3;
+        x = p[0];
+        y = p[1];
+        z = p[2];
+      } else {
+        x = y = z = __int_as_float(0x7f800000);  // padding: distance +inf, never selected
+      }
+      const int o = (i >> 2) * 12 + (i & 3);
+      tf[o] = x;
+      tf[o + 4] = y;
+      tf[o + 8] = z;
+    }
+    __syncthreads();
+    const int g0 = base >> 3;
+#pragma unroll 2
+    for (int g = 0; g < (cnt8 >> 3); ++g) {
+      const float4 X0 = tile[g * 6 + 0], Y0 = tile[g * 6 + 1], Z0 = tile[g * 6 + 2];
+      const float4 X1 = tile[g * 6 + 3], Y1 = tile[g * 6 + 4], Z1 = tile[g * 6 + 5];
+#pragma unroll
+      for (int u = 0; u < Q; ++u) {
+        f32x2 d01 = sqdist2(pack2(X0.x, X0.y), pack2(Y0.x, Y0.y), pack2(Z0.x, Z0.y), nqx[u], nqy[u], nqz[u]);
+        f32x2 d23 = sqdist2(pack2(X0.z, X0.w), pack2(Y0.z, Y0.w), pack2(Z0.z, Z0.w), nqx[u], nqy[u], nqz[u]);
+        f32x2 d45 = sqdist2(pack2(X1.x, X1.y), pack2(Y1.x, Y1.y), pack2(Z1.x, Z1.y), nqx[u], nqy[u], nqz[u]);
+        f32x2 d67 = sqdist2(pack2(X1.z, X1.w), pack2(Y1.z, Y1.w), pack2(Z1.z, Z1.w), nqx[u], nqy[u], nqz[u]);
+        float a0, a1, a2, a3, a4, a5, a6, a7;
+        unpack2(d01, a0, a1);
+        unpack2(d23, a2, a3);
+        unpack2(d45, a4, a5);
+        unpack2(d67, a6, a7);
+        float mn = fminf(fminf(a0, a1), best[u]);
+        mn = fminf(fminf(a2, a3), mn);
+        mn = fminf(fminf(a4, a5), mn);
+        mn = fminf(fminf(a6, a7), mn);
+        grp[u] = (mn < best[u]) ? (g0 + g) : grp[u];  // strict: the first group reaching the minimum wins
+        best[u] = mn;
+      }
+    }
+  }
+
+  // Resolve the exact index inside the winning group of 8 (identical arithmetic => identical bits).
+#pragma unroll
+  for (int u = 0; u < Q; ++u) {
+    const int j = q0 + u * NN_THREADS + (int)threadIdx.x;
+    if (j >= nq) continue;
+    int bi = -1;
+    const int r0 = grp[u] * 8;
+#pragma unroll
+    for (int e = 7; e >= 0; --e) {
+      const int r = r0 + e;
+      if (r < nr) {
+        const float d = sqdist1(qx[u], qy[u], qz[u], rp[(size_t)r * 3], rp[(size_t)r * 3 + 1], rp[(size_t)r * 3 + 2]);
+        if (d == best[u]) bi = r;
+      }
+    }
+    float bd = best[u];
+    if (bi < 0) {  // nothing compared below +inf (NaN / inf inputs): the reference keeps element 0 (nndistance.cu:26)
+      bi = 0;
+      bd = sqdist1(qx[u], qy[u], qz[u], rp[0], rp[1], rp[2]);
+    }
+    dout[j] = bd;
+    iout[j] = bi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward (deterministic)
+// grad_T[j] = 2 g_T[j] (x_T[j] - x_S[idx_T[j]])  -  sum_{l : idx_S[l] == j} 2 g_S[l] (x_S[l] - x_T[j])
+// (nndistance.cu:139-145, both launches of :152-153 folded into one expression per target point)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int NG_THREADS = 512;
+constexpr int NG_HEAVY = 32;  // in-degree above which a target is reduced cooperatively by the whole CTA
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *warp_tot, int *total) {
+  // exclusive scan of one int per thread over NG_THREADS threads
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int t = lane < NG_THREADS / 32 ? warp_tot[lane] : 0;
+    int s = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += u;
+    }
+    if (lane < NG_THREADS / 32) warp_tot[lane] = s - t;  // exclusive warp offsets
+    if (lane == 31) *total = s;
+  }
+  __syncthreads();
+  return warp_tot[w] + inc - v;
+}
+
+__global__ void __launch_bounds__(NG_THREADS)
+nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2,
+               const float *__restrict__ gd1, const int *__restrict__ idx1, const float *__restrict__ gd2,
+               const int *__restrict__ idx2, float *__restrict__ g1, float *__restrict__ g2) {
+  extern __shared__ int sm[];
+  __shared__ int warp_tot[32];
+  __shared__ int scan_total;
+  __shared__ int n_heavy;
+  __shared__ float red[3][NG_THREADS / 32];
+
+  const int dir = blockIdx.y;
+  const size_t cloud = blockIdx.x;
+  const int nT = dir ? m : n, nS = dir ? n : m;
+  const float *__restrict__ xT = (dir ? xyz2 : xyz1) + cloud * (size_t)nT * 3;
+  const float *__restrict__ xS = (dir ? xyz1 : xyz2) + cloud * (size_t)nS * 3;
+  const float *__restrict__ gT = (dir ? gd2 : gd1) + cloud * (size_t)nT;
+  const float *__restrict__ gS = (dir ? gd1 : gd2) + cloud * (size_t)nS;
+  const int *__restrict__ iT = (dir ? idx2 : idx1) + cloud * (size_t)nT;  // target -> nearest source
+  const int *__restrict__ iS = (dir ? idx1 : idx2) + cloud * (size_t)nS;  // source -> nearest target
+  float *__restrict__ out = (dir ? g2 : g1) + cloud * (size_t)nT * 3;
+
+  int *cursor = sm;             // nT
+  int *start = sm + nT;         // nT
+  int *slots = sm + 2 * nT;     // nS
+  int *heavy = slots + nS;      // up to nS / (NG_HEAVY + 1) + 1 entries
+
+  for (int j = threadIdx.x; j < nT; j += NG_THREADS) cursor[j] = 0;
+  if (threadIdx.x == 0) n_heavy = 0;
+  __syncthreads();
+  for (int l = threadIdx.x; l < nS; l += NG_THREADS) {
+    int t = min(max(iS[l], 0), nT - 1);
+    atomicAdd(&cursor[t], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the in-degrees: contiguous chunk per thread
+  const int chunk = (nT + NG_THREADS - 1) / NG_THREADS;
+  const int c0 = min((int)threadIdx.x * chunk, nT), c1 = min(c0 + chunk, nT);
+  int local = 0;
+  for (int j = c0; j < c1; ++j) local += cursor[j];
+  int off = block_exclusive_scan(local, warp_tot, &scan_total);
+  for (int j = c0; j < c1; ++j) {
+    int d = cursor[j];
+    start[j] = off;
+    cursor[j] = off;
+    off += d;
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < nS; l += NG_THREADS) {
+    int t = min(max(iS[l], 0), nT - 1);
+    slots[atomicAdd(&cursor[t], 1)] = l;
+  }
+  __syncthreads();
+
+  for (int j = threadIdx.x; j < nT; j += NG_THREADS) {
+    const int s = start[j], e = cursor[j], deg = e - s;
+    if (deg > NG_HEAVY) {
+      heavy[atomicAdd(&n_heavy, 1)] = j;
+      continue;
+    }
+    // insertion sort of this target's (short) source list => fixed summation order
+    for (int a = s + 1; a < e; ++a) {
+      int v = slots[a], p = a;
+      while (p > s && slots[p - 1] > v) {
+        slots[p] = slots[p - 1];
+        --p;
+      }
+      slots[p] = v;
+    }
+    const float tx = xT[j * 3], ty = xT[j * 3 + 1], tz = xT[j * 3 + 2];
+    const int k = min(max(iT[j], 0), nS - 1);
+    const float g = gT[j] * 2.f;
+    float ax = g * (tx - xS[k * 3]), ay = g * (ty - xS[k * 3 + 1]), az = g * (tz - xS[k * 3 + 2]);
+    for (int a = s; a < e; ++a) {
+      const int l = slots[a];
+      const float gl = gS[l] * 2.f;
+      ax += -(gl * (xS[l * 3] - tx));
+      ay += -(gl * (xS[l * 3 + 1] - ty));
+      az += -(gl * (xS[l * 3 + 2] - tz));
+    }
+    out[j * 3] = ax;
+    out[j * 3 + 1] = ay;
+    out[j * 3 + 2] = az;
+  }
+  __syncthreads();
+
+  // Targets with a long list (collapsed clouds early in training): whole-CTA ordered reduction.
+  const int nh = n_heavy;
+  for (int h = 0; h < nh; ++h) {
+    const int j = heavy[h];
+    const float tx = xT[j * 3], ty = xT[j * 3 + 1], tz = xT[j * 3 + 2];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int l = threadIdx.x; l < nS; l += NG_THREADS) {
+      if (min(max(iS[l], 0), nT - 1) == j) {
+        const float gl = gS[l] * 2.f;
+        ax += -(gl * (xS[l * 3] - tx));
+        ay += -(gl * (xS[l * 3 + 1] - ty));
+        az += -(gl * (xS[l * 3 + 2] - tz));
+      }
+    }
+    ax = warp_sum(ax);
+    ay = warp_sum(ay);
+    az = warp_sum(az);
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = ax;
+      red[1][threadIdx.x >> 5] = ay;
+      red[2][threadIdx.x >> 5] = az;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int k = min(max(iT[j], 0), nS - 1);
+      const float g = gT[j] * 2.f;
+      float sx = g * (tx - xS[k * 3]), sy = g * (ty - xS[k * 3 + 1]), sz = g * (tz - xS[k * 3 + 2]);
+      for (int w = 0; w < NG_THREADS / 32; ++w) {
+        sx += red[0][w];
+        sy += red[1][w];
+        sz += red[2][w];
+      }
+      out[j * 3] = sx;
+      out[j * 3 + 1] = sy;
+      out[j * 3 + 2] = sz;
+    }
+    __syncthreads();
+  }
+}
+
+// Fallback for clouds whose lists do not fit in shared memory: own terms by plain stores, scatter terms by float
+// atomics (same scheme as the reference, not bitwise deterministic).
+__global__ void nn_grad_own_kernel(int b, int n, const float *__restrict__ xyz1, int m,
+                                   const float *__restrict__ xyz2, const float *__restrict__ gd1,
+                                   const int *__restrict__ idx1, float *__restrict__ g1) {
+  const size_t total = (size_t)b * n;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = t / n;
+    const int k = min(max(idx1[t], 0), m - 1);
+    const float g = gd1[t] * 2.f;
+    const float *p = xyz1 + t * 3, *q = xyz2 + (i * m + k) * 3;
+    g1[t * 3] = g * (p[0] - q[0]);
+    g1[t * 3 + 1] = g * (p[1] - q[1]);
+    g1[t * 3 + 2] = g * (p[2] - q[2]);
+  }
+}
+__global__ void nn_grad_scatter_kernel(int b, int n, const float *__restrict__ xyz1, int m,
+                                       const float *__restrict__ xyz2, const float *__restrict__ gd1,
+                                       const int *__restrict__ idx1, float *__restrict__ g2) {
+  const size_t total = (size_t)b * n;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = t / n;
+    const int k = min(max(idx1[t], 0), m - 1);
+    const float g = gd1[t] * 2.f;
+    const float *p = xyz1 + t * 3, *q = xyz2 + (i * m + k) * 3;
+    float *o = g2 + (i * m + k) * 3;
+    atomicAdd(o, -(g * (p[0] - q[0])));
+    atomicAdd(o + 1, -(g * (p[1] - q[1])));
+    atomicAdd(o + 2, -(g * (p[2] - q[2])));
+  }
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" __attribute__((visibility("default"))) int pcc_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *result,
+                              int *result_i, float *result2, int *result2_i, pcc_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCC_EINVAL;
+  if (b == 0 || n == 0 || m == 0) return PCC_OK;  // nothing to compare against: outputs are left untouched
+  if (b > 65535) return PCC_ENOTSUP;
+  const int mx = n > m ? n : m;
+  dim3 grid((mx + NN_THREADS - 1) / NN_THREADS, b, 2);
+  nn_fwd_kernel<1><<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, xyz, m, xyz2, result, result_i, result2,
+                                                                    result2_i);
+  return finish_launch(1);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2,
+                                  const float *grad_dist1, const int *idx1, const float *grad_dist2,
+                                  const int *idx2, float *grad_xyz1, float *grad_xyz2, pcc_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCC_EINVAL;
+  if (b == 0 || (n == 0 && m == 0)) return PCC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0 || m == 0) {  // no neighbours exist: gradients are zero
+    if (n) cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * (size_t)b * n * 3, st);
+    if (m) cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * (size_t)b * m * 3, st);
+    return (int)cudaGetLastError();
+  }
+  const size_t mx = n > m ? n : m, mn = n > m ? m : n;
+  const size_t smem = sizeof(int) * (2 * mx + mx + mx / (NG_HEAVY + 1) + 8);
+  (void)mn;
+  if (smem <= 200 * 1024 && b <= 65535) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(nn_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    nn_grad_kernel<<<dim3(b, 2), NG_THREADS, smem, st>>>(n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2,
+                                                          grad_xyz1, grad_xyz2);
+    return finish_launch(1);
+  }
+  const int threads = 256;
+  const int g1 = (int)(((size_t)b * n + threads - 1) / threads), g2 = (int)(((size_t)b * m + threads - 1) / threads);
+  nn_grad_own_kernel<<<g1 < 65535 * 16 ? g1 : 65535 * 16, threads, 0, st>>>(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_xyz1);
+  nn_grad_own_kernel<<<g2 < 65535 * 16 ? g2 : 65535 * 16, threads, 0, st>>>(b, m, xyz2, n, xyz1, grad_dist2, idx2, grad_xyz2);
+  nn_grad_scatter_kernel<<<g1 < 65535 * 16 ? g1 : 65535 * 16, threads, 0, st>>>(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_xyz2);
+  nn_grad_scatter_kernel<<<g2 < 65535 * 16 ? g2 : 65535 * 16, threads, 0, st>>>(b, m, xyz2, n, xyz1, grad_dist2, idx2, grad_xyz1);
+  return finish_launch(4);
+}

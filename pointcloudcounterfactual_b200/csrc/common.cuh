@@ -1,0 +1,79 @@
+// Shared device helpers for libpcc_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/pcc_b200.h"
+
+namespace pcc {
+
+extern std::atomic<uint64_t> g_launches;  // bumped once per kernel launch (pcc_launch_count)
+
+inline int finish_launch(int nkernels) {
+  g_launches.fetch_add((uint64_t)nkernels, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2) ------------------------------------------
+// A f32x2 value lives in a 64-bit register pair; .x is the low half.  Each op rounds both lanes exactly like
+// the scalar .rn instruction, so results are bit-identical to scalar FADD/FMUL/FFMA.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// Squared distance of two reference points (packed) to one query, canonical order of the reference kernels
+// (nndistance.cu:22-25 as compiled): d = fma(dz,dz, fma(dx,dx, dy*dy)),  d* = ref - query.
+// nq* hold the NEGATED query coordinate in both lanes.
+__device__ __forceinline__ f32x2 sqdist2(f32x2 rx, f32x2 ry, f32x2 rz, f32x2 nqx, f32x2 nqy, f32x2 nqz) {
+  f32x2 dx = add2(rx, nqx), dy = add2(ry, nqy), dz = add2(rz, nqz);
+  return fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+}
+
+__device__ __forceinline__ float sqdist1(float qx, float qy, float qz, float rx, float ry, float rz) {
+  float dx = rx - qx, dy = ry - qy, dz = rz - qz;
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace pcc

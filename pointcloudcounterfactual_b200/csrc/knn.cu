@@ -1,0 +1,186 @@
+// k-nearest-neighbour graph construction (DGCNN) and general argKmin for sm_100a -- exact fp32 SIMT path.
+//
+// Replaces the KeOps reductions behind src/utils/neighbour_ops.py:63-82 (knn / pykeops_knn: argKmin over
+// Sum(Square(x_i - x_j))) and the argmin patterns of src/train/metrics_and_losses.py:33,36 and
+// src/module/quantize.py:28.  Canonical arithmetic: d(i,j) = fma chain over channels in ascending order of
+// (x_i[c] - x_j[c])^2, selection ascending by (distance, index) -- stable, self included.
+//
+// Structure per CTA (128 queries x all references, tiles of 32 references):
+//   phase 1  register-tiled distance tile (4 queries x 8 references per thread, packed FADD2/FFMA2 over
+//            reference pairs), channels streamed through shared memory in chunks of 16;
+//   phase 2  one thread per query: threshold filter of the 32 new distances against its current k-th best,
+//            warp-compacted insertion into a sorted per-query list kept in shared memory ([slot][query] layout,
+//            bank-conflict free).
+#include "common.cuh"
+
+namespace pcc {
+
+constexpr int KN_THREADS = 128;  // == queries per CTA
+constexpr int KN_TQ = 128;
+constexpr int KN_TR = 32;
+constexpr int KN_CK = 16;
+constexpr int KN_DS = KN_TQ + 4;  // row stride of the distance tile
+
+struct KnnSmem {
+  float xq[KN_CK][KN_TQ];
+  float xr[KN_CK][KN_TR];
+  float D[KN_TR][KN_DS];
+  unsigned char cand[KN_TR][KN_TQ];
+};
+
+template <bool POINT_MAJOR>
+__global__ void __launch_bounds__(KN_THREADS)
+knn_kernel(int c, int nq, int nr, int k, const float *__restrict__ qin, const float *__restrict__ rin,
+           int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KnnSmem &S = *reinterpret_cast<KnnSmem *>(smem_raw);
+  float *Ld = reinterpret_cast<float *>(smem_raw + sizeof(KnnSmem));  // [k][KN_TQ]
+  int *Li = reinterpret_cast<int *>(Ld + (size_t)k * KN_TQ);          // [k][KN_TQ]
+
+  const int tid = threadIdx.x;
+  const size_t cloud = blockIdx.y;
+  const int q0 = blockIdx.x * KN_TQ;
+  const float *__restrict__ qb = qin + cloud * (size_t)c * nq;
+  const float *__restrict__ rb = rin + cloud * (size_t)c * nr;
+
+  const int ty = tid >> 2, tx = tid & 3;
+  float thr = __int_as_float(0x7f800000);
+  int have = 0;
+
+  for (int r0 = 0; r0 < nr; r0 += KN_TR) {
+    // ---- phase 1: D[r][q] = sum_c (xq - xr)^2 ------------------------------------------------------------
+    f32x2 acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[a][p] = 0ull;
+
+    for (int c0 = 0; c0 < c; c0 += KN_CK) {
+      const int cn = min(KN_CK, c - c0);
+      __syncthreads();  // previous chunk / previous tile's phase 2 done with shared memory
+      for (int e = tid; e < cn * KN_TQ; e += KN_THREADS) {
+        const int ch = e / KN_TQ, i = e % KN_TQ;
+        float v = 0.f;
+        if (q0 + i < nq)
+          v = POINT_MAJOR ? qb[(size_t)(q0 + i) * c + c0 + ch] : qb[(size_t)(c0 + ch) * nq + q0 + i];
+        S.xq[ch][i] = v;
+      }
+      for (int e = tid; e < cn * KN_TR; e += KN_THREADS) {
+        const int ch = e / KN_TR, i = e % KN_TR;
+        float v = 0.f;
+        if (r0 + i < nr)
+          v = POINT_MAJOR ? rb[(size_t)(r0 + i) * c + c0 + ch] : rb[(size_t)(c0 + ch) * nr + r0 + i];
+        S.xr[ch][i] = v;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int ch = 0; ch < cn; ++ch) {
+        const float4 qv = *reinterpret_cast<const float4 *>(&S.xq[ch][ty * 4]);
+        const float4 ra = *reinterpret_cast<const float4 *>(&S.xr[ch][tx * 4]);
+        const float4 rb4 = *reinterpret_cast<const float4 *>(&S.xr[ch][16 + tx * 4]);
+        const f32x2 rp[4] = {pack2(ra.x, ra.y), pack2(ra.z, ra.w), pack2(rb4.x, rb4.y), pack2(rb4.z, rb4.w)};
+        const float qs[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const f32x2 nq2 = pack2(-qs[a], -qs[a]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const f32x2 d = add2(rp[p], nq2);
+            acc[a][p] = fma2(d, d, acc[a][p]);
+          }
+        }
+      }
+    }
+    // scatter the register tile to D[ref][query]
+    {
+      float v[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) unpack2(acc[a][p], v[a][2 * p], v[a][2 * p + 1]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int rr = (e < 4) ? (tx * 4 + e) : (16 + tx * 4 + e - 4);
+        *reinterpret_cast<float4 *>(&S.D[rr][ty * 4]) = make_float4(v[0][e], v[1][e], v[2][e], v[3][e]);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: thread `tid` owns query q0+tid --------------------------------------------------------
+    int cnt = 0;
+    const int rvalid = min(KN_TR, nr - r0);
+#pragma unroll 8
+    for (int r = 0; r < KN_TR; ++r) {
+      const float d = S.D[r][tid];
+      if (r < rvalid && d < thr) {
+        S.cand[cnt][tid] = (unsigned char)r;
+        ++cnt;
+      }
+    }
+    const int mx = __reduce_max_sync(0xffffffffu, cnt);
+    for (int i = 0; i < mx; ++i) {
+      if (i < cnt) {
+        const int r = S.cand[i][tid];
+        const float d = S.D[r][tid];
+        if (d < thr) {  // thr may have tightened since the filter
+          int p = have < k ? have : k - 1;
+          while (p > 0 && d < Ld[(p - 1) * KN_TQ + tid]) {
+            Ld[p * KN_TQ + tid] = Ld[(p - 1) * KN_TQ + tid];
+            Li[p * KN_TQ + tid] = Li[(p - 1) * KN_TQ + tid];
+            --p;
+          }
+          Ld[p * KN_TQ + tid] = d;
+          Li[p * KN_TQ + tid] = r0 + r;
+          if (have < k) ++have;
+          if (have == k) thr = Ld[(k - 1) * KN_TQ + tid];
+        }
+      }
+    }
+  }
+
+  // slots that never filled (only possible with NaN / inf distances): keep the output memory-safe
+  for (int t = have; t < k; ++t) {
+    Ld[t * KN_TQ + tid] = __int_as_float(0x7f800000);
+    Li[t * KN_TQ + tid] = 0;
+  }
+  __syncthreads();
+  const int nvalid = min(KN_TQ, nq - q0);
+  const size_t obase = (cloud * (size_t)nq + q0) * k;
+  for (int e = tid; e < nvalid * k; e += KN_THREADS) {
+    const int qq = e / k, t = e - qq * k;
+    idx_out[obase + e] = (int64_t)Li[t * KN_TQ + qq];
+    if (dist_out) dist_out[obase + e] = Ld[t * KN_TQ + qq];
+  }
+}
+
+template <bool PM>
+static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const float *r, int64_t *idx,
+                      float *dist, cudaStream_t st) {
+  if (b < 0 || c <= 0 || nq < 0 || nr < 0 || k <= 0) return PCC_EINVAL;
+  if (k > nr) return PCC_EINVAL;  // torch.topk / argKmin cannot return more neighbours than points
+  if (k > PCC_KNN_MAX_K || b > 65535) return PCC_ENOTSUP;
+  if (b == 0 || nq == 0) return PCC_OK;
+  const size_t smem = sizeof(KnnSmem) + (size_t)k * KN_TQ * (sizeof(float) + sizeof(int));
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(knn_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  dim3 grid((nq + KN_TQ - 1) / KN_TQ, b);
+  knn_kernel<PM><<<grid, KN_THREADS, smem, st>>>(c, nq, nr, k, q, r, idx, dist);
+  return finish_launch(1);
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" __attribute__((visibility("default"))) int pcc_knn(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, pcc_stream_t stream) {
+  return launch_knn<false>(b, c, n, n, k, x, x, idx, dist, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_argkmin(int b, int nq, int nr, int c, int k, const float *q, const float *r, int64_t *idx,
+                           float *dist, pcc_stream_t stream) {
+  return launch_knn<true>(b, c, nq, nr, k, q, r, idx, dist, (cudaStream_t)stream);
+}

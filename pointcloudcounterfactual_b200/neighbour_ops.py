@@ -1,0 +1,121 @@
+"""kNN graph construction and the graph operators built on it -- same function names and semantics as the
+reference's ``src/utils/neighbour_ops.py`` (line numbers below refer to that file).
+
+``knn`` / ``pykeops_knn`` run the sm_100a kernel (``pcc_knn``): x (B,C,N) channels-first -> (B,N,k) int64, the k
+smallest squared distances per point including the point itself, ascending by (distance, index).  There is no CPU
+fallback: a CPU tensor raises.  ``torch_knn`` / ``*_square_distance`` keep the reference's dense torch formulas
+for callers that ask for them by name.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .keops import LazyTensor, SquareDistance
+
+
+def knn_indices(x: torch.Tensor, k: int, return_dist: bool = False):
+    """x (B,C,N) CUDA fp32 -> idx (B,N,k) int64 [, dist (B,N,k) fp32]."""
+    x = x.contiguous()
+    L.require_cuda(x)
+    if x.dim() != 3:
+        raise RuntimeError("knn expects a (batch, channels, points) tensor")
+    b, c, n = x.shape
+    with torch.cuda.device(x.device):
+        idx = torch.empty((b, n, k), dtype=torch.int64, device=x.device)
+        dist = torch.empty((b, n, k), dtype=torch.float32, device=x.device) if return_dist else None
+        L.check(L.load().pcc_knn(b, c, n, k, L.ptr(x), L.ptr(idx), L.ptr(dist), L.stream_of(x)), "knn")
+    return (idx, dist) if return_dist else idx
+
+
+def index_k_neighbours(pcs: list[np.ndarray], k: int) -> np.ndarray:
+    """Dataset-side kNN (:16-24; the reference builds a KDTree per cloud on the CPU): list of (N,3) arrays ->
+    (len, N, k) indices, computed on the GPU."""
+    out = []
+    for pc in pcs:
+        x = torch.as_tensor(np.ascontiguousarray(pc), dtype=torch.float32).cuda().t().unsqueeze(0)
+        out.append(knn_indices(x, k)[0].cpu().numpy().reshape(-1, k))
+    return np.stack(out)
+
+
+def square_distance(t1: torch.Tensor, t2: torch.Tensor) -> torch.Tensor | SquareDistance:
+    """(:27-32) symbolic on CUDA, dense on CPU tensors."""
+    if t1.device.type == 'cuda':
+        return pykeops_square_distance(t1, t2)
+    return torch_square_distance(t1, t2)
+
+
+def pykeops_square_distance(t1: torch.Tensor, t2: torch.Tensor) -> SquareDistance:
+    """(:35-40) symbolic squared-distance matrix between (B,N,D) and (B,M,D)."""
+    return ((LazyTensor(t1[:, :, None, :]) - LazyTensor(t2[:, None, :, :])) ** 2).sum(-1)
+
+
+def torch_square_distance(t1: torch.Tensor, t2: torch.Tensor) -> torch.Tensor:
+    """(:43-50) dense GEMM-form squared distances, (B,N,D) x (B,M,D) -> (B,N,M)."""
+    sq1 = (t1 * t1).sum(-1, keepdim=True)
+    sq2 = (t2 * t2).sum(-1).unsqueeze(-2)
+    return torch.baddbmm(sq1 + sq2, t1, t2.transpose(-1, -2), alpha=-2.0) if t1.dim() == 3 else (
+        sq1 + sq2 - 2.0 * t1 @ t2.transpose(-1, -2))
+
+
+def self_square_distance(t1: torch.Tensor) -> torch.Tensor:
+    """(:53-60) dense self-distances of a channels-first (B,C,N) tensor -> (B,N,N)."""
+    sq = (t1 * t1).sum(-2, keepdim=True)
+    return sq + sq.transpose(-1, -2) - 2.0 * (t1.transpose(-1, -2) @ t1)
+
+
+def knn(x: torch.Tensor, k: int) -> torch.Tensor:
+    """(:63-68) k nearest neighbours of every point of x (B,C,N), self included."""
+    return knn_indices(x, k)
+
+
+def pykeops_knn(x: torch.Tensor, k: int) -> torch.Tensor:
+    """(:77-82)"""
+    return knn_indices(x, k)
+
+
+def torch_knn(x: torch.Tensor, k: int) -> torch.Tensor:
+    """(:71-74) dense torch path, kept for callers that name it explicitly."""
+    return self_square_distance(x).topk(k=k, largest=False)[1]
+
+
+def get_neighbours(x: torch.Tensor, indices: torch.Tensor, k: int):
+    """(:85-94) -> (indices (B,N,k), neighbours (B,C,N,k))."""
+    batch, n_feat, n_points = x.size()
+    if not indices.numel():
+        indices = knn(x, k)
+    flat = indices.contiguous().view(batch, 1, k * n_points).expand(-1, n_feat, -1)
+    neighbours = torch.gather(x, 2, flat).view(batch, n_feat, n_points, k)
+    return indices, neighbours
+
+
+def get_local_covariance(x: torch.Tensor, indices: torch.Tensor, k: int = 16) -> torch.Tensor:
+    """(:97-103) appends the flattened k-neighbourhood covariance to the features."""
+    neighbours = get_neighbours(x, indices, k)[1]
+    neighbours = neighbours - neighbours.mean(3, keepdim=True)
+    cov = torch.matmul(neighbours.transpose(1, 2), neighbours.permute(0, 2, 3, 1))
+    return torch.cat([x, cov.flatten(start_dim=2).transpose(1, 2)], dim=1).contiguous()
+
+
+def graph_max_pooling(x: torch.Tensor, indices: torch.Tensor, k: int = 16) -> torch.Tensor:
+    """(:106-110)"""
+    return get_neighbours(x, indices, k)[1].max(dim=-1)[0]
+
+
+def get_graph_features(x: torch.Tensor, indices: torch.Tensor, k: int = 20) -> tuple[torch.Tensor, torch.Tensor]:
+    """(:113-119) EdgeConv input: cat(neighbour - centre, centre) -> (B, 2C, N, k)."""
+    indices_out, neighbours = get_neighbours(x, indices, k)
+    centre = x.unsqueeze(3).expand(-1, -1, -1, k)
+    return indices_out, torch.cat([neighbours - centre, centre], dim=1).contiguous()
+
+
+def graph_filtering(x: torch.Tensor, k: int = 4) -> torch.Tensor:
+    """(:122-133) decoder-output smoothing; relies on ascending kNN with the point itself in column 0."""
+    neighbours = get_neighbours(x, indices=torch.empty(0), k=k)[1][..., 1:]
+    diff = x.unsqueeze(-1) - neighbours
+    dist = torch.sqrt((diff * diff).sum(1).abs())
+    sigma = torch.clamp(dist[..., 0:1].mean(1, keepdim=True), min=0.005)
+    weights = torch.exp(-(dist / sigma))
+    x_weight = weights.sum(2).unsqueeze(1)
+    return (1 + x_weight) * x - (weights.unsqueeze(1) * neighbours).sum(-1)

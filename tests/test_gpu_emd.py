@@ -1,0 +1,112 @@
+"""GPU: approximate-matching EMD (ApproxMatch / MatchCost / MatchCostGrad / fused match_cost) and the auction EMD
+against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import rel_err
+from pointcloudcounterfactual_b200 import synthetic
+from pointcloudcounterfactual_b200.emd import emdModule
+from pointcloudcounterfactual_b200.structural_losses import match_cost
+from pointcloudcounterfactual_b200.structural_losses.structural_losses_backend import (
+    ApproxMatch, MatchCost, MatchCostFused, MatchCostGrad)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5  # north_star: EMD costs and gradients within 1e-5 relative
+
+
+def _clouds(kind, b, n, m):
+    if kind == "s1":
+        return synthetic.s1_near(b, n)
+    a, c = synthetic.s2_far(b, n, m)
+    return a, c
+
+
+@pytest.mark.parametrize("kind,b,n,m", [("s1", 2, 512, 512), ("s2", 2, 384, 384), ("s2", 2, 256, 128), ("s2", 1, 100, 333),
+                                        ("s1", 1, 2048, 2048), ("s2", 2, 1, 7)])
+def test_approxmatch_chain_vs_oracle(cuda, kind, b, n, m):
+    a, c = _clouds(kind, b, n, m)
+    ematch, _ = oracle.approxmatch(a.numpy(), c.numpy())
+    ecost = oracle.matchcost(a.numpy(), c.numpy(), ematch)
+    eg1, eg2 = oracle.matchcostgrad(a.numpy(), c.numpy(), ematch)
+    ta, tc = a.to(cuda), c.to(cuda)
+    match, temp = ApproxMatch(ta, tc)
+    assert match.shape == (b, m, n) and temp.shape == (b, 2 * (n + m))
+    # element-wise: absolute tolerance relative to the row scale (entries span 30 orders of magnitude)
+    assert np.abs(match.cpu().numpy() - ematch).max() < 2e-5 * max(1.0, float(ematch.max()))
+    assert rel_err(match.sum(1).cpu().numpy(), ematch.sum(1)) < TOL
+    cost = MatchCost(ta, tc, match)
+    assert rel_err(cost.cpu().numpy(), ecost) < TOL
+    g1, g2 = MatchCostGrad(ta, tc, match)
+    assert rel_err(g1.cpu().numpy(), eg1) < TOL and rel_err(g2.cpu().numpy(), eg2) < TOL
+    # the same operators fed the ORACLE's match: isolates MatchCost / MatchCostGrad from ApproxMatch
+    om = torch.from_numpy(ematch).to(cuda)
+    assert rel_err(MatchCost(ta, tc, om).cpu().numpy(), ecost) < TOL
+    h1, h2 = MatchCostGrad(ta, tc, om)
+    assert rel_err(h1.cpu().numpy(), eg1) < TOL and rel_err(h2.cpu().numpy(), eg2) < TOL
+    # fused path (no match matrix)
+    fc, f1, f2 = MatchCostFused(ta, tc)
+    assert rel_err(fc.cpu().numpy(), ecost) < TOL
+    assert rel_err(f1.cpu().numpy(), eg1) < TOL and rel_err(f2.cpu().numpy(), eg2) < TOL
+
+
+def test_match_cost_autograd_surface(cuda):
+    a, c = synthetic.s1_near(3, 256)
+    ta, tc = a.to(cuda).requires_grad_(True), c.to(cuda)
+    cost = match_cost(ta, tc)
+    assert cost.shape == (3,)
+    w = torch.tensor([1.0, -2.0, 0.5], device=cuda)
+    (cost * w).sum().backward()
+    ematch, _ = oracle.approxmatch(a.numpy(), c.numpy())
+    eg1, _ = oracle.matchcostgrad(a.numpy(), c.numpy(), ematch)
+    assert rel_err(ta.grad.cpu().numpy(), eg1 * w.cpu().numpy()[:, None, None]) < TOL
+    assert tc.grad is None
+    tb = c.to(cuda).requires_grad_(True)
+    match_cost(a.to(cuda), tb).sum().backward()
+    _, eg2 = oracle.matchcostgrad(a.numpy(), c.numpy(), ematch)
+    assert rel_err(tb.grad.cpu().numpy(), eg2) < TOL
+
+
+def test_invariants_full_size(cuda):
+    """BASELINE config 3 size (B=32, n=m=2048): SURVEY section 4 invariants, no CPU oracle needed."""
+    a, c = synthetic.s1_near(32, 2048)
+    ta, tc = a.to(cuda), c.to(cuda)
+    match, _ = ApproxMatch(ta, tc)
+    rows, cols = match.sum(1), match.sum(2)
+    assert rows.min() > 0.99 and rows.max() <= 1 + 1e-5 and cols.min() > 0.99 and cols.max() <= 1 + 1e-5
+    cost = MatchCost(ta, tc, match)
+    fc, f1, _ = MatchCostFused(ta, tc, want_grad2=False)
+    assert rel_err(fc.cpu().numpy(), cost.cpu().numpy()) < TOL
+    g1, _ = MatchCostGrad(ta, tc, match)
+    assert rel_err(f1.cpu().numpy(), g1.cpu().numpy()) < TOL
+    same, _, _ = MatchCostFused(ta, ta, want_grad1=False, want_grad2=False)
+    assert (same < 1e-3 * cost).all()  # match_cost(x, x) ~ 0
+    del match
+    # two clouds against the oracle at full size
+    em, _ = oracle.approxmatch(a[:2].numpy(), c[:2].numpy())
+    assert rel_err(fc[:2].cpu().numpy(), oracle.matchcost(a[:2].numpy(), c[:2].numpy(), em)) < TOL
+    eg1, _ = oracle.matchcostgrad(a[:2].numpy(), c[:2].numpy(), em)
+    assert rel_err(f1[:2].cpu().numpy(), eg1) < TOL
+
+
+def test_fused_is_deterministic(cuda):
+    a, c = synthetic.s2_far(4, 700, 650)
+    x = MatchCostFused(a.to(cuda), c.to(cuda))
+    y = MatchCostFused(a.to(cuda), c.to(cuda))
+    assert all(torch.equal(p, q) for p, q in zip(x, y))
+
+
+@pytest.mark.parametrize("b,n,eps,iters", [(3, 1024, 0.005, 50), (2, 2048, 0.005, 50), (1, 1024, 0.002, 3000), (2, 1024, 0.01, 1)])
+def test_auction_vs_oracle(cuda, b, n, eps, iters):
+    a, c = synthetic.auction_clouds(b, n)
+    edist, easg, _ = oracle.auction_emd(a.numpy(), c.numpy(), eps, iters)
+    ta = a.to(cuda).requires_grad_(True)
+    dist, asg = emdModule()(ta, c.to(cuda), eps, iters)
+    assert asg.dtype == torch.int32 and dist.shape == (b, n)
+    assert np.array_equal(asg.cpu().numpy(), easg)  # deterministic rounds => identical assignment
+    assert rel_err(dist.detach().cpu().numpy(), edist) < TOL
+    w = torch.randn(b, n, generator=torch.Generator().manual_seed(5))
+    (dist * w.to(cuda)).sum().backward()
+    eg = oracle.auction_emd_grad(a.numpy(), c.numpy(), w.numpy(), easg)
+    assert rel_err(ta.grad.cpu().numpy(), eg) < TOL

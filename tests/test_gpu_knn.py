@@ -1,0 +1,114 @@
+"""GPU: kNN graph construction / argKmin against the CPU oracle and the reference fixtures."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import rel_err
+from pointcloudcounterfactual_b200 import keops, neighbour_ops, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("c,n,k,b", [
+    (3, 1024, 20, 4), (3, 2048, 25, 2), (3, 2048, 4, 2), (3, 300, 16, 3), (3, 33, 33, 2), (3, 5, 1, 2),
+    (64, 1024, 20, 2), (64, 200, 20, 2), (128, 384, 25, 1), (17, 130, 7, 2), (256, 256, 20, 1),
+])
+def test_knn_indices_bit_exact_vs_oracle(cuda, c, n, k, b):
+    x = synthetic.knn_xyz(b, n) if c == 3 else synthetic.knn_features(b, c, n)
+    idx, dist = neighbour_ops.knn_indices(x.to(cuda), k, return_dist=True)
+    eidx, edist = oracle.knn(x.numpy(), k, return_dist=True)
+    assert idx.dtype == torch.int64 and idx.shape == (b, n, k)
+    assert np.array_equal(idx.cpu().numpy(), eidx)
+    assert np.array_equal(dist.cpu().numpy(), edist)  # same sequential fma chain => same bits
+
+
+def test_knn_ties_lowest_index(cuda):
+    a, _ = synthetic.s3_ties(2, 512, pool=64)  # heavy duplication: many exact ties
+    x = a.transpose(1, 2).contiguous()
+    idx = neighbour_ops.knn(x.to(cuda), 20)
+    assert np.array_equal(idx.cpu().numpy(), oracle.knn(x.numpy(), 20))
+    z = torch.zeros(1, 3, 64)
+    assert torch.equal(neighbour_ops.knn(z.to(cuda), 5).cpu(), torch.arange(5).expand(1, 64, 5))
+
+
+@pytest.mark.parametrize("case", ["xyz_k20", "xyz_k4", "feat64_k20", "feat128_k25"])
+def test_knn_golden_reference(cuda, golden, case):
+    g = golden["knn"]
+    x, k = torch.from_numpy(g[f"{case}_x"]), int(g[f"{case}_k"])
+    idx = neighbour_ops.knn(x.to(cuda), k).cpu().numpy()
+    assert np.array_equal(idx, g[f"{case}_keops_idx"])
+    tidx = g[f"{case}_torch_idx"]  # reference torch path (GEMM form + topk): near-ties may be ordered differently
+    mism = idx != tidx
+    assert mism.mean() < 1e-3
+    if mism.any():  # every disagreement must be a near-tie in fp64
+        xd = torch.from_numpy(g[f"{case}_x"]).double()
+        d = (xd[:, :, :, None] - xd[:, :, None, :]).pow(2).sum(1).numpy()
+        bb, qq, tt = np.nonzero(mism)
+        gap = np.abs(d[bb, qq, idx[bb, qq, tt]] - d[bb, qq, tidx[bb, qq, tt]])
+        assert (gap <= 1e-5 * np.maximum(d[bb, qq, idx[bb, qq, tt]], 1e-6)).all()
+
+
+def test_lazytensor_patterns(cuda):
+    """The four KeOps expression patterns of the reference."""
+    t1, t2 = synthetic.s2_far(2, 200, 333)
+    a, c = t1.to(cuda), t2.to(cuda)
+    d = neighbour_ops.square_distance(a, c)
+    dense = oracle.square_distance(t1.numpy(), t2.numpy())
+    order2 = np.argsort(dense, axis=2, kind="stable")
+    order1 = np.argsort(dense, axis=1, kind="stable")
+    assert np.array_equal(d.argKmin(5, dim=2).cpu().numpy(), order2[:, :, :5])
+    assert np.array_equal(d.argmin(axis=2).cpu().numpy(), order2[:, :, :1])
+    assert np.array_equal(d.argmin(axis=1).cpu().numpy(), order1[:, :1, :].transpose(0, 2, 1))
+    assert d.argmin(axis=1).shape == (2, 333, 1)
+    assert rel_err(d.sum(1).cpu().numpy()[..., 0], dense.sum(1)) < 1e-5
+    # quantize.py:20-32 shape pattern: (B*codes, 1, D) against (B*codes, book, D)
+    xq = torch.randn(64, 1, 4, generator=torch.Generator().manual_seed(1))
+    book = torch.randn(64, 16, 4, generator=torch.Generator().manual_seed(2))
+    dq = neighbour_ops.pykeops_square_distance(xq.to(cuda), book.to(cuda))
+    exp = oracle.square_distance(xq.numpy(), book.numpy())
+    assert np.array_equal(dq.argmin(axis=2).cpu().numpy()[:, 0, 0], np.argsort(exp, 2, kind="stable")[:, 0, 0])
+    assert dq.sum(1).shape == (64, 16, 1)
+
+
+def test_graph_ops_golden(cuda, golden):
+    g = golden["graph"]
+    x = torch.from_numpy(g["x"]).to(cuda)
+    empty = torch.empty(0)
+    idx, feat = neighbour_ops.get_graph_features(x, empty, k=8)
+    assert np.array_equal(idx.cpu().numpy(), g["gf_idx"]) and np.array_equal(feat.cpu().numpy(), g["gf_feat"])
+    assert np.array_equal(neighbour_ops.graph_max_pooling(x, empty, k=8).cpu().numpy(), g["gmp"])
+    assert rel_err(neighbour_ops.get_local_covariance(x, empty, k=8).cpu().numpy(), g["cov"]) < 1e-5
+    assert rel_err(neighbour_ops.graph_filtering(x, k=4).cpu().numpy(), g["filt"]) < 1e-5
+    f = torch.from_numpy(g["f"]).to(cuda)
+    idx, feat = neighbour_ops.get_graph_features(f, empty, k=6)
+    assert np.array_equal(idx.cpu().numpy(), g["gf16_idx"]) and np.array_equal(feat.cpu().numpy(), g["gf16_feat"])
+    # precomputed indices are passed through untouched (neighbour_ops.py:88-91)
+    idx2, _ = neighbour_ops.get_graph_features(f, idx, k=6)
+    assert idx2 is idx
+
+
+def test_full_size_properties(cuda):
+    """BASELINE config 2 (B=32, N=1024, k=20; xyz and 64-dim): self first, sorted, matches dense fp64 top-k sets."""
+    for x in (synthetic.knn_xyz(32, 1024), synthetic.knn_features(32, 64, 1024)):
+        xd = x.to(cuda)
+        idx, dist = neighbour_ops.knn_indices(xd, 20, return_dist=True)
+        assert torch.equal(idx[..., 0], torch.arange(1024, device=cuda).expand(32, -1))
+        assert (dist[..., 1:] >= dist[..., :-1]).all() and (dist[..., 0] == 0).all()
+        dense = (xd.double()[:, :, :, None] - xd.double()[:, :, None, :]).pow(2).sum(1)
+        kth = dense.topk(20, largest=False)[0][..., -1]
+        picked = torch.gather(dense, 2, idx)
+        assert (picked <= kth.unsqueeze(-1) * (1 + 1e-5) + 1e-9).all()
+        e = oracle.knn(x[:2].numpy(), 20)
+        assert np.array_equal(idx[:2].cpu().numpy(), e)
+
+
+def test_errors(cuda):
+    x = torch.zeros(1, 3, 8, device=cuda)
+    with pytest.raises(RuntimeError, match="invalid shape"):
+        neighbour_ops.knn(x, 9)  # k > n, like torch.topk
+    with pytest.raises(RuntimeError, match="unsupported"):
+        neighbour_ops.knn(torch.zeros(1, 3, 300, device=cuda), 129)
+    assert neighbour_ops.knn(torch.zeros(0, 3, 8, device=cuda), 2).shape == (0, 8, 2)
+    idx = neighbour_ops.index_k_neighbours([np.random.default_rng(0).random((64, 3)).astype(np.float32)], 4)
+    assert idx.shape == (1, 64, 4) and (idx[0, :, 0] == np.arange(64)).all()
