@@ -20,8 +20,9 @@ namespace pcc {
 
 constexpr int AM_LEVELS = 9;  // j = 7, 6, ..., -1  (approxmatch.cu:24; the j == -2 / level 0 sweep is dead code)
 constexpr int AM_THREADS = 128;
-constexpr int AM_QTILE = 1024;  // partner points per shared-memory tile in the row-sum kernel
-constexpr float AM_LOG2E = 1.4426950408889634f;
+constexpr int AM_P = 4;          // points owned by one thread in a sweep (two packed f32x2 lanes pairs)
+constexpr int AM_QTILE = 2048;   // partner points per shared-memory tile in the sweep kernel (32 KiB)
+constexpr float AM_LOG2E = 1.4426950408889634f;  // 0f3FB8AA3B, the constant __expf multiplies by
 
 enum { EPI_RATIO_L = 0, EPI_RATIO_R = 1, EPI_REMAIN_L = 2 };
 
@@ -32,110 +33,129 @@ __global__ void am_init_kernel(int n, int m, float *__restrict__ temp, float mul
     t[i] = i < n ? multiL : multiR;
 }
 
-// S[p] = sum_q exp2(scale * |x_p - x_q|^2) * w[q], then the epilogue of the sweep.
+__global__ void am_levels_kernel(float *levels) {
+  // the reference evaluates `-powf(4.0f, j)` on the device (approxmatch.cu:25); use the same routine
+  const int t = threadIdx.x;
+  if (t < AM_LEVELS) levels[t] = -powf(4.0f, (float)(7 - t));
+}
+
+// One sweep of the solver, BIT-FAITHFUL to the reference kernel: for every owned point p
+//     acc_p = init;  for q = 0 .. nQ-1 (ascending):  acc_p = fma(E(p,q) [* rl_p], w[q], acc_p)
+// with E = ex2.approx((d2 * level) * log2e), d2 = fma(dz,dz,fma(dx,dx,dy*dy)) -- the exact operation sequence nvcc
+// emits for approxmatch.cu:29-62 / :78-111 / :130-163 -- followed by that sweep's epilogue.  The iteration amplifies
+// rounding differences ~1000x into match / gradients, so the summation order and every rounding are kept; the
+// parallelism is over points only (each thread owns AM_P points, packed two per f32x2 lane pair, so that one
+// broadcast LDS.128 of a partner feeds four exponentials and the SFU pipe, not shared memory, is the limit).
 template <int EPI>
 __global__ void __launch_bounds__(AM_THREADS)
-am_rowsum_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
-                 const float *__restrict__ wQ, size_t wQ_stride, float scale, float *__restrict__ remainP,
-                 size_t remain_stride, float *__restrict__ ratioP, size_t ratio_stride,
-                 const float *__restrict__ ratioP_in) {
-  __shared__ float4 tile[AM_QTILE];  // per partner pair: (x0,x1,y0,y1) (z0,z1,w0,w1)
+am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
+                const float *__restrict__ wQ, size_t wQ_stride, float level, float *__restrict__ remainP,
+                size_t remain_stride, float *__restrict__ ratioP, size_t ratio_stride) {
+  __shared__ float4 tile[AM_QTILE];  // (x, y, z, w) per partner
   const size_t cloud = blockIdx.y;
   xP += cloud * (size_t)nP * 3;
   xQ += cloud * (size_t)nQ * 3;
   wQ += cloud * wQ_stride;
-  const int p = blockIdx.x * AM_THREADS + threadIdx.x;
-  const int pc = min(p, nP - 1);
-  const float px = xP[pc * 3], py = xP[pc * 3 + 1], pz = xP[pc * 3 + 2];
-  const f32x2 npx = pack2(-px, -px), npy = pack2(-py, -py), npz = pack2(-pz, -pz);
-  const f32x2 sc2 = pack2(scale, scale);
-  f32x2 acc = 0ull, acc_b = 0ull;
-  float *tf = reinterpret_cast<float *>(tile);
+  float *rem = remainP + cloud * remain_stride;
+  float *rat = ratioP + cloud * ratio_stride;
+  // thread t of block bx owns points p0 + t + u*AM_THREADS, u = 0..AM_P-1
+  const int p0 = blockIdx.x * (AM_THREADS * AM_P) + threadIdx.x;
+  f32x2 npx[AM_P / 2], npy[AM_P / 2], npz[AM_P / 2], acc[AM_P / 2], rl2[AM_P / 2];
+#pragma unroll
+  for (int h = 0; h < AM_P / 2; ++h) {
+    const int a = min(p0 + (2 * h) * AM_THREADS, nP - 1), b = min(p0 + (2 * h + 1) * AM_THREADS, nP - 1);
+    npx[h] = pack2(-xP[a * 3], -xP[b * 3]);
+    npy[h] = pack2(-xP[a * 3 + 1], -xP[b * 3 + 1]);
+    npz[h] = pack2(-xP[a * 3 + 2], -xP[b * 3 + 2]);
+    const float init = (EPI == EPI_RATIO_L) ? 1e-9f : 0.f;  // approxmatch.cu:37 / :86 / :138
+    acc[h] = pack2(init, init);
+    rl2[h] = (EPI == EPI_REMAIN_L) ? pack2(rat[a], rat[b]) : 0ull;  // ratioL[k] (approxmatch.cu:146)
+  }
+  const f32x2 lvl2 = pack2(level, level), l2e2 = pack2(AM_LOG2E, AM_LOG2E);
 
   for (int base = 0; base < nQ; base += AM_QTILE) {
     const int cnt = min(AM_QTILE, nQ - base);
-    const int cnt4 = (cnt + 3) & ~3;
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt4; i += AM_THREADS) {
-      float x = 0.f, y = 0.f, z = 0.f, w = 0.f;  // padding partner: weight 0
-      if (i < cnt) {
-        const float *q = xQ + (size_t)(base + i) * 3;
-        x = q[0];
-        y = q[1];
-        z = q[2];
-        w = wQ[base + i];
-      }
-      const int o = (i >> 1) * 8 + (i & 1);
-      tf[o] = x;
-      tf[o + 2] = y;
-      tf[o + 4] = z;
-      tf[o + 6] = w;
+    for (int i = threadIdx.x; i < cnt; i += AM_THREADS) {
+      const float *q = xQ + (size_t)(base + i) * 3;
+      tile[i] = make_float4(q[0], q[1], q[2], wQ[base + i]);
     }
     __syncthreads();
-#pragma unroll 2
-    for (int pr = 0; pr < (cnt4 >> 1); pr += 2) {
-      const float4 a0 = tile[pr * 2], a1 = tile[pr * 2 + 1];
-      const float4 b0 = tile[pr * 2 + 2], b1 = tile[pr * 2 + 3];
-      const f32x2 da = mul2(sqdist2(pack2(a0.x, a0.y), pack2(a0.z, a0.w), pack2(a1.x, a1.y), npx, npy, npz), sc2);
-      const f32x2 db = mul2(sqdist2(pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), npx, npy, npz), sc2);
-      float e0, e1, e2, e3;
-      unpack2(da, e0, e1);
-      unpack2(db, e2, e3);
-      acc = fma2(pack2(ex2_ftz(e0), ex2_ftz(e1)), pack2(a1.z, a1.w), acc);
-      acc_b = fma2(pack2(ex2_ftz(e2), ex2_ftz(e3)), pack2(b1.z, b1.w), acc_b);
+#pragma unroll 4
+    for (int l = 0; l < cnt; ++l) {
+      const float4 q = tile[l];
+      const f32x2 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z), qw = pack2(q.w, q.w);
+#pragma unroll
+      for (int h = 0; h < AM_P / 2; ++h) {
+        const f32x2 dx = add2(qx, npx[h]), dy = add2(qy, npy[h]), dz = add2(qz, npz[h]);
+        const f32x2 d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+        const f32x2 arg = mul2(mul2(d2, lvl2), l2e2);
+        float a0, a1;
+        unpack2(arg, a0, a1);
+        f32x2 E = pack2(ex2_ftz(a0), ex2_ftz(a1));
+        if (EPI == EPI_REMAIN_L) E = mul2(rl2[h], E);  // rl * E, then fma(., ratioR, suml)  (compiled :155-157)
+        acc[h] = fma2(E, qw, acc[h]);
+      }
     }
   }
-  if (p >= nP) return;
-  float s0, s1, s2, s3;
-  unpack2(acc, s0, s1);
-  unpack2(acc_b, s2, s3);
-  const float S = (s0 + s1) + (s2 + s3);
-  float *rem = remainP + cloud * remain_stride;
-  float *rat = ratioP + cloud * ratio_stride;
-  if (EPI == EPI_RATIO_L) {  // approxmatch.cu:37,58-61: suml = 1e-9f + sum ; ratioL = remainL / suml
-    rat[p] = rem[p] / (1e-9f + S);
-  } else if (EPI == EPI_RATIO_R) {  // approxmatch.cu:104-109
-    const float r = rem[p];
-    const float sumr = S * r;
-    const float consumption = fminf(r / (sumr + 1e-9f), 1.0f);
-    rat[p] = consumption * r;
-    rem[p] = fmaxf(0.0f, r - sumr);
-  } else {  // approxmatch.cu:150-162: suml = sum_l E*ratioL[k]*ratioR[l] ; remainL = max(0, remainL - suml)
-    const float suml = (ratioP_in + cloud * ratio_stride)[p] * S;
-    rem[p] = fmaxf(0.0f, rem[p] - suml);
+#pragma unroll
+  for (int h = 0; h < AM_P / 2; ++h) {
+    float s[2];
+    unpack2(acc[h], s[0], s[1]);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int p = p0 + (2 * h + e) * AM_THREADS;
+      if (p >= nP) continue;
+      if (EPI == EPI_RATIO_L) {  // approxmatch.cu:60-61
+        rat[p] = rem[p] / s[e];
+      } else if (EPI == EPI_RATIO_R) {  // approxmatch.cu:104-109
+        const float r = rem[p];
+        const float sumr = s[e] * r;
+        const float consumption = fminf(r / (sumr + 1e-9f), 1.0f);
+        rat[p] = consumption * r;
+        rem[p] = fmaxf(0.0f, r - sumr);
+      } else {  // approxmatch.cu:161-162
+        rem[p] = fmaxf(0.0f, rem[p] - s[e]);
+      }
+    }
   }
 }
 
 // ---- phase B -------------------------------------------------------------------------------------------------
 // match(p,q) = sum_t E_t(p,q) * a_t[p] * b_t[q],  t = 0..8  <->  j = 7..-1,  E_t = exp2(c_t * d2)
-struct AmScales {
-  float c[AM_LEVELS];
+struct AmLevels {
+  float lv[AM_LEVELS];  // -4^j as the device's powf returns it (am_levels_kernel)
 };
 
 constexpr int AMF_QTILE = 256;                      // partner points per tile in the phase-B kernels
 constexpr int AMF_F4_PER_PAIR = (3 + AM_LEVELS) / 2;  // 6 float4 per partner pair: 3 coords + 9 factors, 2 lanes each
 
-// evaluates the 9 level terms for two partner points at once (packed lanes = partners)
+// evaluates the 9 level terms for two partner points at once (packed lanes = partners):
+//     match = fma(rl_j * E_j, rr_j, match)   for j = 7 .. -1          (compiled approxmatch.cu:155-157)
+// EXACT: every E_j by MUFU.EX2 on ((d2*level)*log2e) -- bit-identical to the reference's terms.
+// !EXACT (fused cost/gradient path, nothing downstream amplifies the error): E_{j+1} = E_j^4 from 5 anchors.
+template <bool EXACT>
 __device__ __forceinline__ f32x2 am_match_pair(f32x2 d2, const f32x2 *bq /*9*/, const float *ap /*9*/,
-                                               const AmScales &sc) {
-  // anchors j = 7, 5, 3, 1, -1 (t = 0, 2, 4, 6, 8) by MUFU; j+1 from j by E^4 (t-1 from t)
+                                               const AmLevels &lv) {
   float lo, hi;
   f32x2 E[AM_LEVELS];
+  const f32x2 l2e2 = pack2(AM_LOG2E, AM_LOG2E);
 #pragma unroll
-  for (int t = 0; t < AM_LEVELS; t += 2) {
-    const f32x2 a = mul2(d2, pack2(sc.c[t], sc.c[t]));
+  for (int t = 0; t < AM_LEVELS; t += (EXACT ? 1 : 2)) {  // anchors j = 7, 5, 3, 1, -1 (t = 0, 2, 4, 6, 8)
+    const f32x2 a = mul2(mul2(d2, pack2(lv.lv[t], lv.lv[t])), l2e2);
     unpack2(a, lo, hi);
     E[t] = pack2(ex2_ftz(lo), ex2_ftz(hi));
   }
+  if (!EXACT) {
 #pragma unroll
-  for (int t = 2; t < AM_LEVELS; t += 2) {
-    const f32x2 s = mul2(E[t], E[t]);
-    E[t - 1] = mul2(s, s);
+    for (int t = 2; t < AM_LEVELS; t += 2) {
+      const f32x2 s = mul2(E[t], E[t]);
+      E[t - 1] = mul2(s, s);
+    }
   }
   f32x2 mt = 0ull;
 #pragma unroll
-  for (int t = 0; t < AM_LEVELS; ++t)  // same level order as the reference's `match += w` sequence
-    mt = fma2(mul2(E[t], pack2(ap[t], ap[t])), bq[t], mt);
+  for (int t = 0; t < AM_LEVELS; ++t) mt = fma2(mul2(pack2(ap[t], ap[t]), E[t]), bq[t], mt);
   return mt;
 }
 
@@ -164,7 +184,7 @@ __device__ __forceinline__ void amf_fill_tile(float *tf, const float *__restrict
 __global__ void __launch_bounds__(AM_THREADS)
 am_materialize_kernel(int n, int m, int lslab, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                       const float *__restrict__ fL, const float *__restrict__ fR, size_t fL_level_stride,
-                      size_t fR_level_stride, AmScales sc, float *__restrict__ match) {
+                      size_t fR_level_stride, AmLevels sc, float *__restrict__ match) {
   __shared__ float4 tile[AMF_QTILE / 2 * AMF_F4_PER_PAIR];
   const size_t cloud = blockIdx.z;
   xyz1 += cloud * (size_t)n * 3;
@@ -193,7 +213,7 @@ am_materialize_kernel(int n, int m, int lslab, const float *__restrict__ xyz1, c
                                    pack2(c4.z, c4.w), pack2(c5.x, c5.y), pack2(c5.z, c5.w)};
       const f32x2 d2 = sqdist2(pack2(c0.x, c0.y), pack2(c0.z, c0.w), pack2(c1.x, c1.y), npx, npy, npz);
       float m0, m1;
-      unpack2(am_match_pair(d2, bq, ap, sc), m0, m1);
+      unpack2(am_match_pair<true>(d2, bq, ap, sc), m0, m1);
       const int l = base + pr * 2;
       if (k < n) {
         match[(size_t)l * n + k] = m0;
@@ -209,7 +229,7 @@ am_materialize_kernel(int n, int m, int lslab, const float *__restrict__ xyz1, c
 __global__ void __launch_bounds__(AM_THREADS)
 am_costgrad_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
                    const float *__restrict__ fP, const float *__restrict__ fQ, size_t fP_level_stride,
-                   size_t fQ_level_stride, AmScales sc, float *__restrict__ cost_part, float *__restrict__ gradP) {
+                   size_t fQ_level_stride, AmLevels sc, float *__restrict__ cost_part, float *__restrict__ gradP) {
   __shared__ float4 tile[AMF_QTILE / 2 * AMF_F4_PER_PAIR];
   __shared__ float red[AM_THREADS / 32];
   const size_t cloud = blockIdx.y;
@@ -242,7 +262,7 @@ am_costgrad_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__
       const f32x2 dx = add2(pack2(c0.x, c0.y), npx), dy = add2(pack2(c0.z, c0.w), npy),
                   dz = add2(pack2(c1.x, c1.y), npz);
       const f32x2 d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-      const f32x2 mt = am_match_pair(d2, bq, ap, sc);
+      const f32x2 mt = am_match_pair<false>(d2, bq, ap, sc);
       float d0, d1;
       unpack2(d2, d0, d1);
       const f32x2 rinv = pack2(rsqrt_ftz(fmaxf(d0, 1e-20f)), rsqrt_ftz(fmaxf(d1, 1e-20f)));
@@ -409,19 +429,53 @@ struct AmWorkspace {
   size_t fL_level_stride = 0, fR_level_stride = 0;
 };
 
-static AmScales am_scales() {
-  AmScales s;
-  for (int t = 0; t < AM_LEVELS; ++t) {
-    const int j = 7 - t;
-    const float level = -powf(4.0f, (float)j);  // approxmatch.cu:25
-    s.c[t] = level * AM_LOG2E;
+// -4^j for j = 7..-1, evaluated ONCE per process by the device's own powf (the reference calls powf in the kernel,
+// approxmatch.cu:25).  Falls back to the host's powf when the first call happens under stream capture.
+static int am_levels(cudaStream_t st, AmLevels *out) {
+  static AmLevels cached;
+  static bool have = false;
+  if (!have) {
+    for (int t = 0; t < AM_LEVELS; ++t) cached.lv[t] = -powf(4.0f, (float)(7 - t));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      float *d = nullptr;
+      if (cudaMalloc((void **)&d, sizeof(float) * AM_LEVELS) == cudaSuccess) {
+        am_levels_kernel<<<1, 32, 0, st>>>(d);
+        AmLevels dev;
+        if (cudaMemcpyAsync(dev.lv, d, sizeof(float) * AM_LEVELS, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+            cudaStreamSynchronize(st) == cudaSuccess) {
+          cached = dev;
+          have = true;
+        }
+        cudaFree(d);
+      }
+      cudaGetLastError();
+    }
   }
-  return s;
+  *out = cached;
+  return 0;
 }
 
-// Phase A: runs the 27 sweeps; leaves remainL/remainR in temp and the per-level factors in ws.  Returns #launches.
+// keep freed workspace memory cached in the stream-ordered pool (default threshold 0 returns it to the OS at every
+// synchronisation, which makes the next cudaMallocAsync cost milliseconds)
+static void am_pool_setup() {
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+  done[dev] = true;
+}
+
+// Phase A: runs the 27 sweeps; leaves remainL/remainR in temp and the per-level factors in ws.
 static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, float *temp, AmWorkspace &ws,
-                    size_t extra_floats, cudaStream_t st, int *launches) {
+                    size_t extra_floats, const AmLevels &lv, cudaStream_t st, int *launches) {
+  am_pool_setup();
   const size_t nfl = (size_t)AM_LEVELS * b * n, nfr = (size_t)AM_LEVELS * b * m;
   cudaError_t e = cudaMallocAsync((void **)&ws.base, sizeof(float) * (nfl + nfr + extra_floats), st);
   if (e != cudaSuccess) return (int)e;
@@ -438,19 +492,19 @@ static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, f
     multiL = (float)(m / n);
     multiR = 1.f;
   }
-  const AmScales sc = am_scales();
   const size_t tstride = (size_t)(n + m) * 2;
   float *remainL = temp, *remainR = temp + n;
   am_init_kernel<<<dim3((n + m + 255) / 256, b), 256, 0, st>>>(n, m, temp, multiL, multiR);
-  const dim3 gk((n + AM_THREADS - 1) / AM_THREADS, b), gl((m + AM_THREADS - 1) / AM_THREADS, b);
+  const int per_cta = AM_THREADS * AM_P;
+  const dim3 gk((n + per_cta - 1) / per_cta, b), gl((m + per_cta - 1) / per_cta, b);
   for (int t = 0; t < AM_LEVELS; ++t) {
     float *fLt = ws.fL + (size_t)t * ws.fL_level_stride, *fRt = ws.fR + (size_t)t * ws.fR_level_stride;
-    am_rowsum_kernel<EPI_RATIO_L><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, remainR, tstride, sc.c[t], remainL,
-                                                             tstride, fLt, (size_t)n, nullptr);
-    am_rowsum_kernel<EPI_RATIO_R><<<gl, AM_THREADS, 0, st>>>(m, n, xyz2, xyz1, fLt, (size_t)n, sc.c[t], remainR,
-                                                             tstride, fRt, (size_t)m, nullptr);
-    am_rowsum_kernel<EPI_REMAIN_L><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, fRt, (size_t)m, sc.c[t], remainL,
-                                                              tstride, fLt, (size_t)n, fLt);
+    am_sweep_kernel<EPI_RATIO_L><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, remainR, tstride, lv.lv[t], remainL,
+                                                            tstride, fLt, (size_t)n);
+    am_sweep_kernel<EPI_RATIO_R><<<gl, AM_THREADS, 0, st>>>(m, n, xyz2, xyz1, fLt, (size_t)n, lv.lv[t], remainR,
+                                                            tstride, fRt, (size_t)m);
+    am_sweep_kernel<EPI_REMAIN_L><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, fRt, (size_t)m, lv.lv[t], remainL,
+                                                             tstride, fLt, (size_t)n);
   }
   am_export_temp_kernel<<<dim3((n + m + 255) / 256, b), 256, 0, st>>>(
       n, m, ws.fL + (size_t)(AM_LEVELS - 1) * ws.fL_level_stride, ws.fR + (size_t)(AM_LEVELS - 1) * ws.fR_level_stride,
@@ -470,13 +524,15 @@ extern "C" __attribute__((visibility("default"))) int pcc_approxmatch(int b, int
   if (b > 65535) return PCC_ENOTSUP;
   cudaStream_t st = (cudaStream_t)stream;
   AmWorkspace ws;
+  AmLevels lv;
+  am_levels(st, &lv);
   int launches = 0;
-  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, 0, st, &launches);
+  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, 0, lv, st, &launches);
   if (rc == 0) {
     const int lslab = 256;
     dim3 grid((n + AM_THREADS - 1) / AM_THREADS, (m + lslab - 1) / lslab, b);
     am_materialize_kernel<<<grid, AM_THREADS, 0, st>>>(n, m, lslab, xyz1, xyz2, ws.fL, ws.fR, ws.fL_level_stride,
-                                                       ws.fR_level_stride, am_scales(), match);
+                                                       ws.fR_level_stride, lv, match);
     ++launches;
     rc = (int)cudaGetLastError();
   }
@@ -498,11 +554,12 @@ extern "C" __attribute__((visibility("default"))) int pcc_matchcost_fused(int b,
   }
   if (b > 65535) return PCC_ENOTSUP;
   AmWorkspace ws;
+  AmLevels sc;
+  am_levels(st, &sc);
   int launches = 0;
   const int parts = (n + AM_THREADS - 1) / AM_THREADS;
-  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, (size_t)b * parts, st, &launches);
+  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, (size_t)b * parts, sc, st, &launches);
   if (rc == 0) {
-    const AmScales sc = am_scales();
     am_costgrad_kernel<<<dim3(parts, b), AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, ws.fL, ws.fR, ws.fL_level_stride,
                                                               ws.fR_level_stride, sc, cost ? ws.cost_part : nullptr,
                                                               grad1);
@@ -567,8 +624,8 @@ extern "C" __attribute__((visibility("default"))) int pcc_approxmatch_sweep(int 
                                                                             float level, pcc_stream_t stream) {
   if (b <= 0 || n <= 0 || m <= 0) return PCC_EINVAL;
   if (b > 65535) return PCC_ENOTSUP;
-  am_rowsum_kernel<EPI_RATIO_L><<<dim3((n + AM_THREADS - 1) / AM_THREADS, b), AM_THREADS, 0, (cudaStream_t)stream>>>(
-      n, m, xyz1, xyz2, weight, (size_t)m, level * AM_LOG2E, const_cast<float *>(remain), (size_t)n, ratio, (size_t)n,
-      nullptr);
+  const int per_cta = AM_THREADS * AM_P;
+  am_sweep_kernel<EPI_RATIO_L><<<dim3((n + per_cta - 1) / per_cta, b), AM_THREADS, 0, (cudaStream_t)stream>>>(
+      n, m, xyz1, xyz2, weight, (size_t)m, level, const_cast<float *>(remain), (size_t)n, ratio, (size_t)n);
   return finish_launch(1);
 }

@@ -16,46 +16,61 @@ namespace pcc {
 // forward
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NN_THREADS = 128;
+constexpr int NN_WARPS = NN_THREADS / 32;
+constexpr int NN_Q = 4;        // queries per lane: every reference loaded from shared memory is used 4 times
+constexpr int NN_QT = 32 * NN_Q;  // queries per CTA (each warp covers all of them against its share of the references)
 constexpr int NN_TILE = 2048;  // reference points per shared-memory tile (24 KiB)
 
-template <int Q>
-__global__ void __launch_bounds__(NN_THREADS)
+// CTA = 128 queries x all references.  The four warps split every reference tile into quarters; lane l of each warp
+// holds queries l, l+32, l+64, l+96, so one broadcast LDS.128 triple (8 references) feeds 32 distance evaluations.
+// The running minimum is tracked per group of 8 references (3-input FMNMX); the exact lowest index inside the
+// winning group is resolved at the end with the same arithmetic.
+__global__ void __launch_bounds__(NN_THREADS, 7)
 nn_fwd_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2,
               float *__restrict__ dist1, int *__restrict__ idx1, float *__restrict__ dist2,
               int *__restrict__ idx2) {
   __shared__ float4 tile[NN_TILE / 4 * 3];
+  __shared__ float mbest[NN_WARPS][NN_QT];
+  __shared__ int mgrp[NN_WARPS][NN_QT];
   const int dir = blockIdx.z;
   const int nq = dir ? m : n, nr = dir ? n : m;
-  const int q0 = blockIdx.x * (NN_THREADS * Q);
+  const int q0 = blockIdx.x * NN_QT;
   if (q0 >= nq) return;  // grid.x is sized for max(n, m); uniform per CTA
   const size_t cloud = blockIdx.y;
   const float *__restrict__ qp = (dir ? xyz2 : xyz1) + cloud * (size_t)nq * 3;
   const float *__restrict__ rp = (dir ? xyz1 : xyz2) + cloud * (size_t)nr * 3;
   float *__restrict__ dout = (dir ? dist2 : dist1) + cloud * (size_t)nq;
   int *__restrict__ iout = (dir ? idx2 : idx1) + cloud * (size_t)nq;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  float qx[Q], qy[Q], qz[Q], best[Q];
-  int grp[Q];
-  f32x2 nqx[Q], nqy[Q], nqz[Q];
+  float best[NN_Q];
+  int grp[NN_Q];
+  float sx[NN_Q], sy[NN_Q], sz[NN_Q];  // negated query coordinates (broadcast into both f32x2 lanes at use)
 #pragma unroll
-  for (int u = 0; u < Q; ++u) {
-    int j = min(q0 + u * NN_THREADS + (int)threadIdx.x, nq - 1);
-    qx[u] = qp[j * 3 + 0];
-    qy[u] = qp[j * 3 + 1];
-    qz[u] = qp[j * 3 + 2];
-    nqx[u] = pack2(-qx[u], -qx[u]);
-    nqy[u] = pack2(-qy[u], -qy[u]);
-    nqz[u] = pack2(-qz[u], -qz[u]);
+  for (int u = 0; u < NN_Q; ++u) {
+    const int j = min(q0 + u * 32 + lane, nq - 1);
+    sx[u] = -qp[j * 3 + 0];
+    sy[u] = -qp[j * 3 + 1];
+    sz[u] = -qp[j * 3 + 2];
     best[u] = __int_as_float(0x7f800000);
     grp[u] = 0;
   }
 
   float *tf = reinterpret_cast<float *>(tile);
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(rp) & 15) == 0;
   for (int base = 0; base < nr; base += NN_TILE) {
     const int cnt = min(NN_TILE, nr - base);
     const int cnt8 = (cnt + 7) & ~7;
     __syncthreads();  // previous tile fully consumed
-    for (int i = threadIdx.x; i < cnt8; i += NN_THREADS) {
+    const int nvec = vec_ok ? (cnt >> 2) : 0;  // groups of 4 points = 3 aligned float4 loads
+    const float4 *rv = reinterpret_cast<const float4 *>(rp + (size_t)base * 3);
+    for (int g = threadIdx.x; g < nvec; g += NN_THREADS) {
+      const float4 a = rv[g * 3], b = rv[g * 3 + 1], c = rv[g * 3 + 2];  // x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3
+      tile[g * 3 + 0] = make_float4(a.x, a.w, b.z, c.y);
+      tile[g * 3 + 1] = make_float4(a.y, b.x, b.w, c.z);
+      tile[g * 3 + 2] = make_float4(a.z, b.y, c.x, c.w);
+    }
+    for (int i = nvec * 4 + threadIdx.x; i < cnt8; i += NN_THREADS) {
       float x, y, z;
       if (i < cnt) {
         const float *p = rp + (size_t)(base + i) * 3;
@@ -71,17 +86,21 @@ nn_fwd_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restr
       tf[o + 8] = z;
     }
     __syncthreads();
+    const int ng = cnt8 >> 3;                       // groups of 8 references in this tile
+    const int per = (ng + NN_WARPS - 1) / NN_WARPS;  // contiguous share of this warp
+    const int gb = warp * per, ge = min(ng, gb + per);
     const int g0 = base >> 3;
-#pragma unroll 2
-    for (int g = 0; g < (cnt8 >> 3); ++g) {
+#pragma unroll 1
+    for (int g = gb; g < ge; ++g) {
       const float4 X0 = tile[g * 6 + 0], Y0 = tile[g * 6 + 1], Z0 = tile[g * 6 + 2];
       const float4 X1 = tile[g * 6 + 3], Y1 = tile[g * 6 + 4], Z1 = tile[g * 6 + 5];
 #pragma unroll
-      for (int u = 0; u < Q; ++u) {
-        f32x2 d01 = sqdist2(pack2(X0.x, X0.y), pack2(Y0.x, Y0.y), pack2(Z0.x, Z0.y), nqx[u], nqy[u], nqz[u]);
-        f32x2 d23 = sqdist2(pack2(X0.z, X0.w), pack2(Y0.z, Y0.w), pack2(Z0.z, Z0.w), nqx[u], nqy[u], nqz[u]);
-        f32x2 d45 = sqdist2(pack2(X1.x, X1.y), pack2(Y1.x, Y1.y), pack2(Z1.x, Z1.y), nqx[u], nqy[u], nqz[u]);
-        f32x2 d67 = sqdist2(pack2(X1.z, X1.w), pack2(Y1.z, Y1.w), pack2(Z1.z, Z1.w), nqx[u], nqy[u], nqz[u]);
+      for (int u = 0; u < NN_Q; ++u) {
+        const f32x2 nqx_u = pack2(sx[u], sx[u]), nqy_u = pack2(sy[u], sy[u]), nqz_u = pack2(sz[u], sz[u]);
+        f32x2 d01 = sqdist2(pack2(X0.x, X0.y), pack2(Y0.x, Y0.y), pack2(Z0.x, Z0.y), nqx_u, nqy_u, nqz_u);
+        f32x2 d23 = sqdist2(pack2(X0.z, X0.w), pack2(Y0.z, Y0.w), pack2(Z0.z, Z0.w), nqx_u, nqy_u, nqz_u);
+        f32x2 d45 = sqdist2(pack2(X1.x, X1.y), pack2(Y1.x, Y1.y), pack2(Z1.x, Z1.y), nqx_u, nqy_u, nqz_u);
+        f32x2 d67 = sqdist2(pack2(X1.z, X1.w), pack2(Y1.z, Y1.w), pack2(Z1.z, Z1.w), nqx_u, nqy_u, nqz_u);
         float a0, a1, a2, a3, a4, a5, a6, a7;
         unpack2(d01, a0, a1);
         unpack2(d23, a2, a3);
@@ -96,30 +115,44 @@ nn_fwd_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restr
       }
     }
   }
-
-  // Resolve the exact index inside the winning group of 8 (identical arithmetic => identical bits).
 #pragma unroll
-  for (int u = 0; u < Q; ++u) {
-    const int j = q0 + u * NN_THREADS + (int)threadIdx.x;
-    if (j >= nq) continue;
-    int bi = -1;
-    const int r0 = grp[u] * 8;
-#pragma unroll
-    for (int e = 7; e >= 0; --e) {
-      const int r = r0 + e;
-      if (r < nr) {
-        const float d = sqdist1(qx[u], qy[u], qz[u], rp[(size_t)r * 3], rp[(size_t)r * 3 + 1], rp[(size_t)r * 3 + 2]);
-        if (d == best[u]) bi = r;
-      }
-    }
-    float bd = best[u];
-    if (bi < 0) {  // nothing compared below +inf (NaN / inf inputs): the reference keeps element 0 (nndistance.cu:26)
-      bi = 0;
-      bd = sqdist1(qx[u], qy[u], qz[u], rp[0], rp[1], rp[2]);
-    }
-    dout[j] = bd;
-    iout[j] = bi;
+  for (int u = 0; u < NN_Q; ++u) {
+    mbest[warp][u * 32 + lane] = best[u];
+    mgrp[warp][u * 32 + lane] = grp[u];
   }
+  __syncthreads();
+
+  // thread t finishes query q0 + t: merge the four warps (lowest group on equal minima), then resolve the exact
+  // index inside the winning group of 8 (identical arithmetic => identical bits).
+  const int j = q0 + (int)threadIdx.x;
+  if (j >= nq) return;
+  float bd = mbest[0][threadIdx.x];
+  int bg = mgrp[0][threadIdx.x];
+#pragma unroll
+  for (int w = 1; w < NN_WARPS; ++w) {
+    const float d = mbest[w][threadIdx.x];
+    const int g = mgrp[w][threadIdx.x];
+    if (d < bd || (d == bd && g < bg)) {
+      bd = d;
+      bg = g;
+    }
+  }
+  const float qx = qp[j * 3 + 0], qy = qp[j * 3 + 1], qz = qp[j * 3 + 2];
+  int bi = -1;
+#pragma unroll
+  for (int e = 7; e >= 0; --e) {
+    const int r = bg * 8 + e;
+    if (r < nr) {
+      const float d = sqdist1(qx, qy, qz, rp[(size_t)r * 3], rp[(size_t)r * 3 + 1], rp[(size_t)r * 3 + 2]);
+      if (d == bd) bi = r;
+    }
+  }
+  if (bi < 0) {  // nothing compared below +inf (NaN / inf inputs): the reference keeps element 0 (nndistance.cu:26)
+    bi = 0;
+    bd = sqdist1(qx, qy, qz, rp[0], rp[1], rp[2]);
+  }
+  dout[j] = bd;
+  iout[j] = bi;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -323,8 +356,8 @@ extern "C" __attribute__((visibility("default"))) int pcc_nndistance(int b, int 
   if (b == 0 || n == 0 || m == 0) return PCC_OK;  // nothing to compare against: outputs are left untouched
   if (b > 65535) return PCC_ENOTSUP;
   const int mx = n > m ? n : m;
-  dim3 grid((mx + NN_THREADS - 1) / NN_THREADS, b, 2);
-  nn_fwd_kernel<1><<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, xyz, m, xyz2, result, result_i, result2,
+  dim3 grid((mx + NN_QT - 1) / NN_QT, b, 2);
+  nn_fwd_kernel<<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, xyz, m, xyz2, result, result_i, result2,
                                                                     result2_i);
   return finish_launch(1);
 }

@@ -54,7 +54,9 @@ def test_approxmatch_vs_reference_cuda(cuda, ref_sl, maker, b, n, m):
     rcost = ref_sl.MatchCost(ta, tc, rmatch)
     rg1, rg2 = ref_sl.MatchCostGrad(ta, tc, rmatch)
     match, _ = ApproxMatch(ta, tc)
-    assert (match - rmatch).abs().max().item() < 2e-5 * max(1.0, rmatch.max().item())
+    # the solver reproduces the reference's arithmetic and summation order: match agrees to rounding level
+    assert (match - rmatch).abs().max().item() < 1e-6 * max(1.0, rmatch.max().item())
+    assert (match == rmatch).float().mean().item() > 0.99
     assert rel_err(MatchCost(ta, tc, match).cpu().numpy(), rcost.cpu().numpy()) < TOL
     g1, g2 = MatchCostGrad(ta, tc, match)
     assert rel_err(g1.cpu().numpy(), rg1.cpu().numpy()) < TOL and rel_err(g2.cpu().numpy(), rg2.cpu().numpy()) < TOL
