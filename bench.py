@@ -236,7 +236,7 @@ def run_b200(args) -> None:
 
     def sweep():
         _lib.check(lib.pcc_approxmatch_sweep(B_PER_GPU, N_POINTS, N_POINTS, recon_d.data_ptr(), ref_d.data_ptr(),
-                                             ones.data_ptr(), ones.data_ptr(), ratio.data_ptr(), -16.0, st), "sweep")
+                                             ones.data_ptr(), ones.data_ptr(), ratio.data_ptr(), -16.0, 0, st), "sweep")
 
     sweep_ms = ev_time(sweep, 50)
     pairs = B_PER_GPU * N_POINTS * N_POINTS

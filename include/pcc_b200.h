@@ -78,7 +78,8 @@ int pcc_matchcost_fused(int b, int n, int m, const float *xyz1, const float *xyz
  * EMD path -- exactly as pcc_approxmatch / pcc_matchcost_fused launch it for sweep 1 of a level
  * (approxmatch.cu:29-62): ratio[b,n] = remain[b,n] / (1e-9 + sum_l exp(level*|x1_k-x2_l|^2) * weight[b,l]). */
 int pcc_approxmatch_sweep(int b, int n, int m, const float *xyz1, const float *xyz2, const float *weight,
-                          const float *remain, float *ratio, float level, pcc_stream_t stream);
+                          const float *remain, float *ratio, float level, int points_per_thread /* 0 = default */,
+                          pcc_stream_t stream);
 
 /* ---- kNN graph (DGCNN) ------------------------------------------------------------------------------
  * Replaces the KeOps reduction behind `pykeops_knn` / `knn` (src/utils/neighbour_ops.py:63-82):

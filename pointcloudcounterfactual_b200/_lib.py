@@ -28,7 +28,7 @@ _SIGNATURES = {
     "pcc_matchcost": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pcc_matchcostgrad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_matchcost_fused": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "pcc_approxmatch_sweep": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp]),
+    "pcc_approxmatch_sweep": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, _i, _vp]),
     "pcc_knn": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pcc_argkmin": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pcc_emd_forward": (_i, [_i, _i, _i] + [_vp] * 14 + [ctypes.c_float, _i, _vp]),

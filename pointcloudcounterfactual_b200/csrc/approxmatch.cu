@@ -20,7 +20,7 @@ namespace pcc {
 
 constexpr int AM_LEVELS = 9;  // j = 7, 6, ..., -1  (approxmatch.cu:24; the j == -2 / level 0 sweep is dead code)
 constexpr int AM_THREADS = 128;
-constexpr int AM_P = 4;          // points owned by one thread in a sweep (two packed f32x2 lanes pairs)
+constexpr int AM_P_DEFAULT = 2;  // points owned by one thread in a sweep (tuned on B200)
 constexpr int AM_QTILE = 2048;   // partner points per shared-memory tile in the sweep kernel (32 KiB)
 constexpr float AM_LOG2E = 1.4426950408889634f;  // 0f3FB8AA3B, the constant __expf multiplies by
 
@@ -46,7 +46,7 @@ __global__ void am_levels_kernel(float *levels) {
 // rounding differences ~1000x into match / gradients, so the summation order and every rounding are kept; the
 // parallelism is over points only (each thread owns AM_P points, packed two per f32x2 lane pair, so that one
 // broadcast LDS.128 of a partner feeds four exponentials and the SFU pipe, not shared memory, is the limit).
-template <int EPI>
+template <int EPI, int AM_P>
 __global__ void __launch_bounds__(AM_THREADS)
 am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
                 const float *__restrict__ wQ, size_t wQ_stride, float level, float *__restrict__ remainP,
@@ -71,7 +71,10 @@ am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__res
     acc[h] = pack2(init, init);
     rl2[h] = (EPI == EPI_REMAIN_L) ? pack2(rat[a], rat[b]) : 0ull;  // ratioL[k] (approxmatch.cu:146)
   }
-  const f32x2 lvl2 = pack2(level, level), l2e2 = pack2(AM_LOG2E, AM_LOG2E);
+  // level = -4^j is a power of two, so d2*level is exact and ((d2*level)*log2e) == d2*(level*log2e) bit for bit:
+  // one multiply reproduces the reference's two (approxmatch.cu:55 + __expf)
+  const float lc = level * AM_LOG2E;
+  const f32x2 lc2 = pack2(lc, lc);
 
   for (int base = 0; base < nQ; base += AM_QTILE) {
     const int cnt = min(AM_QTILE, nQ - base);
@@ -89,7 +92,7 @@ am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__res
       for (int h = 0; h < AM_P / 2; ++h) {
         const f32x2 dx = add2(qx, npx[h]), dy = add2(qy, npy[h]), dz = add2(qz, npz[h]);
         const f32x2 d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-        const f32x2 arg = mul2(mul2(d2, lvl2), l2e2);
+        const f32x2 arg = mul2(d2, lc2);
         float a0, a1;
         unpack2(arg, a0, a1);
         f32x2 E = pack2(ex2_ftz(a0), ex2_ftz(a1));
@@ -117,6 +120,87 @@ am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__res
       } else {  // approxmatch.cu:161-162
         rem[p] = fmaxf(0.0f, rem[p] - s[e]);
       }
+    }
+  }
+}
+
+// Fused sweep: sweep 3 of level A (remainL update, approxmatch.cu:130-163) and sweep 1 of the NEXT level B
+// (ratioL, :29-62) walk the same (own point k) x (all partners l) loop, so the distance is evaluated once and feeds
+// two exponentials -- 10 instead of 16 FMA-pipe operations per pair for the two sweeps, one partner load instead of two.
+// Each accumulator still sees exactly the reference's operation sequence, so the results stay bit-faithful.
+template <int AM_P>
+__global__ void __launch_bounds__(AM_THREADS)
+am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
+                  const float *__restrict__ ratioR_A, size_t ratioR_stride, const float *__restrict__ remainR,
+                  size_t remainR_stride, float levelA, float levelB, float *__restrict__ remainL,
+                  size_t remainL_stride, const float *__restrict__ ratioL_A, float *__restrict__ ratioL_B,
+                  size_t ratioL_stride) {
+  __shared__ float4 tile[AM_QTILE];  // (x, y, z, ratioR_A) per partner
+  __shared__ float wB[AM_QTILE];     // remainR per partner
+  const size_t cloud = blockIdx.y;
+  xP += cloud * (size_t)nP * 3;
+  xQ += cloud * (size_t)nQ * 3;
+  ratioR_A += cloud * ratioR_stride;
+  remainR += cloud * remainR_stride;
+  float *rem = remainL + cloud * remainL_stride;
+  const float *ratA = ratioL_A + cloud * ratioL_stride;
+  float *ratB = ratioL_B + cloud * ratioL_stride;
+  const int p0 = blockIdx.x * (AM_THREADS * AM_P) + threadIdx.x;
+  f32x2 npx[AM_P / 2], npy[AM_P / 2], npz[AM_P / 2], acc3[AM_P / 2], acc1[AM_P / 2], rl2[AM_P / 2];
+#pragma unroll
+  for (int h = 0; h < AM_P / 2; ++h) {
+    const int a = min(p0 + (2 * h) * AM_THREADS, nP - 1), b = min(p0 + (2 * h + 1) * AM_THREADS, nP - 1);
+    npx[h] = pack2(-xP[a * 3], -xP[b * 3]);
+    npy[h] = pack2(-xP[a * 3 + 1], -xP[b * 3 + 1]);
+    npz[h] = pack2(-xP[a * 3 + 2], -xP[b * 3 + 2]);
+    acc3[h] = 0ull;
+    acc1[h] = pack2(1e-9f, 1e-9f);
+    rl2[h] = pack2(ratA[a], ratA[b]);
+  }
+  const float lcA = levelA * AM_LOG2E, lcB = levelB * AM_LOG2E;
+  const f32x2 lcA2 = pack2(lcA, lcA), lcB2 = pack2(lcB, lcB);
+
+  for (int base = 0; base < nQ; base += AM_QTILE) {
+    const int cnt = min(AM_QTILE, nQ - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += AM_THREADS) {
+      const float *q = xQ + (size_t)(base + i) * 3;
+      tile[i] = make_float4(q[0], q[1], q[2], ratioR_A[base + i]);
+      wB[i] = remainR[base + i];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int l = 0; l < cnt; ++l) {
+      const float4 q = tile[l];
+      const float w1 = wB[l];
+      const f32x2 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z), qw3 = pack2(q.w, q.w),
+                  qw1 = pack2(w1, w1);
+#pragma unroll
+      for (int h = 0; h < AM_P / 2; ++h) {
+        const f32x2 dx = add2(qx, npx[h]), dy = add2(qy, npy[h]), dz = add2(qz, npz[h]);
+        const f32x2 d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+        float a0, a1, b0, b1;
+        unpack2(mul2(d2, lcA2), a0, a1);
+        unpack2(mul2(d2, lcB2), b0, b1);
+        const f32x2 EA = pack2(ex2_ftz(a0), ex2_ftz(a1));
+        const f32x2 EB = pack2(ex2_ftz(b0), ex2_ftz(b1));
+        acc3[h] = fma2(mul2(rl2[h], EA), qw3, acc3[h]);
+        acc1[h] = fma2(EB, qw1, acc1[h]);
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < AM_P / 2; ++h) {
+    float s3[2], s1[2];
+    unpack2(acc3[h], s3[0], s3[1]);
+    unpack2(acc1[h], s1[0], s1[1]);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int p = p0 + (2 * h + e) * AM_THREADS;
+      if (p >= nP) continue;
+      const float r = fmaxf(0.0f, rem[p] - s3[e]);  // approxmatch.cu:161-162 (level A)
+      rem[p] = r;
+      ratB[p] = r / s1[e];                          // approxmatch.cu:60-61   (level B)
     }
   }
 }
@@ -495,21 +579,32 @@ static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, f
   const size_t tstride = (size_t)(n + m) * 2;
   float *remainL = temp, *remainR = temp + n;
   am_init_kernel<<<dim3((n + m + 255) / 256, b), 256, 0, st>>>(n, m, temp, multiL, multiR);
-  const int per_cta = AM_THREADS * AM_P;
+  constexpr int P = AM_P_DEFAULT;
+  const int per_cta = AM_THREADS * P;
   const dim3 gk((n + per_cta - 1) / per_cta, b), gl((m + per_cta - 1) / per_cta, b);
+  // level t: sweep 1 (ratioL_t) -> sweep 2 (ratioR_t, remainR) -> sweep 3 (remainL); sweep 3 of level t-1 and
+  // sweep 1 of level t share one fused launch.
+  auto fL = [&](int t) { return ws.fL + (size_t)t * ws.fL_level_stride; };
+  auto fR = [&](int t) { return ws.fR + (size_t)t * ws.fR_level_stride; };
   for (int t = 0; t < AM_LEVELS; ++t) {
-    float *fLt = ws.fL + (size_t)t * ws.fL_level_stride, *fRt = ws.fR + (size_t)t * ws.fR_level_stride;
-    am_sweep_kernel<EPI_RATIO_L><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, remainR, tstride, lv.lv[t], remainL,
-                                                            tstride, fLt, (size_t)n);
-    am_sweep_kernel<EPI_RATIO_R><<<gl, AM_THREADS, 0, st>>>(m, n, xyz2, xyz1, fLt, (size_t)n, lv.lv[t], remainR,
-                                                            tstride, fRt, (size_t)m);
-    am_sweep_kernel<EPI_REMAIN_L><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, fRt, (size_t)m, lv.lv[t], remainL,
-                                                             tstride, fLt, (size_t)n);
+    if (t == 0) {
+      am_sweep_kernel<EPI_RATIO_L, P><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, remainR, tstride, lv.lv[0], remainL,
+                                                                 tstride, fL(0), (size_t)n);
+    } else {
+      am_sweep31_kernel<P><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, fR(t - 1), (size_t)m, remainR, tstride,
+                                                      lv.lv[t - 1], lv.lv[t], remainL, tstride, fL(t - 1), fL(t),
+                                                      (size_t)n);
+    }
+    am_sweep_kernel<EPI_RATIO_R, P><<<gl, AM_THREADS, 0, st>>>(m, n, xyz2, xyz1, fL(t), (size_t)n, lv.lv[t], remainR,
+                                                               tstride, fR(t), (size_t)m);
   }
+  am_sweep_kernel<EPI_REMAIN_L, P><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, fR(AM_LEVELS - 1), (size_t)m,
+                                                              lv.lv[AM_LEVELS - 1], remainL, tstride, fL(AM_LEVELS - 1),
+                                                              (size_t)n);
   am_export_temp_kernel<<<dim3((n + m + 255) / 256, b), 256, 0, st>>>(
       n, m, ws.fL + (size_t)(AM_LEVELS - 1) * ws.fL_level_stride, ws.fR + (size_t)(AM_LEVELS - 1) * ws.fR_level_stride,
       temp);
-  *launches += 2 + 3 * AM_LEVELS;
+  *launches += 2 + 2 * AM_LEVELS + 1;
   return (int)cudaGetLastError();
 }
 
@@ -618,14 +713,28 @@ extern "C" __attribute__((visibility("default"))) int pcc_matchcostgrad(int b, i
   return finish_launch(2);
 }
 
+template <int P>
+static void launch_sweep_variant(int b, int n, int m, const float *xyz1, const float *xyz2, const float *weight,
+                                 const float *remain, float *ratio, float level, cudaStream_t st) {
+  const int per_cta = AM_THREADS * P;
+  am_sweep_kernel<EPI_RATIO_L, P><<<dim3((n + per_cta - 1) / per_cta, b), AM_THREADS, 0, st>>>(
+      n, m, xyz1, xyz2, weight, (size_t)m, level, const_cast<float *>(remain), (size_t)n, ratio, (size_t)n);
+}
+
 extern "C" __attribute__((visibility("default"))) int pcc_approxmatch_sweep(int b, int n, int m, const float *xyz1,
                                                                             const float *xyz2, const float *weight,
                                                                             const float *remain, float *ratio,
-                                                                            float level, pcc_stream_t stream) {
+                                                                            float level, int points_per_thread,
+                                                                            pcc_stream_t stream) {
   if (b <= 0 || n <= 0 || m <= 0) return PCC_EINVAL;
   if (b > 65535) return PCC_ENOTSUP;
-  const int per_cta = AM_THREADS * AM_P;
-  am_sweep_kernel<EPI_RATIO_L><<<dim3((n + per_cta - 1) / per_cta, b), AM_THREADS, 0, (cudaStream_t)stream>>>(
-      n, m, xyz1, xyz2, weight, (size_t)m, level, const_cast<float *>(remain), (size_t)n, ratio, (size_t)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (points_per_thread) {
+    case 0: launch_sweep_variant<AM_P_DEFAULT>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
+    case 2: launch_sweep_variant<2>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
+    case 4: launch_sweep_variant<4>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
+    case 6: launch_sweep_variant<6>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
+    default: return PCC_ENOTSUP;
+  }
   return finish_launch(1);
 }

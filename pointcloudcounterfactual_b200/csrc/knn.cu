@@ -153,6 +153,198 @@ knn_kernel(int c, int nq, int nr, int k, const float *__restrict__ qin, const fl
   }
 }
 
+// ---- xyz (C == 3) fast path --------------------------------------------------------------------------------------
+// One thread per query, two passes over the reference tile in shared memory (groups of four points: float4 X, Y, Z):
+//   pass 1  distances (packed, canonical order fma(dz,dz,fma(dy,dy,dx*dx))) reduced to one minimum per group of G
+//           references; the K smallest group minima are kept in a branch-free sorted register list (2 FMNMX per slot).
+//           The k-th smallest group minimum tau is an upper bound of the k-th smallest distance (each of those k
+//           groups holds at least one reference <= tau).
+//   pass 2  distances again; references with d <= tau (about k plus a few) are appended to a per-thread buffer in
+//           shared memory in ascending index order, the buffer is stably insertion-sorted by distance => ascending
+//           (distance, index), self included.  A full buffer (massive exact ties) is pruned to its best k in place.
+constexpr int K3_THREADS = 128;
+constexpr int K3_TILE = 2048;  // references per shared-memory tile (24 KiB)
+constexpr int K3_CAP = 48;     // candidate slots per query
+
+__device__ __forceinline__ f32x2 knn_sqdist2(f32x2 rx, f32x2 ry, f32x2 rz, f32x2 nqx, f32x2 nqy, f32x2 nqz) {
+  const f32x2 dx = add2(rx, nqx), dy = add2(ry, nqy), dz = add2(rz, nqz);
+  return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));  // channel order x, y, z
+}
+
+template <int K>
+__global__ void __launch_bounds__(K3_THREADS)
+knn3_kernel(int n, int k, int groups8, const float *__restrict__ x, int64_t *__restrict__ idx_out,
+            float *__restrict__ dist_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *tile = reinterpret_cast<float4 *>(smem_raw);                                   // K3_TILE/4*3 float4
+  float *bufd = reinterpret_cast<float *>(smem_raw + sizeof(float4) * (K3_TILE / 4 * 3));  // [K3_CAP][K3_THREADS]
+  int *bufi = reinterpret_cast<int *>(bufd + K3_CAP * K3_THREADS);
+
+  const int tid = threadIdx.x;
+  const size_t cloud = blockIdx.y;
+  const float *__restrict__ xr = x + cloud * (size_t)3 * n;  // rows: x[0][:], x[1][:], x[2][:]
+  const int q0 = blockIdx.x * K3_THREADS;
+  const int q = min(q0 + tid, n - 1);
+  const float INF = __int_as_float(0x7f800000);
+  const float qx = xr[q], qy = xr[(size_t)n + q], qz = xr[(size_t)2 * n + q];
+  const f32x2 nqx = pack2(-qx, -qx), nqy = pack2(-qy, -qy), nqz = pack2(-qz, -qz);
+  float *tf = reinterpret_cast<float *>(tile);
+
+  float L[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) L[i] = INF;
+  float tau = INF;
+  int cnt = 0;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    float gacc = INF;
+    int gfill = 0;
+    for (int base = 0; base < n; base += K3_TILE) {
+      const int tcnt = min(K3_TILE, n - base);
+      const int tcnt8 = (tcnt + 7) & ~7;
+      if (pass == 0 || n > K3_TILE) {  // a single tile stays resident for pass 2
+        __syncthreads();
+        for (int i = tid; i < tcnt8; i += K3_THREADS) {
+          float vx = INF, vy = INF, vz = INF;  // padding: distance +inf
+          if (i < tcnt) {
+            vx = xr[base + i];
+            vy = xr[(size_t)n + base + i];
+            vz = xr[(size_t)2 * n + base + i];
+          }
+          const int o = (i >> 2) * 12 + (i & 3);
+          tf[o] = vx;
+          tf[o + 4] = vy;
+          tf[o + 8] = vz;
+        }
+        __syncthreads();
+      }
+      for (int g = 0; g < (tcnt8 >> 3); ++g) {
+        const float4 X0 = tile[g * 6 + 0], Y0 = tile[g * 6 + 1], Z0 = tile[g * 6 + 2];
+        const float4 X1 = tile[g * 6 + 3], Y1 = tile[g * 6 + 4], Z1 = tile[g * 6 + 5];
+        float a[8];
+        unpack2(knn_sqdist2(pack2(X0.x, X0.y), pack2(Y0.x, Y0.y), pack2(Z0.x, Z0.y), nqx, nqy, nqz), a[0], a[1]);
+        unpack2(knn_sqdist2(pack2(X0.z, X0.w), pack2(Y0.z, Y0.w), pack2(Z0.z, Z0.w), nqx, nqy, nqz), a[2], a[3]);
+        unpack2(knn_sqdist2(pack2(X1.x, X1.y), pack2(Y1.x, Y1.y), pack2(Z1.x, Z1.y), nqx, nqy, nqz), a[4], a[5]);
+        unpack2(knn_sqdist2(pack2(X1.z, X1.w), pack2(Y1.z, Y1.w), pack2(Z1.z, Z1.w), nqx, nqy, nqz), a[6], a[7]);
+        if (pass == 0) {
+          float mn = fminf(fminf(a[0], a[1]), gacc);
+          mn = fminf(fminf(a[2], a[3]), mn);
+          mn = fminf(fminf(a[4], a[5]), mn);
+          gacc = fminf(fminf(a[6], a[7]), mn);
+          if (++gfill == groups8) {  // uniform: a group of G = 8*groups8 references is complete
+            float c = gacc;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              const float lo = fminf(L[i], c);
+              c = fmaxf(L[i], c);
+              L[i] = lo;
+            }
+            gacc = INF;
+            gfill = 0;
+          }
+        } else {
+          const int r0 = base + g * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (a[e] <= tau) {
+              if (cnt == K3_CAP) {  // rare: prune the buffer to its best k (stable), then accept only d < tau
+                for (int s1 = 1; s1 < cnt; ++s1) {
+                  const float v = bufd[s1 * K3_THREADS + tid];
+                  const int vi = bufi[s1 * K3_THREADS + tid];
+                  int pp = s1;
+                  while (pp > 0 && bufd[(pp - 1) * K3_THREADS + tid] > v) {
+                    bufd[pp * K3_THREADS + tid] = bufd[(pp - 1) * K3_THREADS + tid];
+                    bufi[pp * K3_THREADS + tid] = bufi[(pp - 1) * K3_THREADS + tid];
+                    --pp;
+                  }
+                  bufd[pp * K3_THREADS + tid] = v;
+                  bufi[pp * K3_THREADS + tid] = vi;
+                }
+                cnt = k;
+                const float kth = bufd[(k - 1) * K3_THREADS + tid];
+                tau = (kth > 0.f) ? __int_as_float(__float_as_int(kth) - 1) : -1.f;  // largest float below kth
+              }
+              if (a[e] <= tau) {
+                bufd[cnt * K3_THREADS + tid] = a[e];
+                bufi[cnt * K3_THREADS + tid] = r0 + e;
+                ++cnt;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (pass == 0) {
+      if (gfill > 0) {  // last, partial group
+        float c = gacc;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const float lo = fminf(L[i], c);
+          c = fmaxf(L[i], c);
+          L[i] = lo;
+        }
+      }
+      // tau = L[k-1] = max(L[0..k-1]) (the list is ascending); written as a predicated max so that the list is
+      // never indexed dynamically (which would move it to local memory).  +inf when fewer than k groups exist.
+      tau = 0.f;
+#pragma unroll
+      for (int i = 0; i < K; ++i) tau = (i < k) ? fmaxf(tau, L[i]) : tau;
+    }
+  }
+
+  // stable insertion sort of the candidates by distance (they were appended in ascending index order)
+  for (int s1 = 1; s1 < cnt; ++s1) {
+    const float v = bufd[s1 * K3_THREADS + tid];
+    const int vi = bufi[s1 * K3_THREADS + tid];
+    int pp = s1;
+    while (pp > 0 && bufd[(pp - 1) * K3_THREADS + tid] > v) {
+      bufd[pp * K3_THREADS + tid] = bufd[(pp - 1) * K3_THREADS + tid];
+      bufi[pp * K3_THREADS + tid] = bufi[(pp - 1) * K3_THREADS + tid];
+      --pp;
+    }
+    bufd[pp * K3_THREADS + tid] = v;
+    bufi[pp * K3_THREADS + tid] = vi;
+  }
+  for (int t = cnt; t < k; ++t) {  // only with NaN / inf inputs
+    bufd[t * K3_THREADS + tid] = INF;
+    bufi[t * K3_THREADS + tid] = 0;
+  }
+  __syncthreads();
+  const int nvalid = min(K3_THREADS, n - q0);
+  const size_t obase = (cloud * (size_t)n + q0) * k;
+  for (int e = tid; e < nvalid * k; e += K3_THREADS) {
+    const int qq = e / k, t = e - qq * k;
+    idx_out[obase + e] = (int64_t)bufi[t * K3_THREADS + qq];
+    if (dist_out) dist_out[obase + e] = bufd[t * K3_THREADS + qq];
+  }
+}
+
+template <int K>
+static int launch_knn3_k(int b, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
+  const size_t smem = sizeof(float4) * (K3_TILE / 4 * 3) + (size_t)K3_CAP * K3_THREADS * (sizeof(float) + sizeof(int));
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(knn3_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  // group size G = 8 * groups8: as large as possible while leaving at least ~3k groups (tight tau, few candidates)
+  int groups8 = 4;
+  while (groups8 > 1 && (n / (8 * groups8)) < 3 * k) groups8 >>= 1;
+  dim3 grid((n + K3_THREADS - 1) / K3_THREADS, b);
+  knn3_kernel<K><<<grid, K3_THREADS, smem, st>>>(n, k, groups8, x, idx, dist);
+  return finish_launch(1);
+}
+
+static int launch_knn3(int b, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
+  if (k <= 4) return launch_knn3_k<4>(b, n, k, x, idx, dist, st);
+  if (k <= 8) return launch_knn3_k<8>(b, n, k, x, idx, dist, st);
+  if (k <= 16) return launch_knn3_k<16>(b, n, k, x, idx, dist, st);
+  if (k <= 20) return launch_knn3_k<20>(b, n, k, x, idx, dist, st);
+  if (k <= 24) return launch_knn3_k<24>(b, n, k, x, idx, dist, st);
+  return launch_knn3_k<32>(b, n, k, x, idx, dist, st);
+}
+
 template <bool PM>
 static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const float *r, int64_t *idx,
                       float *dist, cudaStream_t st) {
@@ -160,6 +352,7 @@ static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const
   if (k > nr) return PCC_EINVAL;  // torch.topk / argKmin cannot return more neighbours than points
   if (k > PCC_KNN_MAX_K || b > 65535) return PCC_ENOTSUP;
   if (b == 0 || nq == 0) return PCC_OK;
+  if (!PM && c == 3 && q == r && nq == nr && k <= 32 && k <= K3_CAP / 2) return launch_knn3(b, nq, k, q, idx, dist, st);
   const size_t smem = sizeof(KnnSmem) + (size_t)k * KN_TQ * (sizeof(float) + sizeof(int));
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
