@@ -46,11 +46,27 @@ __global__ void am_levels_kernel(float *levels) {
 // rounding differences ~1000x into match / gradients, so the summation order and every rounding are kept; the
 // parallelism is over points only (each thread owns AM_P points, packed two per f32x2 lane pair, so that one
 // broadcast LDS.128 of a partner feeds four exponentials and the SFU pipe, not shared memory, is the limit).
-template <int EPI, int AM_P>
+// exp2((|x_q - x_p|^2) * lc) for the AM_P points of this thread (two per f32x2) against partner (qx,qy,qz)
+template <int H>
+__device__ __forceinline__ void am_exp_terms(const float4 q, const f32x2 *npx, const f32x2 *npy, const f32x2 *npz,
+                                             f32x2 lc2, f32x2 *E) {
+  const f32x2 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z);
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    const f32x2 dx = add2(qx, npx[h]), dy = add2(qy, npy[h]), dz = add2(qz, npz[h]);
+    const f32x2 d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+    float a0, a1;
+    unpack2(mul2(d2, lc2), a0, a1);
+    E[h] = pack2(ex2_ftz(a0), ex2_ftz(a1));
+  }
+}
+
+template <int EPI, int AM_P, int UNROLL = 16>
 __global__ void __launch_bounds__(AM_THREADS)
 am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
                 const float *__restrict__ wQ, size_t wQ_stride, float level, float *__restrict__ remainP,
                 size_t remain_stride, float *__restrict__ ratioP, size_t ratio_stride) {
+  constexpr int H = AM_P / 2, U = UNROLL;
   __shared__ float4 tile[AM_QTILE];  // (x, y, z, w) per partner
   const size_t cloud = blockIdx.y;
   xP += cloud * (size_t)nP * 3;
@@ -60,9 +76,9 @@ am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__res
   float *rat = ratioP + cloud * ratio_stride;
   // thread t of block bx owns points p0 + t + u*AM_THREADS, u = 0..AM_P-1
   const int p0 = blockIdx.x * (AM_THREADS * AM_P) + threadIdx.x;
-  f32x2 npx[AM_P / 2], npy[AM_P / 2], npz[AM_P / 2], acc[AM_P / 2], rl2[AM_P / 2];
+  f32x2 npx[H], npy[H], npz[H], acc[H], rl2[H];
 #pragma unroll
-  for (int h = 0; h < AM_P / 2; ++h) {
+  for (int h = 0; h < H; ++h) {
     const int a = min(p0 + (2 * h) * AM_THREADS, nP - 1), b = min(p0 + (2 * h + 1) * AM_THREADS, nP - 1);
     npx[h] = pack2(-xP[a * 3], -xP[b * 3]);
     npy[h] = pack2(-xP[a * 3 + 1], -xP[b * 3 + 1]);
@@ -78,31 +94,44 @@ am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__res
 
   for (int base = 0; base < nQ; base += AM_QTILE) {
     const int cnt = min(AM_QTILE, nQ - base);
+    const int cntU = (cnt + U - 1) / U * U;
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt; i += AM_THREADS) {
-      const float *q = xQ + (size_t)(base + i) * 3;
-      tile[i] = make_float4(q[0], q[1], q[2], wQ[base + i]);
+    for (int i = threadIdx.x; i < cntU; i += AM_THREADS) {
+      // padding partners carry weight 0: fma(E, 0, acc) == acc exactly, the summation order is untouched
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < cnt) {
+        const float *q = xQ + (size_t)(base + i) * 3;
+        v = make_float4(q[0], q[1], q[2], wQ[base + i]);
+      }
+      tile[i] = v;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int l = 0; l < cnt; ++l) {
-      const float4 q = tile[l];
-      const f32x2 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z), qw = pack2(q.w, q.w);
+    // U partners per iteration: their exponentials are independent work; the accumulation itself stays strictly
+    // ordered (acc = fma(E_l, w_l, acc), l ascending -- the reference's order).
+#pragma unroll 1
+    for (int l = 0; l < cntU; l += U) {
+      f32x2 E[U][H];
+      float w[U];
 #pragma unroll
-      for (int h = 0; h < AM_P / 2; ++h) {
-        const f32x2 dx = add2(qx, npx[h]), dy = add2(qy, npy[h]), dz = add2(qz, npz[h]);
-        const f32x2 d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-        const f32x2 arg = mul2(d2, lc2);
-        float a0, a1;
-        unpack2(arg, a0, a1);
-        f32x2 E = pack2(ex2_ftz(a0), ex2_ftz(a1));
-        if (EPI == EPI_REMAIN_L) E = mul2(rl2[h], E);  // rl * E, then fma(., ratioR, suml)  (compiled :155-157)
-        acc[h] = fma2(E, qw, acc[h]);
+      for (int u = 0; u < U; ++u) {
+        const float4 q = tile[l + u];
+        w[u] = q.w;
+        am_exp_terms<H>(q, npx, npy, npz, lc2, E[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const f32x2 w2 = pack2(w[u], w[u]);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          f32x2 e = E[u][h];
+          if (EPI == EPI_REMAIN_L) e = mul2(rl2[h], e);  // rl * E, then fma(., ratioR, suml)  (compiled :155-157)
+          acc[h] = fma2(e, w2, acc[h]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int h = 0; h < AM_P / 2; ++h) {
+  for (int h = 0; h < H; ++h) {
     float s[2];
     unpack2(acc[h], s[0], s[1]);
 #pragma unroll
@@ -128,7 +157,7 @@ am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__res
 // (ratioL, :29-62) walk the same (own point k) x (all partners l) loop, so the distance is evaluated once and feeds
 // two exponentials -- 10 instead of 16 FMA-pipe operations per pair for the two sweeps, one partner load instead of two.
 // Each accumulator still sees exactly the reference's operation sequence, so the results stay bit-faithful.
-template <int AM_P>
+template <int AM_P, int UNROLL = 8>
 __global__ void __launch_bounds__(AM_THREADS)
 am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
                   const float *__restrict__ ratioR_A, size_t ratioR_stride, const float *__restrict__ remainR,
@@ -169,7 +198,7 @@ am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__r
       wB[i] = remainR[base + i];
     }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll UNROLL
     for (int l = 0; l < cnt; ++l) {
       const float4 q = tile[l];
       const float w1 = wB[l];
@@ -713,11 +742,11 @@ extern "C" __attribute__((visibility("default"))) int pcc_matchcostgrad(int b, i
   return finish_launch(2);
 }
 
-template <int P>
+template <int P, int U = 16>
 static void launch_sweep_variant(int b, int n, int m, const float *xyz1, const float *xyz2, const float *weight,
                                  const float *remain, float *ratio, float level, cudaStream_t st) {
   const int per_cta = AM_THREADS * P;
-  am_sweep_kernel<EPI_RATIO_L, P><<<dim3((n + per_cta - 1) / per_cta, b), AM_THREADS, 0, st>>>(
+  am_sweep_kernel<EPI_RATIO_L, P, U><<<dim3((n + per_cta - 1) / per_cta, b), AM_THREADS, 0, st>>>(
       n, m, xyz1, xyz2, weight, (size_t)m, level, const_cast<float *>(remain), (size_t)n, ratio, (size_t)n);
 }
 
@@ -733,7 +762,9 @@ extern "C" __attribute__((visibility("default"))) int pcc_approxmatch_sweep(int 
     case 0: launch_sweep_variant<AM_P_DEFAULT>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
     case 2: launch_sweep_variant<2>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
     case 4: launch_sweep_variant<4>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
-    case 6: launch_sweep_variant<6>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
+    case 102: launch_sweep_variant<2, 8>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
+    case 202: launch_sweep_variant<2, 32>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
+    case 104: launch_sweep_variant<4, 8>(b, n, m, xyz1, xyz2, weight, remain, ratio, level, st); break;
     default: return PCC_ENOTSUP;
   }
   return finish_launch(1);
