@@ -70,6 +70,9 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
   return r;
 }
 
+// knn_tc.cu: tcgen05 candidate generator + exact re-rank; PCC_ENOTSUP when the shape is outside that path
+int knn_tc_launch(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,6 +11,8 @@
 //   phase 2  one thread per query: threshold filter of the 32 new distances against its current k-th best,
 //            warp-compacted insertion into a sorted per-query list kept in shared memory ([slot][query] layout,
 //            bank-conflict free).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pcc {
@@ -352,7 +354,12 @@ static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const
   if (k > nr) return PCC_EINVAL;  // torch.topk / argKmin cannot return more neighbours than points
   if (k > PCC_KNN_MAX_K || b > 65535) return PCC_ENOTSUP;
   if (b == 0 || nq == 0) return PCC_OK;
+  static const bool force_simt = getenv("PCC_KNN_SIMT") != nullptr;  // test hook: exact SIMT kernels only
   if (!PM && c == 3 && q == r && nq == nr && k <= 32 && k <= K3_CAP / 2) return launch_knn3(b, nq, k, q, idx, dist, st);
+  if (!PM && !force_simt && q == r && nq == nr && c % 32 == 0) {
+    const int rc = knn_tc_launch(b, c, nq, k, q, idx, dist, st);
+    if (rc != PCC_ENOTSUP) return rc;
+  }
   const size_t smem = sizeof(KnnSmem) + (size_t)k * KN_TQ * (sizeof(float) + sizeof(int));
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {

@@ -1,0 +1,461 @@
+// Feature-space kNN graph (DGCNN EdgeConv, C = 32..256 channels) on the 5th-generation tensor cores of sm_100a.
+//
+// Replaces the KeOps argKmin behind src/utils/neighbour_ops.py:77-82 for high-dimensional features.
+//   prep      x (B,C,N) channels-first -> xT (B,N,C) point-major (K-major rows for the MMA and contiguous rows for the
+//             exact re-rank), squared norms, per-cloud max norm.
+//   main      per CTA: 128 query points of one cloud against all N references, two passes over the reference tiles.
+//             warp 0   TMA producer: 128B-swizzled K-major tiles of xT (cp.async.bulk.tensor.3d, mbarrier complete_tx)
+//             warp 1   MMA issuer: tcgen05.mma kind::tf32, M=128 x N=256 x K=8, accumulators double-buffered in TMEM
+//             warps 4-7  epilogue, one thread per query: tcgen05.ld of its accumulator row, score = |x_j|^2 - 2 x_i.x_j
+//                pass 1  minima over groups of 16 references -> k-th smallest group minimum T (branch-free sorted list)
+//                pass 2  references with score <= T + 2*eps are candidates (eps bounds |TF32 score - exact distance|)
+//                then    EXACT fp32 distances of the ~k+8 candidates in the canonical order (sequential fma over
+//                        channels), stable sort by (distance, index) -> the indices are bit-identical to the exact
+//                        SIMT kernel / the oracle; the tensor cores only generate candidates.
+// The candidate set provably contains the exact top-k: at least k references have score <= T, their exact distances are
+// <= T + eps, so the exact k-th distance is <= T + eps and every exact top-k reference has score <= T + 2 eps.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pcc {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_M = 128;       // queries per CTA (UMMA M)
+constexpr int TC_N = 256;       // references per accumulator tile (UMMA N)
+constexpr int TC_KB = 32;       // fp32 channels per K-block = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_CAP = 48;      // candidate slots per query
+constexpr int TC_A_BYTES = TC_M * TC_KB * 4;  // 16 KiB
+constexpr int TC_B_BYTES = TC_N * TC_KB * 4;  // 32 KiB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+  uint32_t ok;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 26)) asm volatile("trap;");  // watchdog: a protocol bug must fault, not hang the GPU
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (UMMA SmemDescriptor, sm_100 version 1):
+// rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+// ---- prep: transpose + norms ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+knn_tc_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict__ xT, float *__restrict__ norms,
+                   unsigned int *__restrict__ nmax_bits) {
+  __shared__ float t[32][33];
+  const size_t cloud = blockIdx.y;
+  const int n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float *xb = x + cloud * (size_t)c * n;
+  float *xo = xT + cloud * (size_t)n * c;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // thread (tx = channel lane, ty) accumulates points ty, ty+8, ty+16, ty+24
+  for (int c0 = 0; c0 < c; c0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {  // rows = channels c0 + ty + 8r, columns = points n0 + tx
+      const int ch = c0 + ty + 8 * r;
+      t[ty + 8 * r][tx] = (ch < c && n0 + tx < n) ? xb[(size_t)ch * n + n0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {  // rows = points, columns = channels
+      const int p = ty + 8 * r;
+      const float v = t[tx][p];
+      if (n0 + p < n && c0 + tx < c) xo[(size_t)(n0 + p) * c + c0 + tx] = v;
+      acc[r] = fmaf(v, v, acc[r]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float s = warp_sum(acc[r]);
+    const int p = n0 + ty + 8 * r;
+    if (tx == 0 && p < n) {
+      norms[cloud * (size_t)n + p] = s;
+      atomicMax(&nmax_bits[cloud], __float_as_uint(s));  // norms are >= 0: unsigned order == float order
+    }
+  }
+}
+
+// ---- main kernel ---------------------------------------------------------------------------------------------
+struct TcSmemCtl {
+  uint64_t full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+template <int K>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int c, int n, int k,
+              const float *__restrict__ xT, const float *__restrict__ norms, const unsigned int *__restrict__ nmax_bits,
+              int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *stage_base = smem;                                               // TC_STAGES * 48 KiB, 1024-aligned
+  int *cand = reinterpret_cast<int *>(smem + TC_STAGES * TC_STAGE_BYTES);         // [TC_CAP][128]
+  float *candd = reinterpret_cast<float *>(cand + TC_CAP * TC_M);                 // [TC_CAP][128]
+  float *rn = candd + TC_CAP * TC_M;                                              // [2][TC_N]
+  TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(rn + 2 * TC_N);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cloud = blockIdx.y;
+  const int q0 = blockIdx.x * TC_M;
+  const int nkb = c / TC_KB;                       // K-blocks per tile
+  const int ntile = (n + TC_N - 1) / TC_N;         // reference tiles per pass
+  const int niter = 2 * ntile;                     // two passes
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&ctl->tfull[a], 1);
+      mbar_init(&ctl->tempty[a], 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int it = 0; it < niter; ++it) {
+        const int r0 = (it % ntile) * TC_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          unsigned char *sa = stage_base + stage * TC_STAGE_BYTES;
+          mbar_expect_tx(&ctl->full[stage], TC_STAGE_BYTES);
+          tma_load_3d(sa, &tmap_q, &ctl->full[stage], kb * TC_KB, q0, cloud);
+          tma_load_3d(sa + TC_A_BYTES, &tmap_r, &ctl->full[stage], kb * TC_KB, r0, cloud);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int it = 0; it < niter; ++it) {
+        const int a = it & 1;
+        mbar_wait(&ctl->tempty[a], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * TC_N);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&ctl->full[stage], phase);
+          fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * TC_STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + TC_A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < TC_KB / 8; ++kk)  // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
+            mma_tf32(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), TC_IDESC, (kb | kk) ? 1u : 0u);
+          mma_commit(&ctl->empty[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        mma_commit(&ctl->tfull[a]);  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread e owns query q0 + e =====
+    const int e = threadIdx.x - 128;
+    const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31 are accessible to this warp
+    const int q = q0 + e;
+    const float INF = __int_as_float(0x7f800000);
+    const float *nb = norms + (size_t)cloud * n;
+    const float nq = (q < n) ? nb[q] : 0.f;
+    const float nmax = __uint_as_float(nmax_bits[cloud]);
+    // |score + |x_q|^2 - exact| <= eps: TF32 truncation of both operands (2^-9 relative on every product), x2 for the
+    // -2 x.y term, Cauchy-Schwarz; 2^-7.5 leaves 41 % slack, the second term covers fp32 rounding of norms / distances
+    const float eps = 0.0055242717f * sqrtf(nq * nmax) + 4e-5f * (nq + nmax);
+    float L[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) L[i] = INF;
+    float thr = INF;
+    int cnt = 0;
+    bool overflow = false;
+
+    for (int it = 0; it < niter; ++it) {
+      const int a = it & 1;
+      const int pass = it / ntile;
+      const int r0 = (it % ntile) * TC_N;
+      // norms of this reference tile (+inf beyond the cloud => never selected)
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous user of rn[a] is done (two iterations back)
+      rn[a * TC_N + e] = (r0 + e < n) ? nb[r0 + e] : INF;
+      rn[a * TC_N + 128 + e] = (r0 + 128 + e < n) ? nb[r0 + 128 + e] : INF;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&ctl->tfull[a], (it >> 1) & 1);
+      fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * TC_N);
+#pragma unroll 1
+      for (int ch = 0; ch < TC_N / 32; ++ch) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+        const float4 *rn4 = reinterpret_cast<const float4 *>(rn + a * TC_N + ch * 32);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 w = rn4[g];
+          v[4 * g + 0] = fmaf(-2.f, v[4 * g + 0], w.x);
+          v[4 * g + 1] = fmaf(-2.f, v[4 * g + 1], w.y);
+          v[4 * g + 2] = fmaf(-2.f, v[4 * g + 2], w.z);
+          v[4 * g + 3] = fmaf(-2.f, v[4 * g + 3], w.w);
+        }
+        if (pass == 0) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {  // two groups of 16 references
+            float m = fminf(v[16 * h], v[16 * h + 1]);
+#pragma unroll
+            for (int i = 2; i < 16; i += 2) m = fminf(fminf(v[16 * h + i], v[16 * h + i + 1]), m);
+            float cc = m;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              const float lo = fminf(L[i], cc);
+              cc = fmaxf(L[i], cc);
+              L[i] = lo;
+            }
+          }
+        } else {
+          const int jb = r0 + ch * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (v[i] <= thr) {
+              if (cnt < TC_CAP) {
+                cand[cnt * TC_M + e] = jb + i;
+                ++cnt;
+              } else {
+                overflow = true;
+              }
+            }
+          }
+        }
+      }
+      // release the accumulator to the MMA warp
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tempty[a]);
+      if (pass == 0 && it == ntile - 1) {
+        float t = -INF;
+#pragma unroll
+        for (int i = 0; i < K; ++i) t = (i < k) ? fmaxf(t, L[i]) : t;  // k-th smallest group minimum
+        thr = t + 2.f * eps;
+      }
+    }
+
+    // ---- exact re-rank in the canonical arithmetic -----------------------------------------------------------------
+    if (q < n) {
+      const float4 *xq = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + q) * c);
+      if (overflow) {
+        // pathological ties (e.g. duplicated clouds): exact brute force over all references, sorted insertion
+        cnt = 0;
+        for (int j = 0; j < n; ++j) {
+          const float4 *xr = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + j) * c);
+          float d = 0.f;
+          for (int c4 = 0; c4 < c / 4; ++c4) {
+            const float4 aq = xq[c4], ar = xr[c4];
+            float t0 = aq.x - ar.x, t1 = aq.y - ar.y, t2 = aq.z - ar.z, t3 = aq.w - ar.w;
+            d = fmaf(t0, t0, d);
+            d = fmaf(t1, t1, d);
+            d = fmaf(t2, t2, d);
+            d = fmaf(t3, t3, d);
+          }
+          if (cnt == k && !(d < candd[(k - 1) * TC_M + e])) continue;
+          int p = cnt < k ? cnt : k - 1;
+          while (p > 0 && d < candd[(p - 1) * TC_M + e]) {
+            candd[p * TC_M + e] = candd[(p - 1) * TC_M + e];
+            cand[p * TC_M + e] = cand[(p - 1) * TC_M + e];
+            --p;
+          }
+          candd[p * TC_M + e] = d;
+          cand[p * TC_M + e] = j;
+          if (cnt < k) ++cnt;
+        }
+      } else {
+        for (int s = 0; s < cnt; ++s) {
+          const int j = cand[s * TC_M + e];
+          const float4 *xr = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + j) * c);
+          float d = 0.f;
+          for (int c4 = 0; c4 < c / 4; ++c4) {
+            const float4 aq = xq[c4], ar = xr[c4];
+            float t0 = aq.x - ar.x, t1 = aq.y - ar.y, t2 = aq.z - ar.z, t3 = aq.w - ar.w;
+            d = fmaf(t0, t0, d);
+            d = fmaf(t1, t1, d);
+            d = fmaf(t2, t2, d);
+            d = fmaf(t3, t3, d);
+          }
+          candd[s * TC_M + e] = d;
+        }
+        // stable insertion sort by exact distance (candidates were appended in ascending index order)
+        for (int s1 = 1; s1 < cnt; ++s1) {
+          const float dv = candd[s1 * TC_M + e];
+          const int iv = cand[s1 * TC_M + e];
+          int p = s1;
+          while (p > 0 && candd[(p - 1) * TC_M + e] > dv) {
+            candd[p * TC_M + e] = candd[(p - 1) * TC_M + e];
+            cand[p * TC_M + e] = cand[(p - 1) * TC_M + e];
+            --p;
+          }
+          candd[p * TC_M + e] = dv;
+          cand[p * TC_M + e] = iv;
+        }
+      }
+      int64_t *o = idx_out + ((size_t)cloud * n + q) * k;
+      float *od = dist_out ? dist_out + ((size_t)cloud * n + q) * k : nullptr;
+      for (int t = 0; t < k; ++t) {
+        o[t] = t < cnt ? (int64_t)cand[t * TC_M + e] : 0;
+        if (od) od[t] = t < cnt ? candd[t * TC_M + e] : INF;
+      }
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap *m, const float *xT, int b, int n, int c, int box_rows) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return PCC_ENOTSUP;
+  cuuint64_t gdim[3] = {(cuuint64_t)c, (cuuint64_t)n, (cuuint64_t)b};
+  cuuint64_t gstride[2] = {(cuuint64_t)c * 4, (cuuint64_t)n * c * 4};
+  cuuint32_t box[3] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)xT, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : PCC_ENOTSUP;
+}
+
+template <int K>
+static int launch_tc_k(const CUtensorMap &mq, const CUtensorMap &mr, int b, int c, int n, int k, const float *xT,
+                       const float *norms, const unsigned int *nmax, int64_t *idx, float *dist, cudaStream_t st) {
+  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_CAP * TC_M * 8 + 2 * TC_N * 4 + sizeof(TcSmemCtl) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  dim3 grid((n + TC_M - 1) / TC_M, b);
+  knn_tc_kernel<K><<<grid, TC_THREADS, smem, st>>>(mq, mr, c, n, k, xT, norms, nmax, idx, dist);
+  return (int)cudaGetLastError();
+}
+
+// x (b,c,n) channels-first.  Returns PCC_ENOTSUP when the shape is outside this path (caller falls back to SIMT).
+int knn_tc_launch(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
+  if (c % TC_KB != 0 || c < TC_KB || c > 1024 || k > 32 || k > TC_CAP / 2 || n < 16 * k || b > 65535) return PCC_ENOTSUP;
+  if (!get_encode()) return PCC_ENOTSUP;
+  float *ws = nullptr;
+  const size_t nxt = (size_t)b * n * c, nn = (size_t)b * n;
+  cudaError_t e = cudaMallocAsync((void **)&ws, sizeof(float) * (nxt + nn) + sizeof(unsigned int) * b, st);
+  if (e != cudaSuccess) return (int)e;
+  float *xT = ws, *norms = ws + nxt;
+  unsigned int *nmax = reinterpret_cast<unsigned int *>(norms + nn);
+  cudaMemsetAsync(nmax, 0, sizeof(unsigned int) * b, st);
+  knn_tc_prep_kernel<<<dim3((n + 31) / 32, b), 256, 0, st>>>(c, n, x, xT, norms, nmax);
+  CUtensorMap mq, mr;
+  int rc = make_map(&mq, xT, b, n, c, TC_M);
+  if (rc == 0) rc = make_map(&mr, xT, b, n, c, TC_N);
+  if (rc == 0) {
+    if (k <= 8) rc = launch_tc_k<8>(mq, mr, b, c, n, k, xT, norms, nmax, idx, dist, st);
+    else if (k <= 16) rc = launch_tc_k<16>(mq, mr, b, c, n, k, xT, norms, nmax, idx, dist, st);
+    else if (k <= 20) rc = launch_tc_k<20>(mq, mr, b, c, n, k, xT, norms, nmax, idx, dist, st);
+    else if (k <= 24) rc = launch_tc_k<24>(mq, mr, b, c, n, k, xT, norms, nmax, idx, dist, st);
+    else rc = launch_tc_k<32>(mq, mr, b, c, n, k, xT, norms, nmax, idx, dist, st);
+  }
+  cudaFreeAsync(ws, st);
+  if (rc == 0) g_launches.fetch_add(2, std::memory_order_relaxed);
+  return rc;
+}
+
+}  // namespace pcc

@@ -1,0 +1,38 @@
+"""Quick GPU check of the tcgen05 feature-kNN path against the exact SIMT path / oracle."""
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import oracle  # noqa: E402
+from pointcloudcounterfactual_b200 import neighbour_ops, synthetic  # noqa: E402
+
+dev = torch.device("cuda", 0)
+for (b, c, n, k) in [(1, 32, 256, 8), (2, 64, 256, 20), (2, 64, 1024, 20), (1, 128, 384, 25), (2, 64, 300, 16), (1, 256, 512, 20)]:
+    x = synthetic.knn_features(b, c, n)
+    t0 = time.time()
+    idx, dist = neighbour_ops.knn_indices(x.to(dev), k, return_dist=True)
+    torch.cuda.synchronize()
+    e, ed = oracle.knn(x.numpy(), k, return_dist=True)
+    ok = np.array_equal(idx.cpu().numpy(), e)
+    okd = np.array_equal(dist.cpu().numpy(), ed)
+    print(f"b={b} c={c} n={n} k={k}: idx_equal={ok} dist_equal={okd} mismatch_frac={(idx.cpu().numpy() != e).mean():.5f} ({time.time()-t0:.2f}s)", flush=True)
+# duplicated points: overflow path
+x = synthetic.knn_features(1, 64, 64).repeat(1, 1, 8)
+idx = neighbour_ops.knn(x.to(dev), 20)
+print("ties:", np.array_equal(idx.cpu().numpy(), oracle.knn(x.numpy(), 20)))
+x = synthetic.knn_features(32, 64, 1024).to(dev)
+for _ in range(3):
+    neighbour_ops.knn(x, 20)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    neighbour_ops.knn(x, 20)
+e1.record()
+torch.cuda.synchronize()
+print("feat64 k20 n1024 B32: %.1f us" % (e0.elapsed_time(e1) / 20 * 1e3))
