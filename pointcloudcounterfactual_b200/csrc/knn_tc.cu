@@ -22,12 +22,13 @@ namespace pcc {
 
 constexpr int TC_THREADS = 256;
 constexpr int TC_M = 128;       // queries per CTA (UMMA M)
-constexpr int TC_N = 256;       // references per accumulator tile (UMMA N)
+constexpr int TC_N = 128;       // references per accumulator tile (UMMA N)
 constexpr int TC_KB = 32;       // fp32 channels per K-block = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;
-constexpr int TC_CAP = 48;      // candidate slots per query
+constexpr int TC_STAGES = 2;
+constexpr int TC_CAP = 56;      // candidate slots per query (uint16 indices + fp32 distances: 42 KiB per CTA)
 constexpr int TC_A_BYTES = TC_M * TC_KB * 4;  // 16 KiB
-constexpr int TC_B_BYTES = TC_N * TC_KB * 4;  // 32 KiB
+constexpr int TC_B_BYTES = TC_N * TC_KB * 4;  // 16 KiB
+constexpr int TC_TMEM_COLS = 2 * TC_N;        // two accumulators; 256 columns so that two CTAs fit one SM
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------
@@ -101,23 +102,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = TC_N, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 // ---- prep: transpose + norms ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 knn_tc_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict__ xT, float *__restrict__ norms,
                    unsigned int *__restrict__ nmax_bits) {
-  __shared__ float t[32][33];
+  __shared__ float t[64][33];
   const size_t cloud = blockIdx.y;
   const int n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const float *xb = x + cloud * (size_t)c * n;
   float *xo = xT + cloud * (size_t)n * c;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // thread (tx = channel lane, ty) accumulates points ty, ty+8, ty+16, ty+24
-  for (int c0 = 0; c0 < c; c0 += 32) {
+  for (int c0 = 0; c0 < c; c0 += 64) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {  // rows = channels c0 + ty + 8r, columns = points n0 + tx
+    for (int r = 0; r < 8; ++r) {  // rows = channels c0 + ty + 8r, columns = points n0 + tx: 8 loads in flight
       const int ch = c0 + ty + 8 * r;
       t[ty + 8 * r][tx] = (ch < c && n0 + tx < n) ? xb[(size_t)ch * n + n0 + tx] : 0.f;
     }
@@ -125,9 +126,12 @@ knn_tc_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict_
 #pragma unroll
     for (int r = 0; r < 4; ++r) {  // rows = points, columns = channels
       const int p = ty + 8 * r;
-      const float v = t[tx][p];
-      if (n0 + p < n && c0 + tx < c) xo[(size_t)(n0 + p) * c + c0 + tx] = v;
-      acc[r] = fmaf(v, v, acc[r]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float v = t[tx + 32 * h][p];
+        if (n0 + p < n && c0 + tx + 32 * h < c) xo[(size_t)(n0 + p) * c + c0 + tx + 32 * h] = v;
+        acc[r] = fmaf(v, v, acc[r]);
+      }
     }
     __syncthreads();
   }
@@ -146,19 +150,21 @@ knn_tc_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict_
 struct TcSmemCtl {
   uint64_t full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
+  int qcnt[TC_M];  // candidates per query after the two passes (-1: overflow => exact brute force)
 };
 
 template <int K>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int c, int n, int k,
               const float *__restrict__ xT, const float *__restrict__ norms, const unsigned int *__restrict__ nmax_bits,
               int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *stage_base = smem;                                               // TC_STAGES * 48 KiB, 1024-aligned
-  int *cand = reinterpret_cast<int *>(smem + TC_STAGES * TC_STAGE_BYTES);         // [TC_CAP][128]
-  float *candd = reinterpret_cast<float *>(cand + TC_CAP * TC_M);                 // [TC_CAP][128]
-  float *rn = candd + TC_CAP * TC_M;                                              // [2][TC_N]
+  float *candd = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES);    // [TC_CAP][128]
+  unsigned short *cand = reinterpret_cast<unsigned short *>(candd + TC_CAP * TC_M);  // [TC_CAP][128], n <= 65535
+  float *rn = reinterpret_cast<float *>(cand + TC_CAP * TC_M);                    // [2][TC_N]
   TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(rn + 2 * TC_N);
+  int *qcnt = ctl->qcnt;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cloud = blockIdx.y;
@@ -178,7 +184,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, TC_TMEM_COLS);
   fence_before();
   __syncthreads();
   fence_after();
@@ -246,7 +252,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     for (int i = 0; i < K; ++i) L[i] = INF;
     float thr = INF;
     int cnt = 0;
-    bool overflow = false;
 
     for (int it = 0; it < niter; ++it) {
       const int a = it & 1;
@@ -254,8 +259,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const int r0 = (it % ntile) * TC_N;
       // norms of this reference tile (+inf beyond the cloud => never selected)
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous user of rn[a] is done (two iterations back)
-      rn[a * TC_N + e] = (r0 + e < n) ? nb[r0 + e] : INF;
-      rn[a * TC_N + 128 + e] = (r0 + 128 + e < n) ? nb[r0 + 128 + e] : INF;
+      for (int j = e; j < TC_N; j += 128) rn[a * TC_N + j] = (r0 + j < n) ? nb[r0 + j] : INF;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&ctl->tfull[a], (it >> 1) & 1);
       fence_after();
@@ -290,15 +294,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         } else {
           const int jb = r0 + ch * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (v[i] <= thr) {
-              if (cnt < TC_CAP) {
-                cand[cnt * TC_M + e] = jb + i;
-                ++cnt;
-              } else {
-                overflow = true;
-              }
-            }
+          for (int i = 0; i < 32; ++i) {  // branch-free append: always store to the next slot, advance it on a hit
+            cand[min(cnt, TC_CAP - 1) * TC_M + e] = (unsigned short)(jb + i);
+            cnt += (v[i] <= thr) ? 1 : 0;
           }
         }
       }
@@ -314,11 +312,89 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
     }
 
-    // ---- exact re-rank in the canonical arithmetic -----------------------------------------------------------------
+    qcnt[e] = (cnt > TC_CAP - 1) ? -1 : cnt;  // the last slot is scratch for the branch-free append
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+
+  // ---- exact re-rank in the canonical arithmetic (sequential fma over channels) ----------------------------------
+  // Rows are staged through shared memory with coalesced loads (the pipeline stages are free now): per step the 256
+  // threads load one 32-channel chunk of the 128 query rows and of two candidate rows per query (rounds 2rp, 2rp+1),
+  // then thread (e, half) continues the fma chain of query e / candidate 2rp+half from its padded rows.
+  {
+    constexpr int RS = 36;  // padded row stride in floats: 16-byte aligned, 4 wavefronts per warp-wide LDS.128
+    float *qtile = reinterpret_cast<float *>(stage_base);  // [128][RS]
+    float *ctile = qtile + TC_M * RS;                       // [2][128][RS]
+    const int e = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int mycnt = max(qcnt[e], 0);
+    __shared__ int s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    if (half == 0 && q0 + e < n) atomicMax(&s_max, mycnt);
+    __syncthreads();
+    const int rounds = (s_max + 1) / 2;
+    const float4 *xT4 = reinterpret_cast<const float4 *>(xT) + (size_t)cloud * n * (c / 4);
+    const int c4n = c / 4;
+    for (int rp = 0; rp < rounds; ++rp) {
+      const int r = 2 * rp + half;
+      float d = 0.f;
+      for (int c8 = 0; c8 < c / 32; ++c8) {
+        __syncthreads();
+        // 3 * 128 rows * 8 float4 = 12 per thread: all loads are issued before the first store (memory-level parallelism)
+        float4 val[12];
+#pragma unroll
+        for (int it2 = 0; it2 < 12; ++it2) {
+          const int t = threadIdx.x + it2 * TC_THREADS;
+          const int which = t >> 10, row = (t >> 3) & 127, f4 = t & 7;
+          int src = -1;
+          if (which == 0) {
+            src = (q0 + row < n) ? q0 + row : -1;
+          } else {
+            const int rr = 2 * rp + which - 1;
+            if (rr < qcnt[row]) src = cand[rr * TC_M + row];
+          }
+          val[it2] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src >= 0) val[it2] = __ldg(xT4 + (size_t)src * c4n + c8 * 8 + f4);
+        }
+#pragma unroll
+        for (int it2 = 0; it2 < 12; ++it2) {
+          const int t = threadIdx.x + it2 * TC_THREADS;
+          const int which = t >> 10, row = (t >> 3) & 127, f4 = t & 7;
+          float *dst = (which == 0 ? qtile : ctile + (which - 1) * TC_M * RS) + row * RS + f4 * 4;
+          *reinterpret_cast<float4 *>(dst) = val[it2];
+        }
+        __syncthreads();
+        if (r < mycnt) {
+          const float4 *aq = reinterpret_cast<const float4 *>(qtile + e * RS);
+          const float4 *ar = reinterpret_cast<const float4 *>(ctile + half * TC_M * RS + e * RS);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 a = aq[u], b = ar[u];
+            const float t0 = a.x - b.x, t1 = a.y - b.y, t2 = a.z - b.z, t3 = a.w - b.w;
+            d = fmaf(t0, t0, d);
+            d = fmaf(t1, t1, d);
+            d = fmaf(t2, t2, d);
+            d = fmaf(t3, t3, d);
+          }
+        }
+      }
+      if (r < mycnt) candd[r * TC_M + e] = d;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int e = threadIdx.x;
+    const int q = q0 + e;
+    const float INF = __int_as_float(0x7f800000);
+    int cnt = qcnt[e];
     if (q < n) {
-      const float4 *xq = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + q) * c);
-      if (overflow) {
+      int64_t *o = idx_out + ((size_t)cloud * n + q) * k;
+      float *od = dist_out ? dist_out + ((size_t)cloud * n + q) * k : nullptr;
+      if (cnt < 0) {
         // pathological ties (e.g. duplicated clouds): exact brute force over all references, sorted insertion
+        const float4 *xq = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + q) * c);
         cnt = 0;
         for (int j = 0; j < n; ++j) {
           const float4 *xr = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + j) * c);
@@ -339,50 +415,36 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             --p;
           }
           candd[p * TC_M + e] = d;
-          cand[p * TC_M + e] = j;
+          cand[p * TC_M + e] = (unsigned short)j;
           if (cnt < k) ++cnt;
         }
+        for (int t = 0; t < k; ++t) {
+          o[t] = t < cnt ? (int64_t)cand[t * TC_M + e] : 0;
+          if (od) od[t] = t < cnt ? candd[t * TC_M + e] : INF;
+        }
       } else {
-        for (int s = 0; s < cnt; ++s) {
-          const int j = cand[s * TC_M + e];
-          const float4 *xr = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + j) * c);
-          float d = 0.f;
-          for (int c4 = 0; c4 < c / 4; ++c4) {
-            const float4 aq = xq[c4], ar = xr[c4];
-            float t0 = aq.x - ar.x, t1 = aq.y - ar.y, t2 = aq.z - ar.z, t3 = aq.w - ar.w;
-            d = fmaf(t0, t0, d);
-            d = fmaf(t1, t1, d);
-            d = fmaf(t2, t2, d);
-            d = fmaf(t3, t3, d);
-          }
-          candd[s * TC_M + e] = d;
+        // rank sort: position of candidate s among (distance, append order); candidates were appended in ascending
+        // index order, so this is the (distance, index) order.  No data-dependent loop, all loads independent.
+        for (int t = cnt; t < k; ++t) {  // fewer than k candidates only with NaN / inf inputs
+          o[t] = 0;
+          if (od) od[t] = INF;
         }
-        // stable insertion sort by exact distance (candidates were appended in ascending index order)
-        for (int s1 = 1; s1 < cnt; ++s1) {
-          const float dv = candd[s1 * TC_M + e];
-          const int iv = cand[s1 * TC_M + e];
-          int p = s1;
-          while (p > 0 && candd[(p - 1) * TC_M + e] > dv) {
-            candd[p * TC_M + e] = candd[(p - 1) * TC_M + e];
-            cand[p * TC_M + e] = cand[(p - 1) * TC_M + e];
-            --p;
+        for (int s1 = 0; s1 < cnt; ++s1) {
+          const float ds = candd[s1 * TC_M + e];
+          int rank = 0;
+#pragma unroll 8
+          for (int t = 0; t < cnt; ++t) {
+            const float dt = candd[t * TC_M + e];
+            rank += (dt < ds || (dt == ds && t < s1)) ? 1 : 0;
           }
-          candd[p * TC_M + e] = dv;
-          cand[p * TC_M + e] = iv;
+          if (rank < k) {
+            o[rank] = (int64_t)cand[s1 * TC_M + e];
+            if (od) od[rank] = ds;
+          }
         }
-      }
-      int64_t *o = idx_out + ((size_t)cloud * n + q) * k;
-      float *od = dist_out ? dist_out + ((size_t)cloud * n + q) * k : nullptr;
-      for (int t = 0; t < k; ++t) {
-        o[t] = t < cnt ? (int64_t)cand[t * TC_M + e] : 0;
-        if (od) od[t] = t < cnt ? candd[t * TC_M + e] : INF;
       }
     }
   }
-
-  fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------
@@ -419,7 +481,7 @@ static int make_map(CUtensorMap *m, const float *xT, int b, int n, int c, int bo
 template <int K>
 static int launch_tc_k(const CUtensorMap &mq, const CUtensorMap &mr, int b, int c, int n, int k, const float *xT,
                        const float *norms, const unsigned int *nmax, int64_t *idx, float *dist, cudaStream_t st) {
-  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_CAP * TC_M * 8 + 2 * TC_N * 4 + sizeof(TcSmemCtl) + 1024;
+  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_CAP * TC_M * 6 + 2 * TC_N * 4 + sizeof(TcSmemCtl) + 64;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -433,7 +495,8 @@ static int launch_tc_k(const CUtensorMap &mq, const CUtensorMap &mr, int b, int 
 
 // x (b,c,n) channels-first.  Returns PCC_ENOTSUP when the shape is outside this path (caller falls back to SIMT).
 int knn_tc_launch(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
-  if (c % TC_KB != 0 || c < TC_KB || c > 1024 || k > 32 || k > TC_CAP / 2 || n < 16 * k || b > 65535) return PCC_ENOTSUP;
+  if (c % TC_KB != 0 || c < TC_KB || c > 1024 || k > 32 || k > TC_CAP / 2 || n < 16 * k || n > 65535 || b > 65535)
+    return PCC_ENOTSUP;
   if (!get_encode()) return PCC_ENOTSUP;
   float *ws = nullptr;
   const size_t nxt = (size_t)b * n * c, nn = (size_t)b * n;

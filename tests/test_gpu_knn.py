@@ -23,6 +23,18 @@ def test_knn_indices_bit_exact_vs_oracle(cuda, c, n, k, b):
     assert np.array_equal(dist.cpu().numpy(), edist)  # same sequential fma chain => same bits
 
 
+def test_feature_knn_tensor_core_path_edge_cases(cuda):
+    """C % 32 == 0 routes to the tcgen05 candidate generator + exact re-rank: massive duplicates (candidate overflow ->
+    exact brute force), ragged N (TMA zero fill), k = 32, large norms."""
+    x = synthetic.knn_features(1, 64, 64).repeat(1, 1, 8)  # every point 8 times
+    assert np.array_equal(neighbour_ops.knn(x.to(cuda), 20).cpu().numpy(), oracle.knn(x.numpy(), 20))
+    for (b, c, n, k) in [(2, 64, 777, 20), (1, 96, 530, 32), (1, 32, 1111, 4)]:
+        x = synthetic.knn_features(b, c, n) * 7.5 + 1.0
+        idx, dist = neighbour_ops.knn_indices(x.to(cuda), k, return_dist=True)
+        eidx, edist = oracle.knn(x.numpy(), k, return_dist=True)
+        assert np.array_equal(idx.cpu().numpy(), eidx) and np.array_equal(dist.cpu().numpy(), edist)
+
+
 def test_knn_ties_lowest_index(cuda):
     a, _ = synthetic.s3_ties(2, 512, pool=64)  # heavy duplication: many exact ties
     x = a.transpose(1, 2).contiguous()

@@ -25,14 +25,23 @@ for (b, c, n, k) in [(1, 32, 256, 8), (2, 64, 256, 20), (2, 64, 1024, 20), (1, 1
 x = synthetic.knn_features(1, 64, 64).repeat(1, 1, 8)
 idx = neighbour_ops.knn(x.to(dev), 20)
 print("ties:", np.array_equal(idx.cpu().numpy(), oracle.knn(x.numpy(), 20)))
-x = synthetic.knn_features(32, 64, 1024).to(dev)
-for _ in range(3):
-    neighbour_ops.knn(x, 20)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(20):
-    neighbour_ops.knn(x, 20)
-e1.record()
-torch.cuda.synchronize()
-print("feat64 k20 n1024 B32: %.1f us" % (e0.elapsed_time(e1) / 20 * 1e3))
+def graph_us(fn, reps=20):
+    fn(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    for _ in range(3):
+        g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+for (b, c, n, k) in [(32, 64, 1024, 20), (32, 128, 1024, 20), (32, 64, 2048, 25), (8, 64, 1024, 20)]:
+    x = synthetic.knn_features(b, c, n).to(dev)
+    print(f"graph replay B={b} C={c} N={n} k={k}: {graph_us(lambda: neighbour_ops.knn(x, k)):.1f} us", flush=True)
