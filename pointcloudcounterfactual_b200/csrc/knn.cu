@@ -176,7 +176,8 @@ __device__ __forceinline__ f32x2 knn_sqdist2(f32x2 rx, f32x2 ry, f32x2 rz, f32x2
 template <int K>
 __global__ void __launch_bounds__(K3_THREADS)
 knn3_kernel(int n, int k, int groups8, const float *__restrict__ x, int64_t *__restrict__ idx_out,
-            float *__restrict__ dist_out) {
+            float *__restrict__ dist_out, const int *__restrict__ only_hard) {
+  if (only_hard && !only_hard[blockIdx.y]) return;  // repair pass behind knn3w_kernel: only the flagged clouds
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *tile = reinterpret_cast<float4 *>(smem_raw);                                   // K3_TILE/4*3 float4
   float *bufd = reinterpret_cast<float *>(smem_raw + sizeof(float4) * (K3_TILE / 4 * 3));  // [K3_CAP][K3_THREADS]
@@ -321,8 +322,192 @@ knn3_kernel(int n, int k, int groups8, const float *__restrict__ x, int64_t *__r
   }
 }
 
+// ---- xyz (C == 3) warp-cooperative path -----------------------------------------------------------------------------
+// The references live in REGISTERS: lane l of a warp holds the 32 points j = 1024*slice + 32*r + l (r = 0..31) of its
+// slice, S warps ("slices") form a team that covers a cloud of up to 1024*S points, and the team answers one query
+// at a time (query coordinates broadcast from shared memory):
+//   1  every lane evaluates its 32 distances (packed FADD2/FMUL2/FFMA2, canonical order) and their minimum;
+//   2  the 32*S lane minima are sorted with a shuffle bitonic network (merged across the team through shared
+//      memory); tau = their k-th smallest bounds the k-th smallest distance (k lanes hold a point <= tau);
+//   3  every lane flags its distances <= tau (they are still in registers: no second evaluation), a warp scan
+//      compacts the ~1.5 k candidates of the team into shared memory;
+//   4  each candidate's (distance bits, index) key is ranked by counting smaller keys; rank r < k is output slot r.
+// No thread ever loops over the references: a query costs ~400 warp instructions instead of ~10^4 thread
+// instructions.  Clouds whose candidate count exceeds KW_CAP (massive exact ties) are flagged in `hard` and redone by
+// knn3_kernel, which prunes in place.
+constexpr int KW_THREADS = 128;
+constexpr int KW_CAP = 256;  // candidate slots per team
+
+__device__ __forceinline__ void team_sync(int id, int threads) {
+  if (threads == 32)
+    __syncwarp();
+  else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int S>
+__global__ void __launch_bounds__(KW_THREADS, 3)
+knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__restrict__ idx_out,
+             float *__restrict__ dist_out, int *__restrict__ hard) {
+  constexpr int T = KW_THREADS / 32 / S;  // teams per CTA
+  constexpr int NP = 1024 * S;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *xs = reinterpret_cast<float *>(smem_raw), *ys = xs + NP, *zs = ys + NP;
+  __shared__ unsigned long long keys[T][KW_CAP];
+  __shared__ unsigned short cand[T][KW_CAP];
+  __shared__ float xch[T][S][32];
+  __shared__ int tot[T][S];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int team = warp / S, slice = warp % S, tl = slice * 32 + lane;
+  const size_t cloud = blockIdx.y;
+  const float *__restrict__ xr = x + cloud * (size_t)3 * n;
+  const float INF = __int_as_float(0x7f800000);
+  for (int i = tid; i < NP; i += KW_THREADS) {  // padding: +inf coordinates => +inf distance
+    xs[i] = i < n ? xr[i] : INF;
+    ys[i] = i < n ? xr[(size_t)n + i] : INF;
+    zs[i] = i < n ? xr[(size_t)2 * n + i] : INF;
+  }
+  __syncthreads();
+
+  f32x2 rx[16], ry[16], rz[16];
+  unsigned int valid = 0;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const int j0 = slice * 1024 + (2 * p) * 32 + lane, j1 = j0 + 32;
+    rx[p] = pack2(xs[j0], xs[j1]);
+    ry[p] = pack2(ys[j0], ys[j1]);
+    rz[p] = pack2(zs[j0], zs[j1]);
+    valid |= (j0 < n ? 1u : 0u) << (2 * p) | (j1 < n ? 1u : 0u) << (2 * p + 1);
+  }
+  // the direction of every compare-exchange of the 32-lane bitonic network, one bit per stage
+  unsigned int takemin = 0;
+  {
+    int st = 0;
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+      for (int j = k2 >> 1; j > 0; j >>= 1, ++st)
+        takemin |= ((((lane & j) == 0) == ((lane & k2) == 0 || k2 == 32)) ? 1u : 0u) << st;
+  }
+
+  const int q_begin = blockIdx.x * qper, q_end = min(n, q_begin + qper);
+  for (int q = q_begin + team; q < q_end; q += T) {
+    const float qx = xs[q], qy = ys[q], qz = zs[q];
+    const f32x2 nqx = pack2(-qx, -qx), nqy = pack2(-qy, -qy), nqz = pack2(-qz, -qz);
+    float d[32];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) unpack2(knn_sqdist2(rx[p], ry[p], rz[p], nqx, nqy, nqz), d[2 * p], d[2 * p + 1]);
+    float v = fminf(d[0], d[1]);
+#pragma unroll
+    for (int r = 2; r < 32; r += 2) v = fminf(fminf(d[r], d[r + 1]), v);
+    // ---- 2: ascending sort of the lane minima across the warp ----
+    {
+      int st = 0;
+#pragma unroll
+      for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1, ++st) {
+          const float o = __shfl_xor_sync(0xffffffffu, v, j);
+          v = ((takemin >> st) & 1u) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+#pragma unroll
+    for (int hop = 1; hop < S; hop <<= 1) {  // merge with the partner slice: keep the 32 smallest of the union, re-sort
+      xch[team][slice][lane] = v;
+      team_sync(1 + team, S * 32);
+      const float o = xch[team][slice ^ hop][31 - lane];
+      team_sync(1 + team, S * 32);
+      v = fminf(v, o);  // bitonic sequence holding the 32 smallest of both lists
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1) {
+        const float o2 = __shfl_xor_sync(0xffffffffu, v, j);
+        v = ((lane & j) == 0) ? fminf(v, o2) : fmaxf(v, o2);
+      }
+    }
+    const float tau = __shfl_sync(0xffffffffu, v, k - 1);
+    // ---- 3: candidates ----
+    unsigned int mask = 0;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) mask |= (d[r] <= tau) ? (1u << r) : 0u;
+    mask &= valid;
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    int off = incl - cnt;
+    if (S > 1) {
+      if (lane == 0) tot[team][slice] = total;
+      team_sync(1 + team, S * 32);
+      total = 0;
+#pragma unroll
+      for (int s2 = 0; s2 < S; ++s2) {
+        const int t = tot[team][s2];
+        if (s2 < slice) off += t;
+        total += t;
+      }
+    }
+    if (total > KW_CAP) {  // team-uniform
+      if (tl == 0) hard[cloud] = 1;
+      team_sync(1 + team, S * 32);
+      continue;
+    }
+    while (mask) {
+      const int r = __ffs(mask) - 1;
+      mask &= mask - 1;
+      cand[team][off++] = (unsigned short)(slice * 1024 + r * 32 + lane);
+    }
+    team_sync(1 + team, S * 32);
+    // ---- 4: keys (distance recomputed with the same arithmetic => the same bits) and ranks ----
+    for (int t = tl; t < total; t += S * 32) {
+      const int j = cand[team][t];
+      const float dx = xs[j] - qx, dy = ys[j] - qy, dz = zs[j] - qz;
+      const float dd = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+      keys[team][t] = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned int)j;
+    }
+    team_sync(1 + team, S * 32);
+    int64_t *o = idx_out + (cloud * (size_t)n + q) * k;
+    float *od = dist_out ? dist_out + (cloud * (size_t)n + q) * k : nullptr;
+    for (int t = tl; t < total; t += S * 32) {
+      const unsigned long long me = keys[team][t];
+      int rank = 0;
+#pragma unroll 4
+      for (int u = 0; u < total; ++u) rank += (keys[team][u] < me) ? 1 : 0;
+      if (rank < k) {
+        o[rank] = (int64_t)(me & 0xffffffffull);
+        if (od) od[rank] = __uint_as_float((unsigned int)(me >> 32));
+      }
+    }
+    for (int t = total + tl; t < k; t += S * 32) {  // only with NaN / inf inputs
+      o[t] = 0;
+      if (od) od[t] = INF;
+    }
+    team_sync(1 + team, S * 32);
+  }
+}
+
+template <int S>
+static int launch_knn3w_s(int b, int n, int k, int parts, const float *x, int64_t *idx, float *dist, int *hard,
+                          cudaStream_t st) {
+  const size_t smem = sizeof(float) * 3 * 1024 * S;
+  static bool attr = false;
+  if (!attr) {  // static + dynamic shared memory exceeds the 48 KiB default at S = 4
+    cudaError_t e = cudaFuncSetAttribute(knn3w_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int qper = (n + parts - 1) / parts;
+  knn3w_kernel<S><<<dim3((n + qper - 1) / qper, b), KW_THREADS, smem, st>>>(n, k, qper, x, idx, dist, hard);
+  return (int)cudaGetLastError();
+}
+
 template <int K>
-static int launch_knn3_k(int b, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
+static int launch_knn3_k(int b, int n, int k, const float *x, int64_t *idx, float *dist, const int *only_hard,
+                         cudaStream_t st) {
   const size_t smem = sizeof(float4) * (K3_TILE / 4 * 3) + (size_t)K3_CAP * K3_THREADS * (sizeof(float) + sizeof(int));
   static bool attr = false;
   if (!attr) {
@@ -334,17 +519,59 @@ static int launch_knn3_k(int b, int n, int k, const float *x, int64_t *idx, floa
   int groups8 = 4;
   while (groups8 > 1 && (n / (8 * groups8)) < 3 * k) groups8 >>= 1;
   dim3 grid((n + K3_THREADS - 1) / K3_THREADS, b);
-  knn3_kernel<K><<<grid, K3_THREADS, smem, st>>>(n, k, groups8, x, idx, dist);
+  knn3_kernel<K><<<grid, K3_THREADS, smem, st>>>(n, k, groups8, x, idx, dist, only_hard);
   return finish_launch(1);
 }
 
+static int launch_knn3_thread(int b, int n, int k, const float *x, int64_t *idx, float *dist, const int *only_hard,
+                              cudaStream_t st) {
+  if (k <= 4) return launch_knn3_k<4>(b, n, k, x, idx, dist, only_hard, st);
+  if (k <= 8) return launch_knn3_k<8>(b, n, k, x, idx, dist, only_hard, st);
+  if (k <= 16) return launch_knn3_k<16>(b, n, k, x, idx, dist, only_hard, st);
+  if (k <= 20) return launch_knn3_k<20>(b, n, k, x, idx, dist, only_hard, st);
+  if (k <= 24) return launch_knn3_k<24>(b, n, k, x, idx, dist, only_hard, st);
+  return launch_knn3_k<32>(b, n, k, x, idx, dist, only_hard, st);
+}
+
+// Number of query ranges per cloud: fill the 148 SMs x 3 resident CTAs evenly, at least 8 queries per team
+static int knn3w_parts(int b, int n, int teams) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  const int gmax = max(1, n / (8 * teams));
+  int best = 1;
+  double best_eff = 0.0;
+  for (int g = 1; g <= gmax && (long long)b * g <= 3LL * sms; ++g) {
+    const long long ctas = (long long)b * g;
+    const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+    if (eff >= best_eff) {  // ties: more CTAs (more warps to hide latency)
+      best_eff = eff;
+      best = g;
+    }
+  }
+  return best;
+}
+
 static int launch_knn3(int b, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
-  if (k <= 4) return launch_knn3_k<4>(b, n, k, x, idx, dist, st);
-  if (k <= 8) return launch_knn3_k<8>(b, n, k, x, idx, dist, st);
-  if (k <= 16) return launch_knn3_k<16>(b, n, k, x, idx, dist, st);
-  if (k <= 20) return launch_knn3_k<20>(b, n, k, x, idx, dist, st);
-  if (k <= 24) return launch_knn3_k<24>(b, n, k, x, idx, dist, st);
-  return launch_knn3_k<32>(b, n, k, x, idx, dist, st);
+  static const bool thread_only = getenv("PCC_KNN3_THREAD") != nullptr;  // test hook: one-thread-per-query kernel only
+  if (thread_only || n > 4096) return launch_knn3_thread(b, n, k, x, idx, dist, nullptr, st);
+  int *hard = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&hard, sizeof(int) * b, st);
+  if (e != cudaSuccess) return (int)e;
+  cudaMemsetAsync(hard, 0, sizeof(int) * b, st);
+  int rc;
+  if (n <= 1024) rc = launch_knn3w_s<1>(b, n, k, knn3w_parts(b, n, 4), x, idx, dist, hard, st);
+  else if (n <= 2048) rc = launch_knn3w_s<2>(b, n, k, knn3w_parts(b, n, 2), x, idx, dist, hard, st);
+  else rc = launch_knn3w_s<4>(b, n, k, knn3w_parts(b, n, 1), x, idx, dist, hard, st);
+  if (rc == 0) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    rc = launch_knn3_thread(b, n, k, x, idx, dist, hard, st);  // exits at once unless a cloud overflowed KW_CAP
+  }
+  cudaFreeAsync(hard, st);
+  return rc;
 }
 
 template <bool PM>
@@ -355,7 +582,7 @@ static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const
   if (k > PCC_KNN_MAX_K || b > 65535) return PCC_ENOTSUP;
   if (b == 0 || nq == 0) return PCC_OK;
   static const bool force_simt = getenv("PCC_KNN_SIMT") != nullptr;  // test hook: exact SIMT kernels only
-  if (!PM && c == 3 && q == r && nq == nr && k <= 32 && k <= K3_CAP / 2) return launch_knn3(b, nq, k, q, idx, dist, st);
+  if (!PM && c == 3 && q == r && nq == nr && k <= 32) return launch_knn3(b, nq, k, q, idx, dist, st);
   if (!PM && !force_simt && q == r && nq == nr && c % 32 == 0) {
     const int rc = knn_tc_launch(b, c, nq, k, q, idx, dist, st);
     if (rc != PCC_ENOTSUP) return rc;

@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("c,n,k,b", [
     (3, 1024, 20, 4), (3, 2048, 25, 2), (3, 2048, 4, 2), (3, 300, 16, 3), (3, 33, 33, 2), (3, 5, 1, 2),
+    (3, 4096, 32, 1), (3, 3000, 25, 1), (3, 1500, 20, 2), (3, 1025, 1, 1), (3, 32, 32, 2), (3, 5000, 8, 1),
     (64, 1024, 20, 2), (64, 200, 20, 2), (128, 384, 25, 1), (17, 130, 7, 2), (256, 256, 20, 1),
 ])
 def test_knn_indices_bit_exact_vs_oracle(cuda, c, n, k, b):
@@ -42,6 +43,15 @@ def test_knn_ties_lowest_index(cuda):
     assert np.array_equal(idx.cpu().numpy(), oracle.knn(x.numpy(), 20))
     z = torch.zeros(1, 3, 64)
     assert torch.equal(neighbour_ops.knn(z.to(cuda), 5).cpu(), torch.arange(5).expand(1, 64, 5))
+    # more exact ties than the warp-cooperative kernel's candidate buffer: the flagged cloud is redone by the
+    # one-thread-per-query kernel, the other cloud of the batch is left alone
+    zz = torch.cat([torch.zeros(1, 3, 1024), synthetic.knn_xyz(1, 1024)])
+    got = neighbour_ops.knn(zz.to(cuda), 30).cpu()
+    assert torch.equal(got[0], torch.arange(30).expand(1024, 30))
+    assert np.array_equal(got[1].numpy(), oracle.knn(zz[1:].numpy(), 30)[0])
+    a, _ = synthetic.s3_ties(2, 2048, pool=32)
+    x = a.transpose(1, 2).contiguous()
+    assert np.array_equal(neighbour_ops.knn(x.to(cuda), 25).cpu().numpy(), oracle.knn(x.numpy(), 25))
 
 
 @pytest.mark.parametrize("case", ["xyz_k20", "xyz_k4", "feat64_k20", "feat128_k25"])
