@@ -336,13 +336,19 @@ knn3_kernel(int n, int k, int groups8, const float *__restrict__ x, int64_t *__r
 // instructions.  Clouds whose candidate count exceeds KW_CAP (massive exact ties) are flagged in `hard` and redone by
 // knn3_kernel, which prunes in place.
 constexpr int KW_THREADS = 128;
-constexpr int KW_CAP = 256;  // candidate slots per team
+constexpr int KW_CAP = 128;  // candidate slots per team
 
 __device__ __forceinline__ void team_sync(int id, int threads) {
   if (threads == 32)
     __syncwarp();
   else
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// inclusive warp scan step: adds the value `o` lanes below (shfl.up's predicate says whether that lane exists)
+__device__ __forceinline__ int scan_up_add(int v, int o) {
+  asm("{\n.reg .pred p;\n.reg .s32 t;\nshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n@p add.s32 %0, %0, t;\n}" : "+r"(v) : "r"(o));
+  return v;
 }
 
 template <int S>
@@ -353,10 +359,11 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
   constexpr int NP = 1024 * S;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *xs = reinterpret_cast<float *>(smem_raw), *ys = xs + NP, *zs = ys + NP;
-  __shared__ unsigned long long keys[T][KW_CAP];
-  __shared__ unsigned short cand[T][KW_CAP];
-  __shared__ float xch[T][S][32];
+  __shared__ __align__(16) unsigned int dkey[T][KW_CAP];  // candidate distance bits (d >= 0: unsigned order == float order)
+  __shared__ unsigned short cand[T][KW_CAP];              // candidate indices
+  __shared__ __align__(16) unsigned int lmin[T][S * 32];  // lane minima of the team
   __shared__ int tot[T][S];
+  __shared__ int tsum[T];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int team = warp / S, slice = warp % S, tl = slice * 32 + lane;
@@ -368,6 +375,7 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
     ys[i] = i < n ? xr[(size_t)n + i] : INF;
     zs[i] = i < n ? xr[(size_t)2 * n + i] : INF;
   }
+  if (tid < T) tsum[tid] = 0;
   __syncthreads();
 
   f32x2 rx[16], ry[16], rz[16];
@@ -380,16 +388,7 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
     rz[p] = pack2(zs[j0], zs[j1]);
     valid |= (j0 < n ? 1u : 0u) << (2 * p) | (j1 < n ? 1u : 0u) << (2 * p + 1);
   }
-  // the direction of every compare-exchange of the 32-lane bitonic network, one bit per stage
-  unsigned int takemin = 0;
-  {
-    int st = 0;
-#pragma unroll
-    for (int k2 = 2; k2 <= 32; k2 <<= 1)
-#pragma unroll
-      for (int j = k2 >> 1; j > 0; j >>= 1, ++st)
-        takemin |= ((((lane & j) == 0) == ((lane & k2) == 0 || k2 == 32)) ? 1u : 0u) << st;
-  }
+  const unsigned int lt_mask = (1u << lane) - 1u;
 
   const int q_begin = blockIdx.x * qper, q_end = min(n, q_begin + qper);
   for (int q = q_begin + team; q < q_end; q += T) {
@@ -398,48 +397,65 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
     float d[32];
 #pragma unroll
     for (int p = 0; p < 16; ++p) unpack2(knn_sqdist2(rx[p], ry[p], rz[p], nqx, nqy, nqz), d[2 * p], d[2 * p + 1]);
-    float v = fminf(d[0], d[1]);
+    // lane minimum as a tree (short dependency chain)
+    float m8[8];
 #pragma unroll
-    for (int r = 2; r < 32; r += 2) v = fminf(fminf(d[r], d[r + 1]), v);
-    // ---- 2: ascending sort of the lane minima across the warp ----
+    for (int g = 0; g < 8; ++g) m8[g] = fminf(fminf(d[4 * g], d[4 * g + 1]), fminf(d[4 * g + 2], d[4 * g + 3]));
+    const float v = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])), fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
+    // ---- 2: tau = k-th smallest of the team's 32*S lane minima.  Every lane counts the minima strictly below its
+    //         own (all of them broadcast from shared memory: no shuffle chain); the lanes with fewer than k below
+    //         them hold the k smallest values, ties included, so the maximum over those lanes is tau ----
+    const unsigned int vb = __float_as_uint(v);  // v >= 0 or NaN (0x7fc00000 > +inf): unsigned order == float order
+    lmin[team][tl] = vb;
+    team_sync(1 + team, S * 32);
+    int below = 0;
     {
-      int st = 0;
+      const uint4 *lm = reinterpret_cast<const uint4 *>(lmin[team]);
+      int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
 #pragma unroll
-      for (int k2 = 2; k2 <= 32; k2 <<= 1)
-#pragma unroll
-        for (int j = k2 >> 1; j > 0; j >>= 1, ++st) {
-          const float o = __shfl_xor_sync(0xffffffffu, v, j);
-          v = ((takemin >> st) & 1u) ? fminf(v, o) : fmaxf(v, o);
-        }
+      for (int u = 0; u < 8 * S; ++u) {
+        const uint4 w = lm[u];
+        b0 += (w.x - vb) >> 31;  // both < 2^31: bit 31 of the wrapped difference is set iff w < vb
+        b1 += (w.y - vb) >> 31;
+        b2 += (w.z - vb) >> 31;
+        b3 += (w.w - vb) >> 31;
+      }
+      below = (b0 + b1) + (b2 + b3);
     }
-#pragma unroll
-    for (int hop = 1; hop < S; hop <<= 1) {  // merge with the partner slice: keep the 32 smallest of the union, re-sort
-      xch[team][slice][lane] = v;
+    unsigned int taub = __reduce_max_sync(0xffffffffu, below < k ? vb : 0u);
+    if (S > 1) {
+      if (lane == 0) tot[team][slice] = (int)taub;
       team_sync(1 + team, S * 32);
-      const float o = xch[team][slice ^ hop][31 - lane];
-      team_sync(1 + team, S * 32);
-      v = fminf(v, o);  // bitonic sequence holding the 32 smallest of both lists
 #pragma unroll
-      for (int j = 16; j > 0; j >>= 1) {
-        const float o2 = __shfl_xor_sync(0xffffffffu, v, j);
-        v = ((lane & j) == 0) ? fminf(v, o2) : fmaxf(v, o2);
+      for (int s2 = 0; s2 < S; ++s2) taub = max(taub, (unsigned int)tot[team][s2]);
+      team_sync(1 + team, S * 32);  // tot is reused for the candidate counts below
+    }
+    // ---- 3: candidates.  d <= tau  <=>  bits(d) + ~bits(tau) is negative as a signed integer; the sign bits are
+    //         funnel-shifted into the mask (four independent chains) ----
+    const unsigned int ntau = ~taub;
+    unsigned int mk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int r = 7; r >= 0; --r)
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) mk[c4] = __funnelshift_l(__float_as_uint(d[8 * c4 + r]) + ntau, mk[c4], 1);
+    unsigned int mask = ((mk[3] << 24) | (mk[2] << 16) | (mk[1] << 8) | mk[0]) & valid;
+    const int cnt = __popc(mask);
+    // offsets: almost every lane has 0..3 candidates => three ballots instead of a shuffle scan
+    int off, total;
+    {
+      const unsigned int b1 = __ballot_sync(0xffffffffu, cnt >= 1), b2 = __ballot_sync(0xffffffffu, cnt >= 2),
+                         b3 = __ballot_sync(0xffffffffu, cnt >= 3), b4 = __ballot_sync(0xffffffffu, cnt >= 4);
+      if (b4 == 0) {
+        off = __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+        total = __popc(b1) + __popc(b2) + __popc(b3);
+      } else {
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) incl = scan_up_add(incl, o);
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        off = incl - cnt;
       }
     }
-    const float tau = __shfl_sync(0xffffffffu, v, k - 1);
-    // ---- 3: candidates ----
-    unsigned int mask = 0;
-#pragma unroll
-    for (int r = 0; r < 32; ++r) mask |= (d[r] <= tau) ? (1u << r) : 0u;
-    mask &= valid;
-    const int cnt = __popc(mask);
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    int total = __shfl_sync(0xffffffffu, incl, 31);
-    int off = incl - cnt;
     if (S > 1) {
       if (lane == 0) tot[team][slice] = total;
       team_sync(1 + team, S * 32);
@@ -456,36 +472,84 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
       team_sync(1 + team, S * 32);
       continue;
     }
+    // keys: the distance is recomputed with the same arithmetic => the same bits (the register holding it cannot be
+    // indexed dynamically); bank = lane, conflict free
     while (mask) {
       const int r = __ffs(mask) - 1;
       mask &= mask - 1;
-      cand[team][off++] = (unsigned short)(slice * 1024 + r * 32 + lane);
-    }
-    team_sync(1 + team, S * 32);
-    // ---- 4: keys (distance recomputed with the same arithmetic => the same bits) and ranks ----
-    for (int t = tl; t < total; t += S * 32) {
-      const int j = cand[team][t];
+      const int j = slice * 1024 + r * 32 + lane;
       const float dx = xs[j] - qx, dy = ys[j] - qy, dz = zs[j] - qz;
-      const float dd = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-      keys[team][t] = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned int)j;
+      dkey[team][off] = __float_as_uint(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+      cand[team][off] = (unsigned short)j;
+      ++off;
+    }
+    {  // pad the last group of four keys (0x7fffffff is never below a key)
+      const int pi = (total & ~3) + tl;
+      if (tl < 4 && pi >= total && pi < KW_CAP) dkey[team][pi] = 0x7fffffffu;
     }
     team_sync(1 + team, S * 32);
+    // ---- 4: ranks ----
     int64_t *o = idx_out + (cloud * (size_t)n + q) * k;
     float *od = dist_out ? dist_out + (cloud * (size_t)n + q) * k : nullptr;
-    for (int t = tl; t < total; t += S * 32) {
-      const unsigned long long me = keys[team][t];
-      int rank = 0;
-#pragma unroll 4
-      for (int u = 0; u < total; ++u) rank += (keys[team][u] < me) ? 1 : 0;
-      if (rank < k) {
-        o[rank] = (int64_t)(me & 0xffffffffull);
-        if (od) od[rank] = __uint_as_float((unsigned int)(me >> 32));
+    constexpr int ROUNDS = KW_CAP / (S * 32);
+    int rank[ROUNDS];
+    int lsum = 0;
+    const int total4 = (total + 3) >> 2;
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      const int t = tl + rd * S * 32;
+      rank[rd] = 0;
+      if (rd * S * 32 < total) {  // team-uniform
+        const unsigned int me = dkey[team][min(t, total - 1)];
+        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;  // number of candidates strictly closer than mine
+        const uint4 *kv = reinterpret_cast<const uint4 *>(dkey[team]);
+#pragma unroll 2
+        for (int u = 0; u < total4; ++u) {
+          const uint4 kk = kv[u];
+          r0 += (kk.x - me) >> 31;
+          r1 += (kk.y - me) >> 31;
+          r2 += (kk.z - me) >> 31;
+          r3 += (kk.w - me) >> 31;
+        }
+        rank[rd] = (r0 + r1) + (r2 + r3);
+        if (t < total) lsum += rank[rd];
+      }
+    }
+    // without exact ties the strict ranks are a permutation of 0..total-1; every tied pair lowers their sum by one
+    int ssum = __reduce_add_sync(0xffffffffu, lsum);
+    if (S > 1) {
+      if (lane == 0) atomicAdd(&tsum[team], ssum);
+      team_sync(1 + team, S * 32);
+      ssum = tsum[team];
+    }
+    if (ssum != total * (total - 1) / 2) {  // team-uniform, rare: break ties by index
+#pragma unroll
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int t = tl + rd * S * 32;
+        if (t < total) {
+          const unsigned int me = dkey[team][t], mi = cand[team][t];
+          int r = 0;
+          for (int u = 0; u < total; ++u) {
+            const unsigned int ku = dkey[team][u];
+            r += (ku < me || (ku == me && cand[team][u] < mi)) ? 1 : 0;
+          }
+          rank[rd] = r;
+        }
+      }
+    }
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      const int t = tl + rd * S * 32;
+      if (t < total && rank[rd] < k) {
+        o[rank[rd]] = (int64_t)cand[team][t];
+        if (od) od[rank[rd]] = __uint_as_float(dkey[team][t]);
       }
     }
     for (int t = total + tl; t < k; t += S * 32) {  // only with NaN / inf inputs
       o[t] = 0;
       if (od) od[t] = INF;
     }
+    if (S > 1 && tl == 0) tsum[team] = 0;
     team_sync(1 + team, S * 32);
   }
 }
@@ -541,14 +605,21 @@ static int knn3w_parts(int b, int n, int teams) {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
+  static const char *force = getenv("PCC_KNN3_PARTS");  // tuning hook
+  if (force && atoi(force) > 0) return atoi(force);
+  // score = fill of the last wave of 3 resident CTAs per SM, discounted by the per-CTA set-up (the cloud is staged in
+  // shared memory and registers: worth about 4 queries per team)
   const int gmax = max(1, n / (8 * teams));
+  const long long slots = 3LL * sms;
   int best = 1;
-  double best_eff = 0.0;
-  for (int g = 1; g <= gmax && (long long)b * g <= 3LL * sms; ++g) {
+  double best_score = 0.0;
+  for (int g = 1; g <= gmax && g <= 64; ++g) {
     const long long ctas = (long long)b * g;
-    const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
-    if (eff >= best_eff) {  // ties: more CTAs (more warps to hide latency)
-      best_eff = eff;
+    const double fill = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+    const double qper = (double)n / g;
+    const double score = fill * qper / (qper + 4.0 * teams);
+    if (score > best_score) {
+      best_score = score;
       best = g;
     }
   }
