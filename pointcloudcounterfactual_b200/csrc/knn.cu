@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace pcc {
 
@@ -483,9 +484,9 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
       cand[team][off] = (unsigned short)j;
       ++off;
     }
-    {  // pad the last group of four keys (0x7fffffff is never below a key)
-      const int pi = (total & ~3) + tl;
-      if (tl < 4 && pi >= total && pi < KW_CAP) dkey[team][pi] = 0x7fffffffu;
+    {  // pad the last group of sixteen keys (0x7fffffff is never below a key)
+      const int pi = (total & ~15) + tl;
+      if (tl < 16 && pi >= total && pi < KW_CAP) dkey[team][pi] = 0x7fffffffu;
     }
     team_sync(1 + team, S * 32);
     // ---- 4: ranks ----
@@ -494,7 +495,7 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
     constexpr int ROUNDS = KW_CAP / (S * 32);
     int rank[ROUNDS];
     int lsum = 0;
-    const int total4 = (total + 3) >> 2;
+    const int total4 = ((total + 15) >> 4) << 2;  // uint4 groups, a multiple of four
 #pragma unroll
     for (int rd = 0; rd < ROUNDS; ++rd) {
       const int t = tl + rd * S * 32;
@@ -503,13 +504,16 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
         const unsigned int me = dkey[team][min(t, total - 1)];
         int r0 = 0, r1 = 0, r2 = 0, r3 = 0;  // number of candidates strictly closer than mine
         const uint4 *kv = reinterpret_cast<const uint4 *>(dkey[team]);
-#pragma unroll 2
-        for (int u = 0; u < total4; ++u) {
-          const uint4 kk = kv[u];
-          r0 += (kk.x - me) >> 31;
-          r1 += (kk.y - me) >> 31;
-          r2 += (kk.z - me) >> 31;
-          r3 += (kk.w - me) >> 31;
+#pragma unroll 1
+        for (int u = 0; u < total4; u += 4) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint4 kk = kv[u + w];
+            r0 += (kk.x - me) >> 31;
+            r1 += (kk.y - me) >> 31;
+            r2 += (kk.z - me) >> 31;
+            r3 += (kk.w - me) >> 31;
+          }
         }
         rank[rd] = (r0 + r1) + (r2 + r3);
         if (t < total) lsum += rank[rd];
@@ -655,7 +659,9 @@ static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const
   static const bool force_simt = getenv("PCC_KNN_SIMT") != nullptr;  // test hook: exact SIMT kernels only
   if (!PM && c == 3 && q == r && nq == nr && k <= 32) return launch_knn3(b, nq, k, q, idx, dist, st);
   if (!PM && !force_simt && q == r && nq == nr && c % 32 == 0) {
-    const int rc = knn_tc_launch(b, c, nq, k, q, idx, dist, st);
+    static const bool tc_v1 = getenv("PCC_KNN_TC1") != nullptr;  // test hook: first-generation tcgen05 kernel only
+    int rc = tc_v1 ? PCC_ENOTSUP : knn_tc2_launch(b, c, nq, k, q, idx, dist, st);
+    if (rc == PCC_ENOTSUP) rc = knn_tc_launch(b, c, nq, k, q, idx, dist, st);
     if (rc != PCC_ENOTSUP) return rc;
   }
   const size_t smem = sizeof(KnnSmem) + (size_t)k * KN_TQ * (sizeof(float) + sizeof(int));

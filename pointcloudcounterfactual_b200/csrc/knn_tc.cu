@@ -14,9 +14,7 @@
 //                        SIMT kernel / the oracle; the tensor cores only generate candidates.
 // The candidate set provably contains the exact top-k: at least k references have score <= T, their exact distances are
 // <= T + eps, so the exact k-th distance is <= T + eps and every exact top-k reference has score <= T + 2 eps.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace pcc {
 
@@ -31,84 +29,12 @@ constexpr int TC_B_BYTES = TC_N * TC_KB * 4;  // 16 KiB
 constexpr int TC_TMEM_COLS = 2 * TC_N;        // two accumulators; 256 columns so that two CTAs fit one SM
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 
-// ---- PTX wrappers --------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
-  uint32_t ok;
-  uint32_t spins = 0;
-  do {
-    if (++spins > (1u << 26)) asm volatile("trap;");  // watchdog: a protocol bug must fault, not hang the GPU
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
-}
-__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
-      "%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (UMMA SmemDescriptor, sm_100 version 1):
-// rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused for swizzled K-major layouts.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N = TC_N, M = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+constexpr uint32_t TC_IDESC = umma_idesc_tf32(TC_M, TC_N);
 
 // ---- prep: transpose + norms ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 knn_tc_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict__ xT, float *__restrict__ norms,
-                   unsigned int *__restrict__ nmax_bits) {
+                   int norm_stride, unsigned int *__restrict__ nmax_bits) {
   __shared__ float t[64][33];
   const size_t cloud = blockIdx.y;
   const int n0 = blockIdx.x * 32;
@@ -140,8 +66,10 @@ knn_tc_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict_
     const float s = warp_sum(acc[r]);
     const int p = n0 + ty + 8 * r;
     if (tx == 0 && p < n) {
-      norms[cloud * (size_t)n + p] = s;
+      norms[cloud * (size_t)norm_stride + p] = s;
       atomicMax(&nmax_bits[cloud], __float_as_uint(s));  // norms are >= 0: unsigned order == float order
+    } else if (tx == 0 && p < norm_stride) {
+      norms[cloud * (size_t)norm_stride + p] = __int_as_float(0x7f800000);  // padding: never a neighbour
     }
   }
 }
@@ -448,12 +376,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                        CUtensorMapFloatOOBfill);
-
-static PFN_tmapEncodeTiled get_encode() {
+PFN_tmapEncodeTiled tc_get_encode() {
   static PFN_tmapEncodeTiled fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -465,12 +388,12 @@ static PFN_tmapEncodeTiled get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap *m, const float *xT, int b, int n, int c, int box_rows) {
-  PFN_tmapEncodeTiled enc = get_encode();
+int tc_make_map(CUtensorMap *m, const float *xT, int b, int n, int c, int box_rows) {
+  PFN_tmapEncodeTiled enc = tc_get_encode();
   if (!enc) return PCC_ENOTSUP;
   cuuint64_t gdim[3] = {(cuuint64_t)c, (cuuint64_t)n, (cuuint64_t)b};
   cuuint64_t gstride[2] = {(cuuint64_t)c * 4, (cuuint64_t)n * c * 4};
-  cuuint32_t box[3] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)xT, gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -497,7 +420,7 @@ static int launch_tc_k(const CUtensorMap &mq, const CUtensorMap &mr, int b, int 
 int knn_tc_launch(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
   if (c % TC_KB != 0 || c < TC_KB || c > 1024 || k > 32 || k > TC_CAP / 2 || n < 16 * k || n > 65535 || b > 65535)
     return PCC_ENOTSUP;
-  if (!get_encode()) return PCC_ENOTSUP;
+  if (!tc_get_encode()) return PCC_ENOTSUP;
   float *ws = nullptr;
   const size_t nxt = (size_t)b * n * c, nn = (size_t)b * n;
   cudaError_t e = cudaMallocAsync((void **)&ws, sizeof(float) * (nxt + nn) + sizeof(unsigned int) * b, st);
@@ -505,10 +428,10 @@ int knn_tc_launch(int b, int c, int n, int k, const float *x, int64_t *idx, floa
   float *xT = ws, *norms = ws + nxt;
   unsigned int *nmax = reinterpret_cast<unsigned int *>(norms + nn);
   cudaMemsetAsync(nmax, 0, sizeof(unsigned int) * b, st);
-  knn_tc_prep_kernel<<<dim3((n + 31) / 32, b), 256, 0, st>>>(c, n, x, xT, norms, nmax);
+  knn_tc_prep_kernel<<<dim3((n + 31) / 32, b), 256, 0, st>>>(c, n, x, xT, norms, n, nmax);
   CUtensorMap mq, mr;
-  int rc = make_map(&mq, xT, b, n, c, TC_M);
-  if (rc == 0) rc = make_map(&mr, xT, b, n, c, TC_N);
+  int rc = tc_make_map(&mq, xT, b, n, c, TC_M);
+  if (rc == 0) rc = tc_make_map(&mr, xT, b, n, c, TC_N);
   if (rc == 0) {
     if (k <= 8) rc = launch_tc_k<8>(mq, mr, b, c, n, k, xT, norms, nmax, idx, dist, st);
     else if (k <= 16) rc = launch_tc_k<16>(mq, mr, b, c, n, k, xT, norms, nmax, idx, dist, st);

@@ -1,0 +1,428 @@
+// Feature-space kNN graph (DGCNN EdgeConv, C = 32..128 channels) on tcgen05 -- second generation.
+//
+// Replaces the KeOps argKmin behind src/utils/neighbour_ops.py:77-82.  Same contract as knn_tc.cu (TF32 tensor cores
+// only GENERATE candidates, every candidate is re-ranked with the exact fp32 fma chain, so the indices are bit-identical
+// to the SIMT kernel / the oracle), restructured so that nothing on the critical path touches global memory twice:
+//
+//   CTA      = 128*HALVES queries of one cloud (HALVES = 2 for C <= 64: two M=128 accumulators share every key tile).
+//   warp 0   TMA producer: the query tile once, then key tiles of R keys x ALL channels (128B-swizzled K-major boxes)
+//            plus the tile's squared norms (cp.async.bulk), two stages.
+//   warp 1   MMA issuer: tcgen05.mma kind::tf32 M=128 x N=R x K=8 into TMEM accumulator `stage` of each half.
+//   warps 2+ epilogue, one thread per query (tcgen05.ld of its accumulator row), two sweeps over the key tiles:
+//     sweep 1  score = |x_j|^2 - 2 x_i.x_j; one minimum per group of 32 keys.  tau = k-th smallest group minimum
+//              (bitonic network in registers) bounds the k-th smallest score from above.
+//     sweep 2  the accumulators are recomputed (the tensor pipe is idle otherwise); keys with score <= tau + 2 eps are
+//              candidates.  Their EXACT distance is evaluated at once from the key tile that is still resident in
+//              shared memory (the tile that fed the MMA) against the query row held in registers.
+//     finally  the ~1.5 k candidates of a query are ranked by counting; rank r < k is output slot r.
+// The candidate set provably contains the exact top-k (see knn_tc.cu); a query whose candidates overflow the list
+// (massive exact ties) is redone by exact brute force.
+#include "tc_ptx.cuh"
+
+namespace pcc {
+
+template <int KB, int HALVES, int R>
+struct T2 {
+  static constexpr int C = KB * 32;
+  static constexpr int QUERIES = 128 * HALVES;
+  static constexpr int NEPI = 4 * HALVES;              // epilogue warps
+  static constexpr int THREADS = 64 + 32 * NEPI;       // warp 0 = TMA, warp 1 = MMA
+  static constexpr int A_BYTES = KB * QUERIES * 128;   // query tile: KB blocks of [QUERIES][32 floats]
+  static constexpr int B_BYTES = KB * R * 128;         // one key stage
+  static constexpr int CAP = 64;                       // candidate slots per query (also holds <= 64 group minima)
+  static constexpr int CHUNKS = R / 32;                // 32-column TMEM loads per tile
+  static constexpr int TMEM_COLS = HALVES * 2 * R;
+  static constexpr size_t SMEM = 1024 + A_BYTES + 2 * B_BYTES + 2 * R * 4 + (size_t)CAP * QUERIES * 6 + 256;
+  static constexpr bool Q_IN_REGS = KB <= 2;
+};
+
+struct T2Ctl {
+  uint64_t full[2], empty[2], tfull[2], tempty[2], afull;
+  uint32_t tmem_base;
+};
+
+template <int N>
+__device__ __forceinline__ void bitonic_sort_regs(float (&a)[N]) {  // ascending, fully unrolled (static indices)
+#pragma unroll
+  for (int k2 = 2; k2 <= N; k2 <<= 1)
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float lo = fminf(a[i], a[l]), hi = fmaxf(a[i], a[l]);
+          const bool up = (i & k2) == 0;
+          a[i] = up ? lo : hi;
+          a[l] = up ? hi : lo;
+        }
+      }
+}
+
+template <int N>
+__device__ __forceinline__ void bitonic_merge_regs(float (&a)[N]) {  // a is bitonic -> ascending
+#pragma unroll
+  for (int j = N >> 1; j > 0; j >>= 1)
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int l = i ^ j;
+      if (l > i) {
+        const float lo = fminf(a[i], a[l]), hi = fmaxf(a[i], a[l]);
+        a[i] = lo;
+        a[l] = hi;
+      }
+    }
+}
+
+template <int KB, int HALVES, int R>
+__global__ void __launch_bounds__(T2<KB, HALVES, R>::THREADS, 1)
+knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int n, int k,
+               int npad, const float *__restrict__ xT, const float *__restrict__ norms,
+               const unsigned int *__restrict__ nmax_bits, int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+  using Cfg = T2<KB, HALVES, R>;
+  constexpr int C = Cfg::C, Q = Cfg::QUERIES, CAP = Cfg::CAP, CHUNKS = Cfg::CHUNKS;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char *sA = smem;                                        // [KB][Q][128 B]
+  unsigned char *sB = sA + Cfg::A_BYTES;                           // [2][KB][R][128 B]
+  float *rn = reinterpret_cast<float *>(sB + 2 * Cfg::B_BYTES);    // [2][R] squared norms of the staged keys
+  float *candd = rn + 2 * R;                                       // [CAP][Q] exact distances (sweep 1: group minima)
+  unsigned short *cand = reinterpret_cast<unsigned short *>(candd + CAP * Q);  // [CAP][Q] indices
+  T2Ctl *ctl = reinterpret_cast<T2Ctl *>(cand + CAP * Q);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cloud = blockIdx.y;
+  const int q0 = blockIdx.x * Q;
+  const int ntile = npad / R;
+  const int niter = 2 * ntile;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], Cfg::NEPI);
+      mbar_init(&ctl->tfull[s], 1);
+      mbar_init(&ctl->tempty[s], Cfg::NEPI);
+    }
+    mbar_init(&ctl->afull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, Cfg::TMEM_COLS);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(&ctl->afull, Cfg::A_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tma_load_3d(sA + kb * (Q * 128), &tmap_q, &ctl->afull, kb * 32, q0, cloud);
+      for (int i = 0; i < niter; ++i) {
+        const int s = i & 1, par = (i >> 1) & 1;
+        const int r0 = (i % ntile) * R;
+        mbar_wait(&ctl->empty[s], par ^ 1);
+        mbar_expect_tx(&ctl->full[s], Cfg::B_BYTES + R * 4);
+        unsigned char *st = sB + s * Cfg::B_BYTES;
+        for (int kb = 0; kb < KB; ++kb) tma_load_3d(st + kb * (R * 128), &tmap_r, &ctl->full[s], kb * 32, r0, cloud);
+        bulk_load_1d(rn + s * R, norms + (size_t)cloud * npad + r0, R * 4, &ctl->full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t IDESC = umma_idesc_tf32(128, R);
+      mbar_wait(&ctl->afull, 0);
+      for (int i = 0; i < niter; ++i) {
+        const int s = i & 1, par = (i >> 1) & 1;
+        mbar_wait(&ctl->tempty[s], par ^ 1);  // epilogue drained accumulator s
+        mbar_wait(&ctl->full[s], par);
+        fence_after();
+        const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)((h * 2 + s) * R);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t da = umma_desc_sw128(smem_u32(sA) + kb * (Q * 128) + h * (128 * 128));
+            const uint64_t db = umma_desc_sw128(b_addr + kb * (R * 128));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)  // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
+              mma_tf32(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC, (kb | kk) ? 1u : 0u);
+          }
+        }
+        mma_commit(&ctl->tfull[s]);
+      }
+    }
+  } else {
+    // ===== epilogue: one thread per query =====
+    const int quarter = warp & 3;       // TMEM lanes 32*quarter .. +31 are accessible to this warp
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;  // row of the half's accumulator
+    const int e = half * 128 + row;       // query slot in the CTA
+    const int q = q0 + e;
+    const float INF = __int_as_float(0x7f800000);
+    const float nq = (q < n) ? norms[(size_t)cloud * npad + q] : 0.f;
+    const float nmax = __uint_as_float(nmax_bits[cloud]);
+    // |score + |x_q|^2 - exact| <= eps: TF32 truncation of both operands (2^-9 relative on every product), x2 for the
+    // -2 x.y term, Cauchy-Schwarz; 2^-7.5 leaves 41 % slack, the second term covers fp32 rounding of norms / distances
+    const float eps = 0.0055242717f * sqrtf(nq * nmax) + 4e-5f * (nq + nmax);
+    float thr = INF;
+    int cnt = 0;
+    float xq[Cfg::Q_IN_REGS ? C : 1];
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 2 * R);
+
+    for (int i = 0; i < niter; ++i) {
+      const int s = i & 1, par = (i >> 1) & 1;
+      const bool second = i >= ntile;
+      const int t = second ? i - ntile : i;
+      mbar_wait(&ctl->full[s], par);   // acquires the TMA-written key tile and norms for this thread
+      mbar_wait(&ctl->tfull[s], par);
+      fence_after();
+      const uint32_t taddr = tlane + (uint32_t)(s * R);
+      const float *rns = rn + s * R;
+      if (!second) {
+        // ---- sweep 1: group minima ----
+#pragma unroll
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          uint32_t v[32];
+          tmem_ld32_issue(taddr + (uint32_t)(ch * 32), v);
+          tmem_ld_wait();
+          float m = INF;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 w = *reinterpret_cast<const float4 *>(rns + ch * 32 + 4 * g);
+            const float z0 = fmaf(-2.f, __uint_as_float(v[4 * g + 0]), w.x), z1 = fmaf(-2.f, __uint_as_float(v[4 * g + 1]), w.y),
+                        z2 = fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z), z3 = fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w);
+            m = fminf(fminf(z0, z1), fminf(fminf(z2, z3), m));
+          }
+          candd[(t * CHUNKS + ch) * Q + e] = m;
+        }
+        fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&ctl->tempty[s]);
+          mbar_arrive(&ctl->empty[s]);
+        }
+        if (i == ntile - 1) {
+          // ---- tau = k-th smallest of the ng <= 64 group minima (at least k groups hold a key with score <= tau) ----
+          const int ng = ntile * CHUNKS;
+          float a[32];
+#pragma unroll
+          for (int u = 0; u < 32; ++u) a[u] = (u < ng) ? candd[u * Q + e] : INF;
+          bitonic_sort_regs<32>(a);
+          if (ng > 32) {
+            float b2[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) b2[u] = (32 + u < ng) ? candd[(32 + u) * Q + e] : INF;
+            bitonic_sort_regs<32>(b2);
+#pragma unroll
+            for (int u = 0; u < 32; ++u) a[u] = fminf(a[u], b2[31 - u]);  // the 32 smallest of both, a bitonic sequence
+            bitonic_merge_regs<32>(a);
+          }
+          float tau = -INF;
+#pragma unroll
+          for (int u = 0; u < 32; ++u) tau = (u < k) ? fmaxf(tau, a[u]) : tau;
+          // strict compare below: inflate by a few ulps so that score == tau + 2 eps is still a candidate
+          thr = (tau + 2.f * eps) * 1.000001f + 1e-30f;
+          if constexpr (Cfg::Q_IN_REGS) {
+            mbar_wait(&ctl->afull, 0);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+              for (int c16 = 0; c16 < 8; ++c16) {
+                const float4 w = *reinterpret_cast<const float4 *>(sA + kb * (Q * 128) + e * 128 + ((c16 ^ (e & 7)) << 4));
+                xq[kb * 32 + c16 * 4 + 0] = w.x;
+                xq[kb * 32 + c16 * 4 + 1] = w.y;
+                xq[kb * 32 + c16 * 4 + 2] = w.z;
+                xq[kb * 32 + c16 * 4 + 3] = w.w;
+              }
+          } else {
+            mbar_wait(&ctl->afull, 0);
+          }
+        }
+      } else {
+        // ---- sweep 2: candidate masks (sign bit of score - thr), then exact distances from the resident key tile ----
+        unsigned int masks[CHUNKS];
+#pragma unroll
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          uint32_t v[32];
+          tmem_ld32_issue(taddr + (uint32_t)(ch * 32), v);
+          tmem_ld_wait();
+          unsigned int mk = 0;
+#pragma unroll
+          for (int g = 7; g >= 0; --g) {
+            const float4 w = *reinterpret_cast<const float4 *>(rns + ch * 32 + 4 * g);
+            const float z3 = fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w) - thr, z2 = fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z) - thr,
+                        z1 = fmaf(-2.f, __uint_as_float(v[4 * g + 1]), w.y) - thr, z0 = fmaf(-2.f, __uint_as_float(v[4 * g + 0]), w.x) - thr;
+            mk = __funnelshift_l(__float_as_uint(z3), mk, 1);
+            mk = __funnelshift_l(__float_as_uint(z2), mk, 1);
+            mk = __funnelshift_l(__float_as_uint(z1), mk, 1);
+            mk = __funnelshift_l(__float_as_uint(z0), mk, 1);
+          }
+          masks[ch] = mk;
+        }
+        const unsigned char *st = sB + s * Cfg::B_BYTES;
+#pragma unroll
+        for (int ch = 0; ch < CHUNKS; ++ch) {
+          unsigned int mk = masks[ch];
+          while (mk) {
+            const int bit = __ffs(mk) - 1;
+            mk &= mk - 1;
+            const int jl = ch * 32 + bit;
+            float d = 0.f;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+              const unsigned char *rowp = st + kb * (R * 128) + jl * 128;
+#pragma unroll
+              for (int c16 = 0; c16 < 8; ++c16) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(rowp + ((c16 ^ (jl & 7)) << 4));
+                float4 a4;
+                if constexpr (Cfg::Q_IN_REGS) {
+                  a4 = make_float4(xq[kb * 32 + c16 * 4], xq[kb * 32 + c16 * 4 + 1], xq[kb * 32 + c16 * 4 + 2],
+                                   xq[kb * 32 + c16 * 4 + 3]);
+                } else {
+                  a4 = *reinterpret_cast<const float4 *>(sA + kb * (Q * 128) + e * 128 + ((c16 ^ (e & 7)) << 4));
+                }
+                const float t0 = a4.x - b4.x, t1 = a4.y - b4.y, t2 = a4.z - b4.z, t3 = a4.w - b4.w;
+                d = fmaf(t0, t0, d);
+                d = fmaf(t1, t1, d);
+                d = fmaf(t2, t2, d);
+                d = fmaf(t3, t3, d);
+              }
+            }
+            if (cnt < CAP) {
+              candd[cnt * Q + e] = d;
+              cand[cnt * Q + e] = (unsigned short)(t * R + jl);
+            }
+            ++cnt;
+          }
+        }
+        fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&ctl->tempty[s]);
+          mbar_arrive(&ctl->empty[s]);
+        }
+      }
+    }
+
+    // ---- ranking: candidates were appended in ascending index order, so (distance, position) is the
+    //      (distance, index) order.  d >= 0: the bit patterns order like the values. ----
+    if (q < n) {
+      int64_t *o = idx_out + ((size_t)cloud * n + q) * k;
+      float *od = dist_out ? dist_out + ((size_t)cloud * n + q) * k : nullptr;
+      if (cnt > CAP) {
+        // pathological ties (e.g. duplicated clouds): exact brute force over all references, sorted insertion
+        const float4 *xqg = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + q) * C);
+        int have = 0;
+        for (int j = 0; j < n; ++j) {
+          const float4 *xr = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + j) * C);
+          float d = 0.f;
+          for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 aq = xqg[c4], ar = xr[c4];
+            const float t0 = aq.x - ar.x, t1 = aq.y - ar.y, t2 = aq.z - ar.z, t3 = aq.w - ar.w;
+            d = fmaf(t0, t0, d);
+            d = fmaf(t1, t1, d);
+            d = fmaf(t2, t2, d);
+            d = fmaf(t3, t3, d);
+          }
+          if (have == k && !(d < candd[(k - 1) * Q + e])) continue;
+          int p = have < k ? have : k - 1;
+          while (p > 0 && d < candd[(p - 1) * Q + e]) {
+            candd[p * Q + e] = candd[(p - 1) * Q + e];
+            cand[p * Q + e] = cand[(p - 1) * Q + e];
+            --p;
+          }
+          candd[p * Q + e] = d;
+          cand[p * Q + e] = (unsigned short)j;
+          if (have < k) ++have;
+        }
+        for (int t2 = 0; t2 < k; ++t2) {
+          o[t2] = t2 < have ? (int64_t)cand[t2 * Q + e] : 0;
+          if (od) od[t2] = t2 < have ? candd[t2 * Q + e] : INF;
+        }
+      } else {
+        for (int t2 = cnt; t2 < k; ++t2) {  // fewer than k candidates only with NaN / inf inputs
+          o[t2] = 0;
+          if (od) od[t2] = INF;
+        }
+        const unsigned int *cb = reinterpret_cast<const unsigned int *>(candd);
+        for (int s0 = 0; s0 < cnt; s0 += 4) {  // four own candidates at a time against all of them
+          unsigned int me[4];
+          int rk[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) me[w] = cb[min(s0 + w, cnt - 1) * Q + e];
+#pragma unroll 4
+          for (int t2 = 0; t2 < cnt; ++t2) {
+            const unsigned int dt = cb[t2 * Q + e];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              // dt < me, or dt == me and t2 earlier: compare 2*dt + [t2 >= own position] against 2*me + 1 ... written
+              // as two strict tests to stay in 32 bits
+              rk[w] += (dt < me[w] || (dt == me[w] && t2 < s0 + w)) ? 1 : 0;
+            }
+          }
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            if (s0 + w < cnt && rk[w] < k) {
+              o[rk[w]] = (int64_t)cand[(s0 + w) * Q + e];
+              if (od) od[rk[w]] = __uint_as_float(me[w]);
+            }
+        }
+      }
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------
+template <int KB, int HALVES, int R>
+static int launch_tc2(int b, int n, int k, int npad, const float *xT, const float *norms, const unsigned int *nmax,
+                      int64_t *idx, float *dist, cudaStream_t st) {
+  using Cfg = T2<KB, HALVES, R>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(knn_tc2_kernel<KB, HALVES, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  CUtensorMap mq, mr;
+  int rc = tc_make_map(&mq, xT, b, n, Cfg::C, Cfg::QUERIES);
+  if (rc == 0) rc = tc_make_map(&mr, xT, b, n, Cfg::C, R);
+  if (rc != 0) return rc;
+  dim3 grid((n + Cfg::QUERIES - 1) / Cfg::QUERIES, b);
+  knn_tc2_kernel<KB, HALVES, R><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mq, mr, n, k, npad, xT, norms, nmax, idx, dist);
+  return (int)cudaGetLastError();
+}
+
+// x (b,c,n) channels-first.  Returns PCC_ENOTSUP when the shape is outside this path.
+int knn_tc2_launch(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
+  if (c % 32 != 0 || c < 32 || c > 128 || k > 32 || n < 32 * k || n > 2048 || b > 65535) return PCC_ENOTSUP;
+  if (!tc_get_encode()) return PCC_ENOTSUP;
+  const int r = (c <= 64) ? 128 : 64;
+  const int npad = (n + r - 1) / r * r;
+  float *ws = nullptr;
+  const size_t nxt = (size_t)b * n * c, nn = (size_t)b * npad;
+  cudaError_t e = cudaMallocAsync((void **)&ws, sizeof(float) * (nxt + nn) + sizeof(unsigned int) * b, st);
+  if (e != cudaSuccess) return (int)e;
+  float *xT = ws, *norms = ws + nxt;
+  unsigned int *nmax = reinterpret_cast<unsigned int *>(norms + nn);
+  cudaMemsetAsync(nmax, 0, sizeof(unsigned int) * b, st);
+  knn_tc_prep_kernel<<<dim3((npad + 31) / 32, b), 256, 0, st>>>(c, n, x, xT, norms, npad, nmax);
+  int rc;
+  switch (c / 32) {
+    case 1: rc = launch_tc2<1, 2, 128>(b, n, k, npad, xT, norms, nmax, idx, dist, st); break;
+    case 2: rc = launch_tc2<2, 2, 128>(b, n, k, npad, xT, norms, nmax, idx, dist, st); break;
+    case 3: rc = launch_tc2<3, 1, 64>(b, n, k, npad, xT, norms, nmax, idx, dist, st); break;
+    default: rc = launch_tc2<4, 1, 64>(b, n, k, npad, xT, norms, nmax, idx, dist, st); break;
+  }
+  cudaFreeAsync(ws, st);
+  if (rc == 0) g_launches.fetch_add(2, std::memory_order_relaxed);
+  return rc;
+}
+
+}  // namespace pcc

@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
     (3, 1024, 20, 4), (3, 2048, 25, 2), (3, 2048, 4, 2), (3, 300, 16, 3), (3, 33, 33, 2), (3, 5, 1, 2),
     (3, 4096, 32, 1), (3, 3000, 25, 1), (3, 1500, 20, 2), (3, 1025, 1, 1), (3, 32, 32, 2), (3, 5000, 8, 1),
     (64, 1024, 20, 2), (64, 200, 20, 2), (128, 384, 25, 1), (17, 130, 7, 2), (256, 256, 20, 1),
+    (64, 2048, 25, 2), (128, 1024, 20, 1), (128, 2048, 25, 1), (96, 1500, 25, 1), (32, 2048, 32, 1), (64, 1000, 31, 1),
 ])
 def test_knn_indices_bit_exact_vs_oracle(cuda, c, n, k, b):
     x = synthetic.knn_xyz(b, n) if c == 3 else synthetic.knn_features(b, c, n)
@@ -29,7 +30,9 @@ def test_feature_knn_tensor_core_path_edge_cases(cuda):
     exact brute force), ragged N (TMA zero fill), k = 32, large norms."""
     x = synthetic.knn_features(1, 64, 64).repeat(1, 1, 8)  # every point 8 times
     assert np.array_equal(neighbour_ops.knn(x.to(cuda), 20).cpu().numpy(), oracle.knn(x.numpy(), 20))
-    for (b, c, n, k) in [(2, 64, 777, 20), (1, 96, 530, 32), (1, 32, 1111, 4)]:
+    x = synthetic.knn_features(1, 64, 64).repeat(1, 1, 16)  # n = 1024: second-generation kernel, list overflow
+    assert np.array_equal(neighbour_ops.knn(x.to(cuda), 20).cpu().numpy(), oracle.knn(x.numpy(), 20))
+    for (b, c, n, k) in [(2, 64, 777, 20), (1, 96, 530, 32), (1, 32, 1111, 4), (3, 128, 900, 8)]:
         x = synthetic.knn_features(b, c, n) * 7.5 + 1.0
         idx, dist = neighbour_ops.knn_indices(x.to(cuda), k, return_dist=True)
         eidx, edist = oracle.knn(x.numpy(), k, return_dist=True)
