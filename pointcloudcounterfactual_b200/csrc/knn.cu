@@ -346,12 +346,6 @@ __device__ __forceinline__ void team_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// inclusive warp scan step: adds the value `o` lanes below (shfl.up's predicate says whether that lane exists)
-__device__ __forceinline__ int scan_up_add(int v, int o) {
-  asm("{\n.reg .pred p;\n.reg .s32 t;\nshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n@p add.s32 %0, %0, t;\n}" : "+r"(v) : "r"(o));
-  return v;
-}
-
 template <int S>
 __global__ void __launch_bounds__(KW_THREADS, 3)
 knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__restrict__ idx_out,

@@ -12,9 +12,11 @@
 //     sweep 1  score = |x_j|^2 - 2 x_i.x_j; one minimum per group of 32 keys.  tau = k-th smallest group minimum
 //              (bitonic network in registers) bounds the k-th smallest score from above.
 //     sweep 2  the accumulators are recomputed (the tensor pipe is idle otherwise); keys with score <= tau + 2 eps are
-//              candidates.  Their EXACT distance is evaluated at once from the key tile that is still resident in
-//              shared memory (the tile that fed the MMA) against the query row held in registers.
-//     finally  the ~1.5 k candidates of a query are ranked by counting; rank r < k is output slot r.
+//              candidates.  The warp compacts its (query, key) pairs and spreads them evenly over its lanes; each
+//              pair's EXACT distance is evaluated at once from the key tile that is still resident in shared memory
+//              (the tile that fed the MMA) and the resident query tile.
+//     finally  the ~1.5 k candidates of a query are ranked by counting, one query per warp step and one candidate per
+//              lane; rank r < k is output slot r.
 // The candidate set provably contains the exact top-k (see knn_tc.cu); a query whose candidates overflow the list
 // (massive exact ties) is redone by exact brute force.
 #include "tc_ptx.cuh"
@@ -29,11 +31,14 @@ struct T2 {
   static constexpr int THREADS = 64 + 32 * NEPI;       // warp 0 = TMA, warp 1 = MMA
   static constexpr int A_BYTES = KB * QUERIES * 128;   // query tile: KB blocks of [QUERIES][32 floats]
   static constexpr int B_BYTES = KB * R * 128;         // one key stage
-  static constexpr int CAP = 64;                       // candidate slots per query (also holds <= 64 group minima)
+  static constexpr int CAP = 56;                       // candidate slots per query
+  static constexpr int W = 85;                         // words per query record: CAP distances + CAP/2 packed indices,
+                                                       // >= 64 (sweep 1 keeps the group minima there), odd (banks)
+  static constexpr int PCAP = 192;                     // (query, key) pairs per warp and tile
   static constexpr int CHUNKS = R / 32;                // 32-column TMEM loads per tile
   static constexpr int TMEM_COLS = HALVES * 2 * R;
-  static constexpr size_t SMEM = 1024 + A_BYTES + 2 * B_BYTES + 2 * R * 4 + (size_t)CAP * QUERIES * 6 + 256;
-  static constexpr bool Q_IN_REGS = KB <= 2;
+  static constexpr size_t SMEM =
+      A_BYTES + 2 * B_BYTES + 2 * R * 4 + (size_t)QUERIES * W * 4 + (size_t)NEPI * (PCAP + 64) * 4 + 256;
 };
 
 struct T2Ctl {
@@ -80,15 +85,15 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                int npad, const float *__restrict__ xT, const float *__restrict__ norms,
                const unsigned int *__restrict__ nmax_bits, int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
   using Cfg = T2<KB, HALVES, R>;
-  constexpr int C = Cfg::C, Q = Cfg::QUERIES, CAP = Cfg::CAP, CHUNKS = Cfg::CHUNKS;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int C = Cfg::C, Q = Cfg::QUERIES, CAP = Cfg::CAP, CHUNKS = Cfg::CHUNKS, W = Cfg::W;
+  extern __shared__ __align__(1024) unsigned char smem[];  // the 128B swizzle atoms need 1024-byte alignment
   unsigned char *sA = smem;                                        // [KB][Q][128 B]
   unsigned char *sB = sA + Cfg::A_BYTES;                           // [2][KB][R][128 B]
   float *rn = reinterpret_cast<float *>(sB + 2 * Cfg::B_BYTES);    // [2][R] squared norms of the staged keys
-  float *candd = rn + 2 * R;                                       // [CAP][Q] exact distances (sweep 1: group minima)
-  unsigned short *cand = reinterpret_cast<unsigned short *>(candd + CAP * Q);  // [CAP][Q] indices
-  T2Ctl *ctl = reinterpret_cast<T2Ctl *>(cand + CAP * Q);
+  uint32_t *recs = reinterpret_cast<uint32_t *>(rn + 2 * R);       // [Q][W] per-query records
+  uint32_t *plist = recs + Q * W;                                  // [NEPI][PCAP]
+  uint32_t *scratch = plist + Cfg::NEPI * Cfg::PCAP;               // [NEPI][64], 16-byte aligned
+  T2Ctl *ctl = reinterpret_cast<T2Ctl *>(scratch + Cfg::NEPI * 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cloud = blockIdx.y;
@@ -157,8 +162,8 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // ===== epilogue: one thread per query =====
     const int quarter = warp & 3;       // TMEM lanes 32*quarter .. +31 are accessible to this warp
     const int half = (warp - 2) >> 2;
-    const int row = quarter * 32 + lane;  // row of the half's accumulator
-    const int e = half * 128 + row;       // query slot in the CTA
+    const int e0 = half * 128 + quarter * 32;  // first query slot of this warp
+    const int e = e0 + lane;                   // query slot in the CTA
     const int q = q0 + e;
     const float INF = __int_as_float(0x7f800000);
     const float nq = (q < n) ? norms[(size_t)cloud * npad + q] : 0.f;
@@ -168,8 +173,39 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const float eps = 0.0055242717f * sqrtf(nq * nmax) + 4e-5f * (nq + nmax);
     float thr = INF;
     int cnt = 0;
-    float xq[Cfg::Q_IN_REGS ? C : 1];
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 2 * R);
+    uint32_t *rec = recs + e * W;                       // this query's record: distances, then packed indices
+    uint32_t *myplist = plist + (warp - 2) * Cfg::PCAP;  // this warp's (query, key) pairs of the current tile
+    uint32_t *myscr = scratch + (warp - 2) * 64;
+
+    // exact squared distance of query slot eq to key row jl of the staged tile: the canonical sequential fma chain
+    auto exact = [&](const unsigned char *st, int eq, int jl) {
+      float d = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const unsigned char *rowk = st + kb * (R * 128) + jl * 128;
+        const unsigned char *rowq = sA + kb * (Q * 128) + eq * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          const float4 b4 = *reinterpret_cast<const float4 *>(rowk + ((c16 ^ (jl & 7)) << 4));
+          const float4 a4 = *reinterpret_cast<const float4 *>(rowq + ((c16 ^ (eq & 7)) << 4));
+          // the four differences as two packed FADD2 (bit-identical to scalar subtraction), then the scalar chain
+          float t0, t1, t2, t3;
+          unpack2(add2(pack2(a4.x, a4.y), pack2(-b4.x, -b4.y)), t0, t1);
+          unpack2(add2(pack2(a4.z, a4.w), pack2(-b4.z, -b4.w)), t2, t3);
+          d = fmaf(t0, t0, d);
+          d = fmaf(t1, t1, d);
+          d = fmaf(t2, t2, d);
+          d = fmaf(t3, t3, d);
+        }
+      }
+      return d;
+    };
+    auto store_cand = [&](int eq, int slot, float d, int j) {
+      uint32_t *r = recs + eq * W;
+      r[slot] = __float_as_uint(d);
+      reinterpret_cast<unsigned short *>(r + CAP)[slot] = (unsigned short)j;
+    };
 
     for (int i = 0; i < niter; ++i) {
       const int s = i & 1, par = (i >> 1) & 1;
@@ -195,7 +231,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                         z2 = fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z), z3 = fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w);
             m = fminf(fminf(z0, z1), fminf(fminf(z2, z3), m));
           }
-          candd[(t * CHUNKS + ch) * Q + e] = m;
+          rec[t * CHUNKS + ch] = __float_as_uint(m);
         }
         fence_before();
         __syncwarp();
@@ -208,12 +244,12 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           const int ng = ntile * CHUNKS;
           float a[32];
 #pragma unroll
-          for (int u = 0; u < 32; ++u) a[u] = (u < ng) ? candd[u * Q + e] : INF;
+          for (int u = 0; u < 32; ++u) a[u] = (u < ng) ? __uint_as_float(rec[u]) : INF;
           bitonic_sort_regs<32>(a);
           if (ng > 32) {
             float b2[32];
 #pragma unroll
-            for (int u = 0; u < 32; ++u) b2[u] = (32 + u < ng) ? candd[(32 + u) * Q + e] : INF;
+            for (int u = 0; u < 32; ++u) b2[u] = (32 + u < ng) ? __uint_as_float(rec[32 + u]) : INF;
             bitonic_sort_regs<32>(b2);
 #pragma unroll
             for (int u = 0; u < 32; ++u) a[u] = fminf(a[u], b2[31 - u]);  // the 32 smallest of both, a bitonic sequence
@@ -224,25 +260,12 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           for (int u = 0; u < 32; ++u) tau = (u < k) ? fmaxf(tau, a[u]) : tau;
           // strict compare below: inflate by a few ulps so that score == tau + 2 eps is still a candidate
           thr = (tau + 2.f * eps) * 1.000001f + 1e-30f;
-          if constexpr (Cfg::Q_IN_REGS) {
-            mbar_wait(&ctl->afull, 0);
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-              for (int c16 = 0; c16 < 8; ++c16) {
-                const float4 w = *reinterpret_cast<const float4 *>(sA + kb * (Q * 128) + e * 128 + ((c16 ^ (e & 7)) << 4));
-                xq[kb * 32 + c16 * 4 + 0] = w.x;
-                xq[kb * 32 + c16 * 4 + 1] = w.y;
-                xq[kb * 32 + c16 * 4 + 2] = w.z;
-                xq[kb * 32 + c16 * 4 + 3] = w.w;
-              }
-          } else {
-            mbar_wait(&ctl->afull, 0);
-          }
+          mbar_wait(&ctl->afull, 0);  // the query tile is read by the exact re-rank
         }
       } else {
-        // ---- sweep 2: candidate masks (sign bit of score - thr), then exact distances from the resident key tile ----
+        // ---- sweep 2: candidate masks (sign bit of score - thr) ----
         unsigned int masks[CHUNKS];
+        int c_l = 0;
 #pragma unroll
         for (int ch = 0; ch < CHUNKS; ++ch) {
           uint32_t v[32];
@@ -260,43 +283,69 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             mk = __funnelshift_l(__float_as_uint(z0), mk, 1);
           }
           masks[ch] = mk;
+          c_l += __popc(mk);
         }
+        // a list that would overflow is first pruned to its k best entries (exact distances, so nothing is lost);
+        // only a tile with more than CAP - k candidates of one query (massive ties) defeats this
+        if (cnt <= CAP && cnt + c_l > CAP && cnt > k) {
+          float *rd = reinterpret_cast<float *>(rec);
+          unsigned short *rix = reinterpret_cast<unsigned short *>(rec + CAP);
+          for (int s1 = 1; s1 < cnt; ++s1) {
+            const float vd = rd[s1];
+            const unsigned short vi = rix[s1];
+            int p = s1;
+            while (p > 0 && (rd[p - 1] > vd || (rd[p - 1] == vd && rix[p - 1] > vi))) {
+              rd[p] = rd[p - 1];
+              rix[p] = rix[p - 1];
+              --p;
+            }
+            rd[p] = vd;
+            rix[p] = vi;
+          }
+          cnt = k;
+        }
+        __syncwarp();
+        // ---- (query, key) pairs of the whole warp, compacted so that the exact re-rank is spread evenly over the
+        //      lanes (the candidates of one query differ a lot from tile to tile) ----
         const unsigned char *st = sB + s * Cfg::B_BYTES;
+        int incl = c_l;
 #pragma unroll
-        for (int ch = 0; ch < CHUNKS; ++ch) {
-          unsigned int mk = masks[ch];
-          while (mk) {
-            const int bit = __ffs(mk) - 1;
-            mk &= mk - 1;
-            const int jl = ch * 32 + bit;
-            float d = 0.f;
+        for (int o = 1; o < 32; o <<= 1) incl = scan_up_add(incl, o);
+        const int npairs = __shfl_sync(0xffffffffu, incl, 31);
+        if (npairs <= Cfg::PCAP) {
+          int pos = incl - c_l, slot = cnt;
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
-              const unsigned char *rowp = st + kb * (R * 128) + jl * 128;
-#pragma unroll
-              for (int c16 = 0; c16 < 8; ++c16) {
-                const float4 b4 = *reinterpret_cast<const float4 *>(rowp + ((c16 ^ (jl & 7)) << 4));
-                float4 a4;
-                if constexpr (Cfg::Q_IN_REGS) {
-                  a4 = make_float4(xq[kb * 32 + c16 * 4], xq[kb * 32 + c16 * 4 + 1], xq[kb * 32 + c16 * 4 + 2],
-                                   xq[kb * 32 + c16 * 4 + 3]);
-                } else {
-                  a4 = *reinterpret_cast<const float4 *>(sA + kb * (Q * 128) + e * 128 + ((c16 ^ (e & 7)) << 4));
-                }
-                const float t0 = a4.x - b4.x, t1 = a4.y - b4.y, t2 = a4.z - b4.z, t3 = a4.w - b4.w;
-                d = fmaf(t0, t0, d);
-                d = fmaf(t1, t1, d);
-                d = fmaf(t2, t2, d);
-                d = fmaf(t3, t3, d);
-              }
+          for (int ch = 0; ch < CHUNKS; ++ch) {
+            unsigned int mk = masks[ch];
+            while (mk) {
+              const int bit = __ffs(mk) - 1;
+              mk &= mk - 1;
+              myplist[pos++] = ((unsigned int)lane << 14) | ((unsigned int)min(slot, 127) << 7) | (unsigned int)(ch * 32 + bit);
+              ++slot;
             }
-            if (cnt < CAP) {
-              candd[cnt * Q + e] = d;
-              cand[cnt * Q + e] = (unsigned short)(t * R + jl);
+          }
+          __syncwarp();
+          for (int p2 = lane; p2 < npairs; p2 += 32) {
+            const unsigned int pr = myplist[p2];
+            const int jl = pr & 127, sl = (pr >> 7) & 127, eq = e0 + (int)(pr >> 14);
+            const float d = exact(st, eq, jl);
+            if (sl < CAP) store_cand(eq, sl, d, t * R + jl);
+          }
+        } else {  // more pairs than the list holds (massive ties): every thread walks its own candidates
+          int slot = cnt;
+#pragma unroll
+          for (int ch = 0; ch < CHUNKS; ++ch) {
+            unsigned int mk = masks[ch];
+            while (mk) {
+              const int bit = __ffs(mk) - 1;
+              mk &= mk - 1;
+              const int jl = ch * 32 + bit;
+              if (slot < CAP) store_cand(e, slot, exact(st, e, jl), t * R + jl);
+              ++slot;
             }
-            ++cnt;
           }
         }
+        cnt += c_l;
         fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -306,69 +355,96 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
     }
 
-    // ---- ranking: candidates were appended in ascending index order, so (distance, position) is the
-    //      (distance, index) order.  d >= 0: the bit patterns order like the values. ----
-    if (q < n) {
-      int64_t *o = idx_out + ((size_t)cloud * n + q) * k;
-      float *od = dist_out ? dist_out + ((size_t)cloud * n + q) * k : nullptr;
-      if (cnt > CAP) {
-        // pathological ties (e.g. duplicated clouds): exact brute force over all references, sorted insertion
-        const float4 *xqg = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + q) * C);
-        int have = 0;
-        for (int j = 0; j < n; ++j) {
-          const float4 *xr = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + j) * C);
-          float d = 0.f;
-          for (int c4 = 0; c4 < C / 4; ++c4) {
-            const float4 aq = xqg[c4], ar = xr[c4];
-            const float t0 = aq.x - ar.x, t1 = aq.y - ar.y, t2 = aq.z - ar.z, t3 = aq.w - ar.w;
-            d = fmaf(t0, t0, d);
-            d = fmaf(t1, t1, d);
-            d = fmaf(t2, t2, d);
-            d = fmaf(t3, t3, d);
-          }
-          if (have == k && !(d < candd[(k - 1) * Q + e])) continue;
-          int p = have < k ? have : k - 1;
-          while (p > 0 && d < candd[(p - 1) * Q + e]) {
-            candd[p * Q + e] = candd[(p - 1) * Q + e];
-            cand[p * Q + e] = cand[(p - 1) * Q + e];
-            --p;
-          }
-          candd[p * Q + e] = d;
-          cand[p * Q + e] = (unsigned short)j;
-          if (have < k) ++have;
-        }
-        for (int t2 = 0; t2 < k; ++t2) {
-          o[t2] = t2 < have ? (int64_t)cand[t2 * Q + e] : 0;
-          if (od) od[t2] = t2 < have ? candd[t2 * Q + e] : INF;
+    // ---- ranking, one query of the warp at a time, one candidate per lane.  d >= 0, so the bit patterns order like the
+    //      values.  Without exact ties the strict ranks are a permutation (their sum is c(c-1)/2). ----
+    __syncwarp();
+    for (int lq = 0; lq < 32; ++lq) {
+      const int c = __shfl_sync(0xffffffffu, cnt, lq);
+      const int qq = q0 + e0 + lq;
+      if (qq >= n || c > CAP) continue;  // warp-uniform
+      const uint32_t *r = recs + (e0 + lq) * W;
+      const unsigned short *ri = reinterpret_cast<const unsigned short *>(r + CAP);
+      int64_t *o = idx_out + ((size_t)cloud * n + qq) * k;
+      float *od = dist_out ? dist_out + ((size_t)cloud * n + qq) * k : nullptr;
+      const unsigned int me0 = lane < c ? r[lane] : 0x7fffffffu, me1 = lane + 32 < c ? r[lane + 32] : 0x7fffffffu;
+      myscr[lane] = me0;
+      myscr[lane + 32] = me1;
+      __syncwarp();
+      int rk0 = 0, rk1 = 0;
+      const uint4 *sv = reinterpret_cast<const uint4 *>(myscr);
+      const int c4 = (c + 3) >> 2;
+      if (c <= 32) {
+#pragma unroll 2
+        for (int u = 0; u < c4; ++u) {
+          const uint4 kk = sv[u];
+          rk0 += ((kk.x - me0) >> 31) + ((kk.y - me0) >> 31) + ((kk.z - me0) >> 31) + ((kk.w - me0) >> 31);
         }
       } else {
-        for (int t2 = cnt; t2 < k; ++t2) {  // fewer than k candidates only with NaN / inf inputs
-          o[t2] = 0;
-          if (od) od[t2] = INF;
+#pragma unroll 2
+        for (int u = 0; u < c4; ++u) {
+          const uint4 kk = sv[u];
+          rk0 += ((kk.x - me0) >> 31) + ((kk.y - me0) >> 31) + ((kk.z - me0) >> 31) + ((kk.w - me0) >> 31);
+          rk1 += ((kk.x - me1) >> 31) + ((kk.y - me1) >> 31) + ((kk.z - me1) >> 31) + ((kk.w - me1) >> 31);
         }
-        const unsigned int *cb = reinterpret_cast<const unsigned int *>(candd);
-        for (int s0 = 0; s0 < cnt; s0 += 4) {  // four own candidates at a time against all of them
-          unsigned int me[4];
-          int rk[4] = {0, 0, 0, 0};
-#pragma unroll
-          for (int w = 0; w < 4; ++w) me[w] = cb[min(s0 + w, cnt - 1) * Q + e];
-#pragma unroll 4
-          for (int t2 = 0; t2 < cnt; ++t2) {
-            const unsigned int dt = cb[t2 * Q + e];
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              // dt < me, or dt == me and t2 earlier: compare 2*dt + [t2 >= own position] against 2*me + 1 ... written
-              // as two strict tests to stay in 32 bits
-              rk[w] += (dt < me[w] || (dt == me[w] && t2 < s0 + w)) ? 1 : 0;
-            }
-          }
-#pragma unroll
-          for (int w = 0; w < 4; ++w)
-            if (s0 + w < cnt && rk[w] < k) {
-              o[rk[w]] = (int64_t)cand[(s0 + w) * Q + e];
-              if (od) od[rk[w]] = __uint_as_float(me[w]);
-            }
+      }
+      const int ssum = __reduce_add_sync(0xffffffffu, (lane < c ? rk0 : 0) + (lane + 32 < c ? rk1 : 0));
+      if (ssum != c * (c - 1) / 2) {  // exact ties: break them by index
+        const unsigned int i0 = lane < c ? ri[lane] : 0xffffu, i1 = lane + 32 < c ? ri[lane + 32] : 0xffffu;
+        rk0 = rk1 = 0;
+        for (int u = 0; u < c; ++u) {
+          const unsigned int du = myscr[u], iu = ri[u];
+          rk0 += (du < me0 || (du == me0 && iu < i0)) ? 1 : 0;
+          rk1 += (du < me1 || (du == me1 && iu < i1)) ? 1 : 0;
         }
+      }
+      if (lane < c && rk0 < k) {
+        o[rk0] = (int64_t)ri[lane];
+        if (od) od[rk0] = __uint_as_float(me0);
+      }
+      if (lane + 32 < c && rk1 < k) {
+        o[rk1] = (int64_t)ri[lane + 32];
+        if (od) od[rk1] = __uint_as_float(me1);
+      }
+      for (int t2 = c + lane; t2 < k; t2 += 32) {  // fewer than k candidates only with NaN / inf inputs
+        o[t2] = 0;
+        if (od) od[t2] = INF;
+      }
+      __syncwarp();
+    }
+    if (q < n && cnt > CAP) {
+      // pathological ties (e.g. duplicated clouds): exact brute force over all references, sorted insertion into the
+      // query's own record
+      int64_t *o = idx_out + ((size_t)cloud * n + q) * k;
+      float *od = dist_out ? dist_out + ((size_t)cloud * n + q) * k : nullptr;
+      float *rd = reinterpret_cast<float *>(rec);
+      unsigned short *rix = reinterpret_cast<unsigned short *>(rec + CAP);
+      const float4 *xqg = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + q) * C);
+      int have = 0;
+      for (int j = 0; j < n; ++j) {
+        const float4 *xr = reinterpret_cast<const float4 *>(xT + ((size_t)cloud * n + j) * C);
+        float d = 0.f;
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+          const float4 aq = xqg[c4], ar = xr[c4];
+          const float t0 = aq.x - ar.x, t1 = aq.y - ar.y, t2 = aq.z - ar.z, t3 = aq.w - ar.w;
+          d = fmaf(t0, t0, d);
+          d = fmaf(t1, t1, d);
+          d = fmaf(t2, t2, d);
+          d = fmaf(t3, t3, d);
+        }
+        if (have == k && !(d < rd[k - 1])) continue;
+        int p = have < k ? have : k - 1;
+        while (p > 0 && d < rd[p - 1]) {
+          rd[p] = rd[p - 1];
+          rix[p] = rix[p - 1];
+          --p;
+        }
+        rd[p] = d;
+        rix[p] = (unsigned short)j;
+        if (have < k) ++have;
+      }
+      for (int t2 = 0; t2 < k; ++t2) {
+        o[t2] = t2 < have ? (int64_t)rix[t2] : 0;
+        if (od) od[t2] = t2 < have ? rd[t2] : INF;
       }
     }
   }

@@ -92,6 +92,12 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// inclusive warp scan step: adds the value `o` lanes below (shfl.up's predicate says whether that lane exists)
+__device__ __forceinline__ int scan_up_add(int v, int o) {
+  asm("{\n.reg .pred p;\n.reg .s32 t;\nshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n@p add.s32 %0, %0, t;\n}" : "+r"(v) : "r"(o));
+  return v;
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (UMMA SmemDescriptor, sm_100 version 1):
 // rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused for swizzled K-major layouts.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
