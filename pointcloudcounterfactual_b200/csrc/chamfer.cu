@@ -8,6 +8,8 @@
 //     reference points and resolved exactly at the end (lowest index wins ties, like the reference's strict '<').
 //   * ONE deterministic backward launch (CTA per cloud and direction, counting sort of the nearest-neighbour
 //     lists in shared memory, ordered segmented sums) instead of float atomics.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pcc {
@@ -153,6 +155,212 @@ nn_fwd_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restr
   }
   dout[j] = bd;
   iout[j] = bi;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward, symmetric: every unordered pair (i in cloud 1, j in cloud 2) is evaluated ONCE and feeds both directions
+// (the squared distance is bit-identical in both: the differences only change sign).  Halves the FP32-pipe work.
+//   unit (one warp)   128 rows i (4 consecutive per lane, registers) x 256 columns j (shared memory, broadcast)
+//     row side    running minimum per row in registers, argmin tracked per group of 8 columns (as nn_fwd_kernel)
+//     column side per column the minimum over the lane's 4 rows (3-input FMNMX), REDUX.MIN over the warp, the lowest
+//                 lane holding it (ballot): value + lane are the unit's partial result for that column
+//   CTA               4 units: the same 128 rows against 4 x 256 consecutive columns
+//   partial results   rows: (min, group) per (column chunk of 1024, row); columns: (min, lane) per (row block, column)
+//   nn_sym_finalize_kernel merges the partials (lowest chunk / block / lane wins ties = lowest index) and resolves the
+//                 exact index inside the winning group of 8 columns / the winning lane's 4 rows with the same arithmetic.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int NS_THREADS = 128;
+constexpr int NS_ROWS = 128;     // rows per CTA (4 per lane)
+constexpr int NS_WCOLS = 256;    // columns per warp
+constexpr int NS_CCOLS = 4 * NS_WCOLS;  // columns per CTA
+
+struct NnPart {
+  float v;
+  int loc;
+};
+
+__global__ void __launch_bounds__(NS_THREADS, 7)
+nn_sym_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2, int nrb, int ncc,
+              NnPart *__restrict__ rowpart, NnPart *__restrict__ colpart) {
+  __shared__ float4 tile[NS_CCOLS / 4 * 3];  // groups of 4 columns: X, Y, Z
+  __shared__ float cval[NS_CCOLS];           // per column: minimum over this CTA's rows
+  __shared__ int cloc[NS_CCOLS];             //             lowest lane attaining it
+  __shared__ float mbest[4][NS_ROWS];
+  __shared__ int mgrp[4][NS_ROWS];
+  const int rb = blockIdx.x / ncc, cc = blockIdx.x % ncc;
+  const size_t cloud = blockIdx.y;
+  const float *__restrict__ rp = xyz1 + cloud * (size_t)n * 3;  // rows
+  const float *__restrict__ cp = xyz2 + cloud * (size_t)m * 3;  // columns
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float INF = __int_as_float(0x7f800000);
+
+  float best[4], sx[4], sy[4], sz[4];
+  int grp[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = min(rb * NS_ROWS + lane * 4 + u, n - 1);
+    sx[u] = -rp[i * 3 + 0];
+    sy[u] = -rp[i * 3 + 1];
+    sz[u] = -rp[i * 3 + 2];
+    best[u] = INF;
+    grp[u] = 0;
+  }
+  // stage this CTA's columns (padding: +inf coordinates => +inf distance, never selected)
+  const int cbase = cc * NS_CCOLS;
+  const int ccnt = min(NS_CCOLS, m - cbase);
+  float *tf = reinterpret_cast<float *>(tile);
+  for (int i = threadIdx.x; i < NS_CCOLS; i += NS_THREADS) {
+    float x = INF, y = INF, z = INF;
+    if (i < ccnt) {
+      const float *p = cp + (size_t)(cbase + i) * 3;
+      x = p[0];
+      y = p[1];
+      z = p[2];
+    }
+    const int o = (i >> 2) * 12 + (i & 3);
+    tf[o] = x;
+    tf[o + 4] = y;
+    tf[o + 8] = z;
+  }
+  __syncthreads();
+
+  const int g0 = warp * (NS_WCOLS / 8);  // first group of 8 columns of this warp inside the CTA tile
+#pragma unroll 1
+  for (int g = g0; g < g0 + NS_WCOLS / 8; ++g) {
+    const float4 X0 = tile[g * 6 + 0], Y0 = tile[g * 6 + 1], Z0 = tile[g * 6 + 2];
+    const float4 X1 = tile[g * 6 + 3], Y1 = tile[g * 6 + 4], Z1 = tile[g * 6 + 5];
+    float cm[8];
+#pragma unroll
+    for (int up = 0; up < 2; ++up) {
+      float a[2][8];
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int u = 2 * up + w;
+        const f32x2 nqx = pack2(sx[u], sx[u]), nqy = pack2(sy[u], sy[u]), nqz = pack2(sz[u], sz[u]);
+        unpack2(sqdist2(pack2(X0.x, X0.y), pack2(Y0.x, Y0.y), pack2(Z0.x, Z0.y), nqx, nqy, nqz), a[w][0], a[w][1]);
+        unpack2(sqdist2(pack2(X0.z, X0.w), pack2(Y0.z, Y0.w), pack2(Z0.z, Z0.w), nqx, nqy, nqz), a[w][2], a[w][3]);
+        unpack2(sqdist2(pack2(X1.x, X1.y), pack2(Y1.x, Y1.y), pack2(Z1.x, Z1.y), nqx, nqy, nqz), a[w][4], a[w][5]);
+        unpack2(sqdist2(pack2(X1.z, X1.w), pack2(Y1.z, Y1.w), pack2(Z1.z, Z1.w), nqx, nqy, nqz), a[w][6], a[w][7]);
+        float mn = fminf(fminf(a[w][0], a[w][1]), best[u]);
+        mn = fminf(fminf(a[w][2], a[w][3]), mn);
+        mn = fminf(fminf(a[w][4], a[w][5]), mn);
+        mn = fminf(fminf(a[w][6], a[w][7]), mn);
+        grp[u] = (mn < best[u]) ? g : grp[u];  // strict: the first group reaching the minimum wins
+        best[u] = mn;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cm[e] = up ? fminf(fminf(a[0][e], a[1][e]), cm[e]) : fminf(a[0][e], a[1][e]);
+    }
+    // column minima over the warp's 128 rows: d >= 0 (or NaN, dropped by fminf), so unsigned order == float order
+    float mv[8];
+    int ml[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const unsigned int bits = __float_as_uint(cm[e]);
+      const unsigned int mn = __reduce_min_sync(0xffffffffu, bits);
+      mv[e] = __uint_as_float(mn);
+      ml[e] = __ffs(__ballot_sync(0xffffffffu, bits == mn)) - 1;
+    }
+    if (lane == 0) {
+      *reinterpret_cast<float4 *>(&cval[g * 8]) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      *reinterpret_cast<float4 *>(&cval[g * 8 + 4]) = make_float4(mv[4], mv[5], mv[6], mv[7]);
+      *reinterpret_cast<int4 *>(&cloc[g * 8]) = make_int4(ml[0], ml[1], ml[2], ml[3]);
+      *reinterpret_cast<int4 *>(&cloc[g * 8 + 4]) = make_int4(ml[4], ml[5], ml[6], ml[7]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    mbest[warp][lane * 4 + u] = best[u];
+    mgrp[warp][lane * 4 + u] = grp[u];
+  }
+  __syncthreads();
+  // column partials of this row block
+  NnPart *cpart = colpart + (cloud * (size_t)nrb + rb) * m;
+  for (int i = threadIdx.x; i < ccnt; i += NS_THREADS) cpart[cbase + i] = NnPart{cval[i], cloc[i]};
+  // row partials of this column chunk: merge the four warps (they cover ascending column ranges)
+  const int i = rb * NS_ROWS + (int)threadIdx.x;
+  if (i < n) {
+    float bd = mbest[0][threadIdx.x];
+    int bg = mgrp[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+      const float d = mbest[w][threadIdx.x];
+      if (d < bd) {
+        bd = d;
+        bg = mgrp[w][threadIdx.x];
+      }
+    }
+    rowpart[(cloud * (size_t)ncc + cc) * n + i] = NnPart{bd, cc * (NS_CCOLS / 8) + bg};
+  }
+}
+
+// one thread per point of either cloud: blockIdx.z = 0 rows (cloud 1 -> nearest in cloud 2), 1 columns
+__global__ void __launch_bounds__(256)
+nn_sym_finalize_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2, int nrb, int ncc,
+                       const NnPart *__restrict__ rowpart, const NnPart *__restrict__ colpart,
+                       float *__restrict__ dist1, int *__restrict__ idx1, float *__restrict__ dist2,
+                       int *__restrict__ idx2) {
+  const size_t cloud = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const float *__restrict__ p1 = xyz1 + cloud * (size_t)n * 3;
+  const float *__restrict__ p2 = xyz2 + cloud * (size_t)m * 3;
+  if (blockIdx.z == 0) {
+    if (t >= n) return;
+    const NnPart *rp = rowpart + cloud * (size_t)ncc * n + t;
+    NnPart b = rp[0];
+    for (int c = 1; c < ncc; ++c) {
+      const NnPart q = rp[(size_t)c * n];
+      if (q.v < b.v) b = q;  // strict: the lower chunk (lower indices) wins ties
+    }
+    const float qx = p1[t * 3], qy = p1[t * 3 + 1], qz = p1[t * 3 + 2];
+    int bi = -1;
+#pragma unroll
+    for (int e = 7; e >= 0; --e) {
+      const int r = b.loc * 8 + e;
+      if (r < m) {
+        const float d = sqdist1(qx, qy, qz, p2[(size_t)r * 3], p2[(size_t)r * 3 + 1], p2[(size_t)r * 3 + 2]);
+        if (d == b.v) bi = r;
+      }
+    }
+    float bd = b.v;
+    if (bi < 0) {  // nothing compared below +inf (NaN / inf inputs): the reference keeps element 0 (nndistance.cu:26)
+      bi = 0;
+      bd = sqdist1(qx, qy, qz, p2[0], p2[1], p2[2]);
+    }
+    dist1[cloud * (size_t)n + t] = bd;
+    idx1[cloud * (size_t)n + t] = bi;
+  } else {
+    if (t >= m) return;
+    const NnPart *cpp = colpart + cloud * (size_t)nrb * m + t;
+    NnPart b = cpp[0];
+    int brb = 0;
+    for (int r = 1; r < nrb; ++r) {
+      const NnPart q = cpp[(size_t)r * m];
+      if (q.v < b.v) {
+        b = q;
+        brb = r;
+      }
+    }
+    // the query of direction 2 is the column point; arithmetic d = fma(dz,dz,fma(dx,dx,dy*dy)) with d* = ref - query:
+    // the sign of the differences flips against direction 1, the squares do not => the same bits
+    const float qx = p2[t * 3], qy = p2[t * 3 + 1], qz = p2[t * 3 + 2];
+    int bi = -1;
+#pragma unroll
+    for (int u = 3; u >= 0; --u) {
+      const int r = brb * NS_ROWS + b.loc * 4 + u;
+      if (r < n) {
+        const float d = sqdist1(qx, qy, qz, p1[(size_t)r * 3], p1[(size_t)r * 3 + 1], p1[(size_t)r * 3 + 2]);
+        if (d == b.v) bi = r;
+      }
+    }
+    float bd = b.v;
+    if (bi < 0) {
+      bi = 0;
+      bd = sqdist1(qx, qy, qz, p1[0], p1[1], p1[2]);
+    }
+    dist2[cloud * (size_t)m + t] = bd;
+    idx2[cloud * (size_t)m + t] = bi;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -355,11 +563,27 @@ extern "C" __attribute__((visibility("default"))) int pcc_nndistance(int b, int 
   if (b < 0 || n < 0 || m < 0) return PCC_EINVAL;
   if (b == 0 || n == 0 || m == 0) return PCC_OK;  // nothing to compare against: outputs are left untouched
   if (b > 65535) return PCC_ENOTSUP;
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool asym = getenv("PCC_NN_ASYM") != nullptr;  // test hook: one launch per direction pair, no sharing
+  if (asym) {
+    const int mx = n > m ? n : m;
+    dim3 grid((mx + NN_QT - 1) / NN_QT, b, 2);
+    nn_fwd_kernel<<<grid, NN_THREADS, 0, st>>>(n, xyz, m, xyz2, result, result_i, result2, result2_i);
+    return finish_launch(1);
+  }
+  const int nrb = (n + NS_ROWS - 1) / NS_ROWS, ncc = (m + NS_CCOLS - 1) / NS_CCOLS;
+  if ((long long)nrb * ncc > 2147483647LL) return PCC_ENOTSUP;
+  NnPart *scratch = nullptr;
+  const size_t nrow = (size_t)b * ncc * n, ncol = (size_t)b * nrb * m;
+  cudaError_t e = cudaMallocAsync((void **)&scratch, sizeof(NnPart) * (nrow + ncol), st);
+  if (e != cudaSuccess) return (int)e;
+  NnPart *rowpart = scratch, *colpart = scratch + nrow;
+  nn_sym_kernel<<<dim3(nrb * ncc, b), NS_THREADS, 0, st>>>(n, xyz, m, xyz2, nrb, ncc, rowpart, colpart);
   const int mx = n > m ? n : m;
-  dim3 grid((mx + NN_QT - 1) / NN_QT, b, 2);
-  nn_fwd_kernel<<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, xyz, m, xyz2, result, result_i, result2,
-                                                                    result2_i);
-  return finish_launch(1);
+  nn_sym_finalize_kernel<<<dim3((mx + 255) / 256, b, 2), 256, 0, st>>>(n, xyz, m, xyz2, nrb, ncc, rowpart, colpart, result,
+                                                                      result_i, result2, result2_i);
+  cudaFreeAsync(scratch, st);
+  return finish_launch(2);
 }
 
 extern "C" __attribute__((visibility("default"))) int pcc_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2,
