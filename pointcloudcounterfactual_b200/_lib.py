@@ -6,12 +6,14 @@ a RuntimeError is raised.  torch is used only for device memory, streams and aut
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "_lib" / "libpcc_b200.so"
+# PCC_B200_LIB: alternative build of the same library (kernel A/B experiments on the GPU box)
+LIB_PATH = Path(os.environ["PCC_B200_LIB"]) if os.environ.get("PCC_B200_LIB") else _PKG / "_lib" / "libpcc_b200.so"
 _lib: ctypes.CDLL | None = None
 
 _vp = ctypes.c_void_p

@@ -160,31 +160,35 @@ nn_fwd_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restr
 // ------------------------------------------------------------------------------------------------------------
 // forward, symmetric: every unordered pair (i in cloud 1, j in cloud 2) is evaluated ONCE and feeds both directions
 // (the squared distance is bit-identical in both: the differences only change sign).  Halves the FP32-pipe work.
-//   unit (one warp)   128 rows i (4 consecutive per lane, registers) x 256 columns j (shared memory, broadcast)
-//     row side    running minimum per row in registers, argmin tracked per group of 8 columns (as nn_fwd_kernel)
-//     column side per column the minimum over the lane's 4 rows (3-input FMNMX), REDUX.MIN over the warp, the lowest
+//   unit (one warp)   256 rows i (8 consecutive per lane, registers) x 128 columns j (shared memory, broadcast)
+//     row side    running minimum per row in registers; which block of 32 columns reached it is noted once per block
+//     column side per column the minimum over the lane's 8 rows (3-input FMNMX), REDUX.MIN over the warp, the lowest
 //                 lane holding it (ballot): value + lane are the unit's partial result for that column
-//   CTA               4 units: the same 128 rows against 4 x 256 consecutive columns
-//   partial results   rows: (min, group) per (column chunk of 1024, row); columns: (min, lane) per (row block, column)
+//   CTA               4 units: the same 256 rows against 4 x 128 consecutive columns
+//   partial results   rows: (min, 32-column block) per (column chunk of 512, row); columns: (min, lane) per
+//                     (row block, column)
 //   nn_sym_finalize_kernel merges the partials (lowest chunk / block / lane wins ties = lowest index) and resolves the
-//                 exact index inside the winning group of 8 columns / the winning lane's 4 rows with the same arithmetic.
+//                 exact index inside the winning 32 columns / the winning lane's 8 rows with the same arithmetic.
+// 4096 units at B=32 x 2048 x 2048: 6.9 per SM sub-partition, so the FP32 pipes are evenly loaded.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NS_THREADS = 128;
-constexpr int NS_ROWS = 128;     // rows per CTA (4 per lane)
-constexpr int NS_WCOLS = 256;    // columns per warp
-constexpr int NS_CCOLS = 4 * NS_WCOLS;  // columns per CTA
+constexpr int NS_RPL = 8;                // rows per lane
+constexpr int NS_ROWS = 32 * NS_RPL;     // rows per CTA
+constexpr int NS_WCOLS = 128;            // columns per warp
+constexpr int NS_CCOLS = 4 * NS_WCOLS;   // columns per CTA
+constexpr int NS_SG = 32;                // columns per argmin block of the row side
 
 struct NnPart {
   float v;
   int loc;
 };
 
-__global__ void __launch_bounds__(NS_THREADS, 7)
+__global__ void __launch_bounds__(NS_THREADS, 4)
 nn_sym_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2, int nrb, int ncc,
               NnPart *__restrict__ rowpart, NnPart *__restrict__ colpart) {
   __shared__ float4 tile[NS_CCOLS / 4 * 3];  // groups of 4 columns: X, Y, Z
-  __shared__ float cval[NS_CCOLS];           // per column: minimum over this CTA's rows
-  __shared__ int cloc[NS_CCOLS];             //             lowest lane attaining it
+  __shared__ __align__(16) float cval[NS_CCOLS];  // per column: minimum over this CTA's rows
+  __shared__ __align__(16) int cloc[NS_CCOLS];    //             lowest lane attaining it
   __shared__ float mbest[4][NS_ROWS];
   __shared__ int mgrp[4][NS_ROWS];
   const int rb = blockIdx.x / ncc, cc = blockIdx.x % ncc;
@@ -194,15 +198,15 @@ nn_sym_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float INF = __int_as_float(0x7f800000);
 
-  float best[4], sx[4], sy[4], sz[4];
-  int grp[4];
+  float best[NS_RPL], prev[NS_RPL], sx[NS_RPL], sy[NS_RPL], sz[NS_RPL];
+  int grp[NS_RPL];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int i = min(rb * NS_ROWS + lane * 4 + u, n - 1);
+  for (int u = 0; u < NS_RPL; ++u) {
+    const int i = min(rb * NS_ROWS + lane * NS_RPL + u, n - 1);
     sx[u] = -rp[i * 3 + 0];
     sy[u] = -rp[i * 3 + 1];
     sz[u] = -rp[i * 3 + 2];
-    best[u] = INF;
+    best[u] = prev[u] = INF;
     grp[u] = 0;
   }
   // stage this CTA's columns (padding: +inf coordinates => +inf distance, never selected)
@@ -231,7 +235,7 @@ nn_sym_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restr
     const float4 X1 = tile[g * 6 + 3], Y1 = tile[g * 6 + 4], Z1 = tile[g * 6 + 5];
     float cm[8];
 #pragma unroll
-    for (int up = 0; up < 2; ++up) {
+    for (int up = 0; up < NS_RPL / 2; ++up) {
       float a[2][8];
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
@@ -244,14 +248,19 @@ nn_sym_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restr
         float mn = fminf(fminf(a[w][0], a[w][1]), best[u]);
         mn = fminf(fminf(a[w][2], a[w][3]), mn);
         mn = fminf(fminf(a[w][4], a[w][5]), mn);
-        mn = fminf(fminf(a[w][6], a[w][7]), mn);
-        grp[u] = (mn < best[u]) ? g : grp[u];  // strict: the first group reaching the minimum wins
-        best[u] = mn;
+        best[u] = fminf(fminf(a[w][6], a[w][7]), mn);
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) cm[e] = up ? fminf(fminf(a[0][e], a[1][e]), cm[e]) : fminf(a[0][e], a[1][e]);
     }
-    // column minima over the warp's 128 rows: d >= 0 (or NaN, dropped by fminf), so unsigned order == float order
+    if ((g & (NS_SG / 8 - 1)) == NS_SG / 8 - 1) {  // uniform: a block of 32 columns is complete
+#pragma unroll
+      for (int u = 0; u < NS_RPL; ++u) {
+        grp[u] = (best[u] < prev[u]) ? g : grp[u];  // strict: the first block reaching the minimum wins
+        prev[u] = best[u];
+      }
+    }
+    // column minima over the warp's 256 rows: d >= 0 (or NaN, dropped by fminf), so unsigned order == float order
     float mv[8];
     int ml[8];
 #pragma unroll
@@ -259,107 +268,104 @@ nn_sym_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restr
       const unsigned int bits = __float_as_uint(cm[e]);
       const unsigned int mn = __reduce_min_sync(0xffffffffu, bits);
       mv[e] = __uint_as_float(mn);
-      ml[e] = __ffs(__ballot_sync(0xffffffffu, bits == mn)) - 1;
+      ml[e] = (int)__ballot_sync(0xffffffffu, bits == mn);
     }
     if (lane == 0) {
       *reinterpret_cast<float4 *>(&cval[g * 8]) = make_float4(mv[0], mv[1], mv[2], mv[3]);
       *reinterpret_cast<float4 *>(&cval[g * 8 + 4]) = make_float4(mv[4], mv[5], mv[6], mv[7]);
-      *reinterpret_cast<int4 *>(&cloc[g * 8]) = make_int4(ml[0], ml[1], ml[2], ml[3]);
+      *reinterpret_cast<int4 *>(&cloc[g * 8]) = make_int4(ml[0], ml[1], ml[2], ml[3]);  // lane masks, decoded below
       *reinterpret_cast<int4 *>(&cloc[g * 8 + 4]) = make_int4(ml[4], ml[5], ml[6], ml[7]);
     }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    mbest[warp][lane * 4 + u] = best[u];
-    mgrp[warp][lane * 4 + u] = grp[u];
+  for (int u = 0; u < NS_RPL; ++u) {
+    mbest[warp][lane * NS_RPL + u] = best[u];
+    mgrp[warp][lane * NS_RPL + u] = grp[u];
   }
   __syncthreads();
   // column partials of this row block
   NnPart *cpart = colpart + (cloud * (size_t)nrb + rb) * m;
-  for (int i = threadIdx.x; i < ccnt; i += NS_THREADS) cpart[cbase + i] = NnPart{cval[i], cloc[i]};
+  for (int i = threadIdx.x; i < ccnt; i += NS_THREADS) cpart[cbase + i] = NnPart{cval[i], __ffs(cloc[i]) - 1};
   // row partials of this column chunk: merge the four warps (they cover ascending column ranges)
-  const int i = rb * NS_ROWS + (int)threadIdx.x;
-  if (i < n) {
-    float bd = mbest[0][threadIdx.x];
-    int bg = mgrp[0][threadIdx.x];
+  for (int r = threadIdx.x; r < NS_ROWS; r += NS_THREADS) {
+    const int i = rb * NS_ROWS + r;
+    if (i >= n) break;
+    float bd = mbest[0][r];
+    int bg = mgrp[0][r];
 #pragma unroll
     for (int w = 1; w < 4; ++w) {
-      const float d = mbest[w][threadIdx.x];
+      const float d = mbest[w][r];
       if (d < bd) {
         bd = d;
-        bg = mgrp[w][threadIdx.x];
+        bg = mgrp[w][r];
       }
     }
-    rowpart[(cloud * (size_t)ncc + cc) * n + i] = NnPart{bd, cc * (NS_CCOLS / 8) + bg};
+    rowpart[(cloud * (size_t)ncc + cc) * n + i] = NnPart{bd, (cc * (NS_CCOLS / 8) + bg) / (NS_SG / 8)};
   }
 }
 
-// one thread per point of either cloud: blockIdx.z = 0 rows (cloud 1 -> nearest in cloud 2), 1 columns
+// eight lanes per point of either cloud (blockIdx.z = 0: rows, cloud 1 -> nearest in cloud 2; 1: columns): the lanes
+// split the partial results, agree on the winner with three shuffles, then split the exact index search.
 __global__ void __launch_bounds__(256)
 nn_sym_finalize_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2, int nrb, int ncc,
                        const NnPart *__restrict__ rowpart, const NnPart *__restrict__ colpart,
                        float *__restrict__ dist1, int *__restrict__ idx1, float *__restrict__ dist2,
                        int *__restrict__ idx2) {
   const size_t cloud = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const float *__restrict__ p1 = xyz1 + cloud * (size_t)n * 3;
-  const float *__restrict__ p2 = xyz2 + cloud * (size_t)m * 3;
-  if (blockIdx.z == 0) {
-    if (t >= n) return;
-    const NnPart *rp = rowpart + cloud * (size_t)ncc * n + t;
-    NnPart b = rp[0];
-    for (int c = 1; c < ncc; ++c) {
-      const NnPart q = rp[(size_t)c * n];
-      if (q.v < b.v) b = q;  // strict: the lower chunk (lower indices) wins ties
+  const bool cols = blockIdx.z != 0;
+  const int sub = threadIdx.x & 7;
+  const int npts = cols ? m : n, nother = cols ? n : m, nparts = cols ? nrb : ncc;
+  const int t = min((int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3), npts - 1);  // clamped: all lanes stay in the shuffles
+  const bool writer = sub == 0 && (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3) < npts;
+  const float *__restrict__ pq = (cols ? xyz2 : xyz1) + cloud * (size_t)npts * 3;    // the point itself
+  const float *__restrict__ pr = (cols ? xyz1 : xyz2) + cloud * (size_t)nother * 3;  // the cloud it is matched against
+  const NnPart *part = (cols ? colpart : rowpart) + cloud * (size_t)nparts * npts + t;
+  const int BIG = 0x7fffffff;
+  float bv = __int_as_float(0x7f800000);
+  int bl = 0, bp = BIG;
+  for (int p = sub; p < nparts; p += 8) {
+    const NnPart q = part[(size_t)p * npts];
+    if (q.v < bv || bp == BIG) {  // ascending p per lane: strict keeps the lowest part on ties
+      bv = q.v;
+      bl = q.loc;
+      bp = p;
     }
-    const float qx = p1[t * 3], qy = p1[t * 3 + 1], qz = p1[t * 3 + 2];
-    int bi = -1;
+  }
 #pragma unroll
-    for (int e = 7; e >= 0; --e) {
-      const int r = b.loc * 8 + e;
-      if (r < m) {
-        const float d = sqdist1(qx, qy, qz, p2[(size_t)r * 3], p2[(size_t)r * 3 + 1], p2[(size_t)r * 3 + 2]);
-        if (d == b.v) bi = r;
-      }
+  for (int o = 1; o < 8; o <<= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int ol = __shfl_xor_sync(0xffffffffu, bl, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
+    if (ov < bv || (ov == bv && op < bp)) {
+      bv = ov;
+      bl = ol;
+      bp = op;
     }
-    float bd = b.v;
-    if (bi < 0) {  // nothing compared below +inf (NaN / inf inputs): the reference keeps element 0 (nndistance.cu:26)
-      bi = 0;
-      bd = sqdist1(qx, qy, qz, p2[0], p2[1], p2[2]);
-    }
-    dist1[cloud * (size_t)n + t] = bd;
-    idx1[cloud * (size_t)n + t] = bi;
-  } else {
-    if (t >= m) return;
-    const NnPart *cpp = colpart + cloud * (size_t)nrb * m + t;
-    NnPart b = cpp[0];
-    int brb = 0;
-    for (int r = 1; r < nrb; ++r) {
-      const NnPart q = cpp[(size_t)r * m];
-      if (q.v < b.v) {
-        b = q;
-        brb = r;
-      }
-    }
-    // the query of direction 2 is the column point; arithmetic d = fma(dz,dz,fma(dx,dx,dy*dy)) with d* = ref - query:
-    // the sign of the differences flips against direction 1, the squares do not => the same bits
-    const float qx = p2[t * 3], qy = p2[t * 3 + 1], qz = p2[t * 3 + 2];
-    int bi = -1;
+  }
+  // d = fma(dz,dz,fma(dx,dx,dy*dy)) with d* = ref - query: the sign of the differences flips between the two
+  // directions, the squares do not => the same bits as the value found by nn_sym_kernel
+  const float qx = pq[t * 3], qy = pq[t * 3 + 1], qz = pq[t * 3 + 2];
+  int bi = BIG;
+  if (!cols) {  // the winning block of 32 columns: 4 per lane
 #pragma unroll
-    for (int u = 3; u >= 0; --u) {
-      const int r = brb * NS_ROWS + b.loc * 4 + u;
-      if (r < n) {
-        const float d = sqdist1(qx, qy, qz, p1[(size_t)r * 3], p1[(size_t)r * 3 + 1], p1[(size_t)r * 3 + 2]);
-        if (d == b.v) bi = r;
-      }
+    for (int e = 3; e >= 0; --e) {
+      const int r = bl * NS_SG + sub * 4 + e;
+      if (r < nother && sqdist1(qx, qy, qz, pr[(size_t)r * 3], pr[(size_t)r * 3 + 1], pr[(size_t)r * 3 + 2]) == bv) bi = r;
     }
-    float bd = b.v;
-    if (bi < 0) {
+  } else {  // the winning lane's 8 rows: one per lane
+    const int r = bp * NS_ROWS + bl * NS_RPL + sub;
+    if (bp != BIG && r < nother &&
+        sqdist1(qx, qy, qz, pr[(size_t)r * 3], pr[(size_t)r * 3 + 1], pr[(size_t)r * 3 + 2]) == bv)
+      bi = r;
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) bi = min(bi, __shfl_xor_sync(0xffffffffu, bi, o));
+  if (writer) {
+    if (bi == BIG) {  // nothing compared below +inf (NaN / inf inputs): the reference keeps element 0 (nndistance.cu:26)
       bi = 0;
-      bd = sqdist1(qx, qy, qz, p1[0], p1[1], p1[2]);
+      bv = sqdist1(qx, qy, qz, pr[0], pr[1], pr[2]);
     }
-    dist2[cloud * (size_t)m + t] = bd;
-    idx2[cloud * (size_t)m + t] = bi;
+    (cols ? dist2 : dist1)[cloud * (size_t)npts + t] = bv;
+    (cols ? idx2 : idx1)[cloud * (size_t)npts + t] = bi;
   }
 }
 
@@ -580,7 +586,7 @@ extern "C" __attribute__((visibility("default"))) int pcc_nndistance(int b, int 
   NnPart *rowpart = scratch, *colpart = scratch + nrow;
   nn_sym_kernel<<<dim3(nrb * ncc, b), NS_THREADS, 0, st>>>(n, xyz, m, xyz2, nrb, ncc, rowpart, colpart);
   const int mx = n > m ? n : m;
-  nn_sym_finalize_kernel<<<dim3((mx + 255) / 256, b, 2), 256, 0, st>>>(n, xyz, m, xyz2, nrb, ncc, rowpart, colpart, result,
+  nn_sym_finalize_kernel<<<dim3((mx + 31) / 32, b, 2), 256, 0, st>>>(n, xyz, m, xyz2, nrb, ncc, rowpart, colpart, result,
                                                                       result_i, result2, result2_i);
   cudaFreeAsync(scratch, st);
   return finish_launch(2);
