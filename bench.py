@@ -34,7 +34,8 @@ N_POINTS = 2048
 KNN_N, KNN_K, KNN_C = 1024, 20, 64
 METRIC = "chamfer_emd_fwd_bwd_clouds_per_sec"
 WORKLOAD = ("ChamferEMD recon loss fwd+bwd (pykeops_chamfer + match_cost), B=32 x 2048 xyz points per GPU, "
-            "S1 synthetic ShapeNet-shaped clouds (BASELINE configs[0]+[2]); kNN k=20 N=1024 C=3/64 in sub_metrics (configs[1])")
+            "S1 synthetic ShapeNet-shaped clouds (BASELINE configs[0]+[2]); kNN graphs/s k=20 N=1024 C=3/64 "
+            "(configs[1]) in sub_metrics")
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -243,13 +244,22 @@ def run_b200(args) -> None:
     mufu_peak = pipe.get("mufu_ex2_gops", 148 * 16 * 1.965) if rank == 0 else 1.0
     fp32_peak = pipe.get("ffma_tflops", 74.4) if rank == 0 else 1.0
     roofline = {
-        "kernel": "am_rowsum_kernel (approxmatch sweep; 27 launches per step)",
+        "kernel": "am_sweep_kernel (approxmatch solver sweep: 27 sweeps per step in 19 launches, 9 of them two sweeps fused)",
         "bound": "sfu", "unit": "Gexp/s", "achieved": pairs / (sweep_ms * 1e-3) / 1e9, "peak": mufu_peak,
-        "frac": pairs / (sweep_ms * 1e-3) / 1e9 / mufu_peak, "traffic": None,
+        "frac": pairs / (sweep_ms * 1e-3) / 1e9 / mufu_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one am_sweep_kernel launch, ncu --set full capture
+        # (profiles/r01b_ncu_full_summary.md): the clouds and the scaling vectors, everything else stays on chip
+        "traffic": 2108416,
+        "hbm_view": {"algorithmic_bytes": 3 * B_PER_GPU * N_POINTS * 4 * 2 + 3 * B_PER_GPU * N_POINTS * 4,
+                     "achieved_gbs": 2108416 / (sweep_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                     "frac": 2108416 / (sweep_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "note": "not HBM-bound: 2 MB per launch against 134 M exponentials"},
         "peak_source": pipe.get("source", ""), "launch_ms": sweep_ms,
         "fp32_tflops": 11 * pairs / (sweep_ms * 1e-3) / 1e12, "fp32_frac": 11 * pairs / (sweep_ms * 1e-3) / 1e12 / fp32_peak,
         "share_of_step": 27 * sweep_ms / (sum(times) / K),
-        "note": "1 MUFU.EX2 + 11 flop per pair; the SFU pipe (16 lanes/SM) bounds the kernel, not HBM or tensor cores",
+        "algorithmic_unit": "exp-pair evaluations: B*n*m = 134.2 M per sweep launch (DESIGN.md section 4)",
+        "note": "1 MUFU.EX2 + 11 flop per pair; the SFU pipe (16 lanes/SM) bounds the kernel, not HBM or tensor cores; "
+                "share_of_step counts 27 single-sweep durations (the fused launches run two sweeps in ~1.7 of them)",
     }
 
     # ---- sub-metrics ----------------------------------------------------------------------------------------
@@ -299,16 +309,24 @@ def run_b200(args) -> None:
                                                "peak": fp32_peak, "frac": flops / (ms * 1e-3) / 1e12 / fp32_peak}}
         ms, gr = graph_or_eager(emd_fb, reps=10)
         sub["emd_fwd_bwd"] = {"ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr}
+        tf32_peak = peaks["bf16_tflops"] / 2.0  # dense TF32 = half the bf16 tensor rate (nominal 1.1 vs 2.25 PFLOP/s)
         for name, x, k, c in (("knn_xyz_k20_n1024", x3, KNN_K, 3), ("knn_feat64_k20_n1024", xf, KNN_K, KNN_C),
                               ("knn_xyz_k25_n2048", x25, 25, 3), ("knn_xyz_k4_n2048", x25, 4, 3)):
             ms, gr = graph_or_eager(lambda x=x, k=k: neighbour_ops.knn(x, k))
             n = x.shape[2]
-            fl = (8.0 if c == 3 else 3.0 * c) * B_PER_GPU * n * n
-            sub[name] = {"ms": ms, "graphs_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
-                         "roofline": {"bound": "fp32", "unit": "TFLOP/s", "achieved": fl / (ms * 1e-3) / 1e12,
-                                      "peak": fp32_peak, "frac": fl / (ms * 1e-3) / 1e12 / fp32_peak,
-                                      "note": "exact fp32 direct-difference path (sub+fma per channel); "
-                                              "tcgen05 candidate-generator path not yet enabled"}}
+            if c == 3:
+                fl = 8.0 * B_PER_GPU * n * n
+                rl = {"bound": "fp32", "unit": "TFLOP/s", "achieved": fl / (ms * 1e-3) / 1e12, "peak": fp32_peak,
+                      "frac": fl / (ms * 1e-3) / 1e12 / fp32_peak,
+                      "note": "warp-cooperative exact fp32 kernel (references in registers); 8 flop per pair, selection "
+                              "(threshold, compaction, ranking) is not counted as work"}
+            else:
+                fl = 2.0 * c * B_PER_GPU * n * n  # algorithmic: one -2 X X^T contraction
+                rl = {"bound": "tensor", "unit": "TFLOP/s", "achieved": fl / (ms * 1e-3) / 1e12, "peak": tf32_peak,
+                      "frac": fl / (ms * 1e-3) / 1e12 / tf32_peak, "peak_source": "MEASURED_PEAKS bf16 / 2 (TF32)",
+                      "note": "tcgen05 kind::tf32 candidate generator (issues the contraction twice) + exact fp32 re-rank "
+                              "from the shared-memory key tiles; time includes the transpose/norm prep launch"}
+            sub[name] = {"ms": ms, "graphs_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr, "roofline": rl}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
