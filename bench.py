@@ -350,7 +350,7 @@ def run_b200(args) -> None:
             "peaks": {**peaks, "pipe": pipe},
             "sub_metrics": sub,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -414,10 +414,29 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all0,
     }
-    print(json.dumps(out))
+    emit(out)
+
+
+def _claim_stdout() -> None:
+    """Libraries print to stdout (NCCL's version banner under torchrun): keep fd 1 for the ONE JSON line by pointing it
+    at stderr for everything else; print() below writes to the saved descriptor."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_JSON_OUT = None
+
+
+def emit(obj: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":
+    _claim_stdout()
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
