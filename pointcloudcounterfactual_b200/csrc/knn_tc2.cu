@@ -9,7 +9,7 @@
 //            plus the tile's squared norms (cp.async.bulk), two stages.
 //   warp 1   MMA issuer: tcgen05.mma kind::tf32 M=128 x N=R x K=8 into TMEM accumulator `stage` of each half.
 //   warps 2+ epilogue, one thread per query (tcgen05.ld of its accumulator row), two sweeps over the key tiles:
-//     sweep 1  score = |x_j|^2 - 2 x_i.x_j; one minimum per group of 32 keys.  tau = k-th smallest group minimum
+//     sweep 1  score = |x_j|^2 - 2 x_i.x_j; one minimum per group of 16 or 32 keys (at most 64 groups).  tau = k-th smallest group minimum
 //              (bitonic network in registers) bounds the k-th smallest score from above.
 //     sweep 2  the accumulators are recomputed (the tensor pipe is idle otherwise); keys with score <= tau + 2 eps are
 //              candidates.  The warp compacts its (query, key) pairs and spreads them evenly over its lanes; each
@@ -100,6 +100,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int q0 = blockIdx.x * Q;
   const int ntile = npad / R;
   const int niter = 2 * ntile;
+  const bool fine = ntile * CHUNKS <= 32;  // group minima over 16 instead of 32 keys while at most 64 groups result
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -223,15 +224,23 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           uint32_t v[32];
           tmem_ld32_issue(taddr + (uint32_t)(ch * 32), v);
           tmem_ld_wait();
-          float m = INF;
+          float mlo = INF, mhi = INF;  // minima of the two groups of 16 keys of this chunk
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 w = *reinterpret_cast<const float4 *>(rns + ch * 32 + 4 * g);
             const float z0 = fmaf(-2.f, __uint_as_float(v[4 * g + 0]), w.x), z1 = fmaf(-2.f, __uint_as_float(v[4 * g + 1]), w.y),
                         z2 = fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z), z3 = fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w);
-            m = fminf(fminf(z0, z1), fminf(fminf(z2, z3), m));
+            if (g < 4)
+              mlo = fminf(fminf(z0, z1), fminf(fminf(z2, z3), mlo));
+            else
+              mhi = fminf(fminf(z0, z1), fminf(fminf(z2, z3), mhi));
           }
-          rec[t * CHUNKS + ch] = __float_as_uint(m);
+          if (fine) {  // n <= 1024: 64 groups of 16 (tighter tau, fewer candidates to re-rank)
+            rec[(t * CHUNKS + ch) * 2] = __float_as_uint(mlo);
+            rec[(t * CHUNKS + ch) * 2 + 1] = __float_as_uint(mhi);
+          } else {
+            rec[t * CHUNKS + ch] = __float_as_uint(fminf(mlo, mhi));
+          }
         }
         fence_before();
         __syncwarp();
@@ -241,7 +250,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         if (i == ntile - 1) {
           // ---- tau = k-th smallest of the ng <= 64 group minima (at least k groups hold a key with score <= tau) ----
-          const int ng = ntile * CHUNKS;
+          const int ng = ntile * CHUNKS * (fine ? 2 : 1);
           float a[32];
 #pragma unroll
           for (int u = 0; u < 32; ++u) a[u] = (u < ng) ? __uint_as_float(rec[u]) : INF;
