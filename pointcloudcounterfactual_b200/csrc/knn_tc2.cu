@@ -312,6 +312,9 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             rix[p] = vi;
           }
           cnt = k;
+          // the k-th best exact distance so far bounds the final one: a key of the final top-k has
+          // score <= d - |x_q|^2 + eps <= rd[k-1] - |x_q|^2 + eps, usually far below tau + 2 eps
+          thr = fminf(thr, (rd[k - 1] - nq + eps) * (rd[k - 1] - nq + eps > 0.f ? 1.000001f : 0.999999f) + 1e-30f);
         }
         __syncwarp();
         // ---- (query, key) pairs of the whole warp, compacted so that the exact re-rank is spread evenly over the
