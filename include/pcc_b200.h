@@ -55,6 +55,17 @@ int pcc_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2
                        const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
                        float *grad_xyz2, pcc_stream_t stream);
 
+/* Fused Chamfer loss behind `pykeops_chamfer` / `torch_chamfer` (src/train/metrics_and_losses.py:21-47):
+ * loss[b] = scale1 * sum_j dist1[b,j] + scale2 * sum_k dist2[b,k]  (scale = 1/points for the mean form, 1 for the sum
+ * form), with dist/idx exactly as pcc_nndistance writes them (kept for the backward).  Deterministic reduction. */
+int pcc_chamfer_reduce(int b, int n, const float *xyz1, int m, const float *xyz2, float scale1, float scale2,
+                       float *loss, float *dist1, int *idx1, float *dist2, int *idx2, pcc_stream_t stream);
+/* Its backward: pcc_nndistancegrad with the upstream gradient grad_loss[b] * scale1 (scale2) for every point of cloud
+ * 1 (2), without materialising the per-point gradient arrays.  PCC_ENOTSUP for clouds above 16k points. */
+int pcc_chamfer_reduce_grad(int b, int n, const float *xyz1, int m, const float *xyz2, const int *idx1,
+                            const int *idx2, const float *grad_loss, float scale1, float scale2, float *grad_xyz1,
+                            float *grad_xyz2, pcc_stream_t stream);
+
 /* ---- Approximate-matching EMD -----------------------------------------------------------------------
  * Replaces `void approxmatch(int b,int n,int m,const float*xyz1,const float*xyz2,float*match,float*temp,
  *                            cudaStream_t)` (structural_loss.cpp:10, approxmatch.cu:299-307).

@@ -26,6 +26,8 @@ _SIGNATURES = {
     "pcc_launch_count": (ctypes.c_uint64, []),
     "pcc_nndistance": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_nndistancegrad": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcc_chamfer_reduce": (_i, [_i, _i, _vp, _i, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcc_chamfer_reduce_grad": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
     "pcc_approxmatch": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pcc_matchcost": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pcc_matchcostgrad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

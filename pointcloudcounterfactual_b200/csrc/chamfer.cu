@@ -403,10 +403,13 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_tot, int *t
   return warp_tot[w] + inc - v;
 }
 
+// Upstream gradients: per point (gd1, gd2), or -- for the fused reduced loss -- per cloud: gcloud[b] * s1 for every
+// point of cloud 1 and gcloud[b] * s2 for every point of cloud 2 (gd1 == gd2 == nullptr).
 __global__ void __launch_bounds__(NG_THREADS)
 nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2,
                const float *__restrict__ gd1, const int *__restrict__ idx1, const float *__restrict__ gd2,
-               const int *__restrict__ idx2, float *__restrict__ g1, float *__restrict__ g2) {
+               const int *__restrict__ idx2, float *__restrict__ g1, float *__restrict__ g2,
+               const float *__restrict__ gcloud, float s1, float s2) {
   extern __shared__ int sm[];
   __shared__ int warp_tot[32];
   __shared__ int scan_total;
@@ -418,8 +421,10 @@ nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__rest
   const int nT = dir ? m : n, nS = dir ? n : m;
   const float *__restrict__ xT = (dir ? xyz2 : xyz1) + cloud * (size_t)nT * 3;
   const float *__restrict__ xS = (dir ? xyz1 : xyz2) + cloud * (size_t)nS * 3;
-  const float *__restrict__ gT = (dir ? gd2 : gd1) + cloud * (size_t)nT;
-  const float *__restrict__ gS = (dir ? gd1 : gd2) + cloud * (size_t)nS;
+  const bool per_cloud = gcloud != nullptr;
+  const float *__restrict__ gT = per_cloud ? nullptr : (dir ? gd2 : gd1) + cloud * (size_t)nT;
+  const float *__restrict__ gS = per_cloud ? nullptr : (dir ? gd1 : gd2) + cloud * (size_t)nS;
+  const float gcT = per_cloud ? gcloud[cloud] * (dir ? s2 : s1) : 0.f, gcS = per_cloud ? gcloud[cloud] * (dir ? s1 : s2) : 0.f;
   const int *__restrict__ iT = (dir ? idx2 : idx1) + cloud * (size_t)nT;  // target -> nearest source
   const int *__restrict__ iS = (dir ? idx1 : idx2) + cloud * (size_t)nS;  // source -> nearest target
   float *__restrict__ out = (dir ? g2 : g1) + cloud * (size_t)nT * 3;
@@ -473,11 +478,11 @@ nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__rest
     }
     const float tx = xT[j * 3], ty = xT[j * 3 + 1], tz = xT[j * 3 + 2];
     const int k = min(max(iT[j], 0), nS - 1);
-    const float g = gT[j] * 2.f;
+    const float g = (per_cloud ? gcT : gT[j]) * 2.f;
     float ax = g * (tx - xS[k * 3]), ay = g * (ty - xS[k * 3 + 1]), az = g * (tz - xS[k * 3 + 2]);
     for (int a = s; a < e; ++a) {
       const int l = slots[a];
-      const float gl = gS[l] * 2.f;
+      const float gl = (per_cloud ? gcS : gS[l]) * 2.f;
       ax += -(gl * (xS[l * 3] - tx));
       ay += -(gl * (xS[l * 3 + 1] - ty));
       az += -(gl * (xS[l * 3 + 2] - tz));
@@ -496,7 +501,7 @@ nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__rest
     float ax = 0.f, ay = 0.f, az = 0.f;
     for (int l = threadIdx.x; l < nS; l += NG_THREADS) {
       if (min(max(iS[l], 0), nT - 1) == j) {
-        const float gl = gS[l] * 2.f;
+        const float gl = (per_cloud ? gcS : gS[l]) * 2.f;
         ax += -(gl * (xS[l * 3] - tx));
         ay += -(gl * (xS[l * 3 + 1] - ty));
         az += -(gl * (xS[l * 3 + 2] - tz));
@@ -513,7 +518,7 @@ nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__rest
     __syncthreads();
     if (threadIdx.x == 0) {
       const int k = min(max(iT[j], 0), nS - 1);
-      const float g = gT[j] * 2.f;
+      const float g = (per_cloud ? gcT : gT[j]) * 2.f;
       float sx = g * (tx - xS[k * 3]), sy = g * (ty - xS[k * 3 + 1]), sz = g * (tz - xS[k * 3 + 2]);
       for (int w = 0; w < NG_THREADS / 32; ++w) {
         sx += red[0][w];
@@ -525,6 +530,32 @@ nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__rest
       out[j * 3 + 2] = sz;
     }
     __syncthreads();
+  }
+}
+
+// loss[b] = s1 * sum_j dist1[b][j] + s2 * sum_k dist2[b][k]: fixed summation order (deterministic)
+__global__ void __launch_bounds__(256)
+nn_reduce_kernel(int n, int m, const float *__restrict__ dist1, const float *__restrict__ dist2, float s1, float s2,
+                 float *__restrict__ loss) {
+  __shared__ float red[2][8];
+  const size_t cloud = blockIdx.x;
+  float a = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) a += dist1[cloud * (size_t)n + i];
+  for (int i = threadIdx.x; i < m; i += 256) c += dist2[cloud * (size_t)m + i];
+  a = warp_sum(a);
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = a;
+    red[1][threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sa = 0.f, sc = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      sa += red[0][w];
+      sc += red[1][w];
+    }
+    loss[cloud] = s2 * sc + s1 * sa;
   }
 }
 
@@ -614,7 +645,7 @@ extern "C" __attribute__((visibility("default"))) int pcc_nndistancegrad(int b, 
       attr_set = true;
     }
     nn_grad_kernel<<<dim3(b, 2), NG_THREADS, smem, st>>>(n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2,
-                                                          grad_xyz1, grad_xyz2);
+                                                          grad_xyz1, grad_xyz2, nullptr, 0.f, 0.f);
     return finish_launch(1);
   }
   const int threads = 256;
@@ -624,4 +655,35 @@ extern "C" __attribute__((visibility("default"))) int pcc_nndistancegrad(int b, 
   nn_grad_scatter_kernel<<<g1 < 65535 * 16 ? g1 : 65535 * 16, threads, 0, st>>>(b, n, xyz1, m, xyz2, grad_dist1, idx1, grad_xyz2);
   nn_grad_scatter_kernel<<<g2 < 65535 * 16 ? g2 : 65535 * 16, threads, 0, st>>>(b, m, xyz2, n, xyz1, grad_dist2, idx2, grad_xyz1);
   return finish_launch(4);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_chamfer_reduce(int b, int n, const float *xyz1, int m, const float *xyz2, float scale1,
+                                  float scale2, float *loss, float *dist1, int *idx1, float *dist2, int *idx2,
+                                  pcc_stream_t stream) {
+  if (b < 0 || n <= 0 || m <= 0) return PCC_EINVAL;
+  if (b == 0) return PCC_OK;
+  int rc = pcc_nndistance(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, stream);
+  if (rc != 0) return rc;
+  nn_reduce_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(n, m, dist1, dist2, scale1, scale2, loss);
+  return finish_launch(1);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_chamfer_reduce_grad(int b, int n, const float *xyz1, int m, const float *xyz2,
+                                       const int *idx1, const int *idx2, const float *grad_loss, float scale1,
+                                       float scale2, float *grad_xyz1, float *grad_xyz2, pcc_stream_t stream) {
+  if (b < 0 || n <= 0 || m <= 0) return PCC_EINVAL;
+  if (b == 0) return PCC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t mx = n > m ? n : m;
+  const size_t smem = sizeof(int) * (2 * mx + mx + mx / (NG_HEAVY + 1) + 8);
+  if (smem > 200 * 1024 || b > 65535) return PCC_ENOTSUP;  // caller falls back to per-point upstream gradients
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(nn_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  nn_grad_kernel<<<dim3(b, 2), NG_THREADS, smem, st>>>(n, xyz1, m, xyz2, nullptr, idx1, nullptr, idx2, grad_xyz1, grad_xyz2,
+                                                        grad_loss, scale1, scale2);
+  return finish_launch(1);
 }

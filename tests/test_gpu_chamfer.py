@@ -116,3 +116,23 @@ def test_full_size_properties(cuda):
 def test_empty_batch(cuda):
     d1, i1, d2, i2 = NNDistance(torch.zeros(0, 16, 3, device=cuda), torch.zeros(0, 8, 3, device=cuda))
     assert d1.shape == (0, 16) and i2.shape == (0, 8)
+
+
+@pytest.mark.parametrize("b,n,m", [(3, 512, 512), (2, 300, 777), (2, 2048, 2048), (1, 5, 1)])
+def test_fused_chamfer_losses_match_the_unfused_composition(cuda, b, n, m):
+    """pykeops_chamfer / torch_chamfer run as one fused forward (+ reduction) and ONE backward launch; they must agree
+    with nn_distance followed by torch reductions, value and gradients, for non-uniform upstream gradients."""
+    a, c = synthetic.s2_far(b, max(n, 2), max(m, 2))
+    a, c = a[:, :n].contiguous().to(cuda), c[:, :m].contiguous().to(cuda)
+    w = torch.linspace(-1.0, 2.0, b, device=cuda)
+    for fused, mean in ((losses.pykeops_chamfer, True), (losses.torch_chamfer, False)):
+        x, y = a.clone().requires_grad_(True), c.clone().requires_grad_(True)
+        loss = fused(x, y)
+        (loss * w).sum().backward()
+        u, v = a.clone().requires_grad_(True), c.clone().requires_grad_(True)
+        d1, d2 = nn_distance(u, v)
+        ref = d2.mean(1) + d1.mean(1) if mean else d1.sum(1) + d2.sum(1)
+        (ref * w).sum().backward()
+        assert rel_err(loss.detach().cpu().numpy(), ref.detach().cpu().numpy()) < TOL
+        assert rel_err(x.grad.cpu().numpy(), u.grad.cpu().numpy()) < TOL
+        assert rel_err(y.grad.cpu().numpy(), v.grad.cpu().numpy()) < TOL
