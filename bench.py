@@ -297,6 +297,8 @@ def run_b200(args) -> None:
         xf = synthetic.knn_features(B_PER_GPU, KNN_C, KNN_N, seed=2000 + rank).to(dev)
         x25 = synthetic.knn_xyz(B_PER_GPU, N_POINTS, first=rank * B_PER_GPU).to(dev)
 
+        f64a_ = synthetic.knn_features(B_PER_GPU, 64, N_POINTS, seed=3000 + rank).to(dev)
+
         ms, gr = graph_or_eager(chamfer_f)
         flops = 8.0 * 2 * B_PER_GPU * N_POINTS * N_POINTS
         sub["chamfer_fwd"] = {"ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
@@ -327,6 +329,70 @@ def run_b200(args) -> None:
                       "note": "tcgen05 kind::tf32 candidate generator (issues the contraction twice) + exact fp32 re-rank "
                               "from the shared-memory key tiles; time includes the transpose/norm prep launch"}
             sub[name] = {"ms": ms, "graphs_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr, "roofline": rl}
+
+        # ---- EdgeConv front-end: get_graph_features forward / backward, HBM-bound -----------------------
+        idx25 = neighbour_ops.knn(f64a_, 25)
+        fa = f64a_.detach().requires_grad_(True)
+        gf_bytes = 2 * 64 * B_PER_GPU * N_POINTS * 25 * 4  # the (B,2C,N,k) tensor: written once fwd, read once bwd
+
+        def gf_fwd():
+            neighbour_ops.get_graph_features(f64a_, idx25, 25)
+
+        feat = neighbour_ops.get_graph_features(fa, idx25, 25)[1]
+        gfeat = torch.ones_like(feat)
+
+        def gf_bwd():
+            torch.autograd.grad(feat, fa, gfeat, retain_graph=True)
+
+        for nm, fn in (("graph_features_c64_n2048_k25_fwd", gf_fwd), ("graph_features_c64_n2048_k25_bwd", gf_bwd)):
+            ms, gr = graph_or_eager(fn, reps=10)
+            sub[nm] = {"ms": ms, "cuda_graph": gr,
+                       "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": gf_bytes / (ms * 1e-3) / 1e9,
+                                    "peak": peaks["hbm_gbs"], "frac": gf_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                    "algorithmic_bytes": gf_bytes,
+                                    "note": "the (B,2C,N,k) feature tensor crosses HBM once; x and idx stay in L2"}}
+        del feat, gfeat
+
+        # ---- BASELINE configs[3] / [4]: the reference's models cannot be instantiated here (drytorch / hydra are not
+        # installed), so these are the hot-path op sequences of one training step / one latent-optimisation
+        # iteration, per GPU, with the step's real collective ------------------------------------------------------
+        f64a = f64a_
+        f64b = synthetic.knn_features(B_PER_GPU, 64, N_POINTS, seed=3100 + rank).to(dev)
+        f128 = synthetic.knn_features(B_PER_GPU, 128, N_POINTS, seed=3200 + rank).to(dev)
+        grad_buf = torch.zeros(45 * (1 << 20) // 4, device=dev)  # ~45 MB of fp32 autoencoder gradients
+
+        def ae_step():
+            neighbour_ops.knn(x25, 25)      # encoder EdgeConv 1 (xyz)
+            neighbour_ops.knn(f64a, 25)     # EdgeConv 2, 3 (64 channels)
+            neighbour_ops.knn(f64b, 25)
+            neighbour_ops.knn(f128, 25)     # EdgeConv 4 (128 channels)
+            neighbour_ops.knn(rr.detach().transpose(1, 2).contiguous(), 4)  # decoder graph_filtering
+            loss = losses.chamfer_emd(rr, ref_d)
+            torch.autograd.grad(loss.sum(), rr)
+            if world > 1:
+                dist.all_reduce(grad_buf)
+
+        ms = ev_time(ae_step, 10) if world > 1 else graph_or_eager(ae_step, reps=10)[0]
+        sub["ae_step_hotpath"] = {
+            "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": world == 1,
+            "note": "stand-in for configs[3]: kNN k=25 N=2048 on C=3,64,64,128 + decoder kNN k=4 + ChamferEMD fwd+bwd"
+                    + (" + NCCL all-reduce of 45 MB fp32 gradients" if world > 1 else "") + "; 32 clouds per GPU"}
+
+        leaf = recon_d.detach().clone().requires_grad_(True)
+        opt = torch.optim.Adam([leaf], lr=1e-3, capturable=True)
+
+        def generate_iter():
+            neighbour_ops.knn(leaf.detach().transpose(1, 2).contiguous(), 4)
+            loss = losses.pykeops_chamfer(leaf, ref_d)
+            opt.zero_grad(set_to_none=False)
+            loss.sum().backward()
+            opt.step()
+
+        ms, gr = graph_or_eager(generate_iter, reps=20)
+        sub["generate_loop_iter"] = {
+            "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
+            "note": "synthetic stand-in for configs[4] (the reference's generate.py has no optimisation loop): kNN k=4 + "
+                    "Chamfer fwd+bwd w.r.t. the cloud + Adam on a (32,2048,3) leaf per GPU"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -105,6 +105,20 @@ int pcc_knn(int b, int c, int n, int k, const float *x, int64_t *idx, float *dis
 int pcc_argkmin(int b, int nq, int nr, int c, int k, const float *q, const float *r, int64_t *idx, float *dist,
                 pcc_stream_t stream);
 
+/* ---- EdgeConv front-end ----------------------------------------------------------------
+ * Replaces the torch composition of get_neighbours (src/utils/neighbour_ops.py:85-94: expand + torch.gather) and
+ * get_graph_features (:113-119: gather, expand, subtract, cat, contiguous) with one pass that writes the result once.
+ * x (b,c,n) channels-first fp32, idx (b,n,k) int64 (as produced by pcc_knn or passed in by the caller).
+ *   mode 0: out (b,c,n,k)   out[c][i][t] = x[c][idx[i][t]]
+ *   mode 1: out (b,2c,n,k)  out[c][i][t] = x[c][idx[i][t]] - x[c][i],  out[c+C][i][t] = x[c][i]
+ * Indices outside [0,n) are clamped (torch.gather raises).  PCC_ENOTSUP for k > 32 or n > 8192 (caller composes). */
+int pcc_graph_gather(int b, int c, int n, int k, const float *x, const int64_t *idx, int mode, float *out,
+                     pcc_stream_t stream);
+/* Its backward w.r.t. x: grad_x (b,c,n) is fully written; scatter-add by shared-memory float atomics (summation order
+ * not fixed, like the backward of torch.gather). */
+int pcc_graph_gather_grad(int b, int c, int n, int k, const int64_t *idx, int mode, const float *grad_out,
+                          float *grad_x, pcc_stream_t stream);
+
 /* ---- Auction EMD ------------------------------------------------------------------------------------
  * Replaces `int emd_cuda_forward(at::Tensor xyz1, ..., float eps, int iters)` (external/emd/src/emd.cpp:14-21,
  * emd_cuda.cu:227-281) with the tensors passed as raw pointers in the same order.  The caller allocates and

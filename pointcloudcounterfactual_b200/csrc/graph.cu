@@ -1,0 +1,168 @@
+// EdgeConv front-end: neighbour gather and graph features for sm_100a, forward and backward.
+//
+// Replaces the torch composition behind src/utils/neighbour_ops.py:85-94 (get_neighbours: view/expand + torch.gather)
+// and :113-119 (get_graph_features: gather, expand, subtract, cat, contiguous -- three (B,C,N,k) temporaries and one
+// (B,2C,N,k) result, the tensors that dominate the encoder's memory traffic) with one pass that writes
+// the result once:
+//   mode 0  out (B,C,N,k):   out[c][i][t] = x[c][idx[i][t]]
+//   mode 1  out (B,2C,N,k):  out[c][i][t] = x[c][idx[i][t]] - x[c][i],   out[C+c][i][t] = x[c][i]
+// Both kernels are HBM-bound by construction: the forward writes the result exactly once (rows of x are staged in
+// shared memory, 8 KB per channel at N = 2048, and gathered from there), the backward reads the upstream gradient
+// exactly once and scatter-adds into a shared-memory row (float atomics: summation order is not fixed, like
+// torch.gather's own backward).
+#include "common.cuh"
+
+namespace pcc {
+
+constexpr int GG_THREADS = 256;
+constexpr int GG_PT = 128;   // points per CTA
+constexpr int GG_CH = 4;     // channels staged per step
+constexpr int GG_ITEMS = 16; // (point, neighbour) items per thread: GG_PT * 32 / GG_THREADS
+constexpr int GG_MAXN = 8192;  // GG_CH rows of this many floats fit the dynamic shared memory
+
+template <int MODE>
+__global__ void __launch_bounds__(GG_THREADS)
+graph_gather_kernel(int c, int n, int k, const float *__restrict__ x, const int64_t *__restrict__ idx,
+                    float *__restrict__ out) {
+  extern __shared__ __align__(16) float rows[];  // [GG_CH][n]
+  const size_t cloud = blockIdx.y;
+  const int i0 = blockIdx.x * GG_PT;
+  const int items = min(GG_PT, n - i0) * k;
+  const float *xb = x + cloud * (size_t)c * n;
+  const int64_t *ib = idx + (cloud * (size_t)n + i0) * k;
+  const int co = MODE ? 2 * c : c;
+  float *ob = out + cloud * (size_t)co * n * k + (size_t)i0 * k;
+  // this thread's items: neighbour index and own point, fixed for all channels
+  int nbr[GG_ITEMS], own[GG_ITEMS];
+#pragma unroll
+  for (int it = 0; it < GG_ITEMS; ++it) {
+    const int o = threadIdx.x + it * GG_THREADS;
+    nbr[it] = 0;
+    own[it] = 0;
+    if (o < items) {
+      const long long j = ib[o];
+      nbr[it] = (int)min(max(j, 0LL), (long long)n - 1);  // memory-safe for invalid indices
+      own[it] = i0 + o / k;
+    }
+  }
+  for (int c0 = 0; c0 < c; c0 += GG_CH) {
+    const int cn = min(GG_CH, c - c0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cn * n; e += GG_THREADS) rows[e] = xb[(size_t)c0 * n + e];  // rows are contiguous
+    __syncthreads();
+    for (int cc = 0; cc < cn; ++cc) {
+      const float *row = rows + cc * n;
+      float *o_top = ob + (size_t)(c0 + cc) * n * k;
+      float *o_bot = ob + (size_t)(c + c0 + cc) * n * k;
+#pragma unroll
+      for (int it = 0; it < GG_ITEMS; ++it) {
+        const int o = threadIdx.x + it * GG_THREADS;
+        if (o < items) {
+          const float xj = row[nbr[it]];
+          if (MODE) {
+            const float xi = row[own[it]];
+            o_top[o] = xj - xi;
+            o_bot[o] = xi;
+          } else {
+            o_top[o] = xj;
+          }
+        }
+      }
+    }
+  }
+}
+
+// one CTA per (cloud, channel): grad_x[c][j] = sum over (i,t) with idx[i][t] == j of g_top[i][t]
+//                               (+ mode 1:  sum_t (g_bot[i][t] - g_top[i][t]) for the point itself)
+template <int MODE>
+__global__ void __launch_bounds__(GG_THREADS)
+graph_gather_grad_kernel(int c, int n, int k, const int64_t *__restrict__ idx, const float *__restrict__ gout,
+                         float *__restrict__ gx) {
+  extern __shared__ __align__(16) float acc[];  // [n]
+  const size_t cloud = blockIdx.y;
+  const int ch = blockIdx.x;
+  const int co = MODE ? 2 * c : c;
+  const int64_t *ib = idx + cloud * (size_t)n * k;
+  const float *g_top = gout + (cloud * (size_t)co + ch) * n * k;
+  const float *g_bot = gout + (cloud * (size_t)co + c + ch) * n * k;
+  for (int i = threadIdx.x; i < n; i += GG_THREADS) acc[i] = 0.f;
+  __syncthreads();
+  // coalesced over the (point, neighbour) plane; the own term is reduced over the runs of equal point inside the warp
+  // (k consecutive entries belong to one point) before it touches shared memory
+  const unsigned int total = (unsigned int)n * (unsigned int)k;
+  const unsigned int magic = (unsigned int)((0x100000000ULL + (unsigned int)k - 1) / (unsigned int)k);  // o / k == umulhi(o, magic) for o < 2^32 / k
+  const int lane = threadIdx.x & 31;
+  for (unsigned int o0 = 0; o0 < total; o0 += GG_THREADS) {
+    const unsigned int o = o0 + threadIdx.x;
+    const bool ok = o < total;
+    int pid = -1;
+    float v = 0.f;
+    if (ok) {
+      const long long j = ib[o];
+      const float g = g_top[o];
+      atomicAdd(&acc[(int)min(max(j, 0LL), (long long)n - 1)], g);
+      if (MODE) {
+        pid = (int)__umulhi(o, magic);
+        v = g_bot[o] - g;
+      }
+    }
+    if (MODE) {
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float u = __shfl_down_sync(0xffffffffu, v, d);
+        const int p = __shfl_down_sync(0xffffffffu, pid, d);
+        if (lane + d < 32 && p == pid) v += u;
+      }
+      const int prev = __shfl_up_sync(0xffffffffu, pid, 1);
+      if (ok && (lane == 0 || prev != pid)) atomicAdd(&acc[pid], v);
+    }
+  }
+  __syncthreads();
+  float *gr = gx + (cloud * (size_t)c + ch) * n;
+  for (int i = threadIdx.x; i < n; i += GG_THREADS) gr[i] = acc[i];
+}
+
+template <int MODE>
+static int launch_gather(int b, int c, int n, int k, const float *x, const int64_t *idx, float *out, cudaStream_t st) {
+  const size_t smem = sizeof(float) * GG_CH * n;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(graph_gather_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  graph_gather_kernel<MODE><<<dim3((n + GG_PT - 1) / GG_PT, b), GG_THREADS, smem, st>>>(c, n, k, x, idx, out);
+  return finish_launch(1);
+}
+
+template <int MODE>
+static int launch_gather_grad(int b, int c, int n, int k, const int64_t *idx, const float *gout, float *gx,
+                              cudaStream_t st) {
+  const size_t smem = sizeof(float) * n;
+  graph_gather_grad_kernel<MODE><<<dim3(c, b), GG_THREADS, smem, st>>>(c, n, k, idx, gout, gx);
+  return finish_launch(1);
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" __attribute__((visibility("default"))) int pcc_graph_gather(int b, int c, int n, int k, const float *x, const int64_t *idx, int mode,
+                                                                        float *out, pcc_stream_t stream) {
+  if (b < 0 || c <= 0 || n <= 0 || k <= 0 || (mode != 0 && mode != 1)) return PCC_EINVAL;
+  if (b == 0) return PCC_OK;
+  if (k > 32 || n > GG_MAXN || b > 65535) return PCC_ENOTSUP;
+  cudaStream_t st = (cudaStream_t)stream;
+  return mode ? launch_gather<1>(b, c, n, k, x, idx, out, st) : launch_gather<0>(b, c, n, k, x, idx, out, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_graph_gather_grad(int b, int c, int n, int k, const int64_t *idx, int mode,
+                                                                             const float *grad_out, float *grad_x,
+                                                                             pcc_stream_t stream) {
+  if (b < 0 || c <= 0 || n <= 0 || k <= 0 || (mode != 0 && mode != 1)) return PCC_EINVAL;
+  if (b == 0) return PCC_OK;
+  if (n > GG_MAXN || b > 65535 || c > 65535) return PCC_ENOTSUP;
+  cudaStream_t st = (cudaStream_t)stream;
+  return mode ? launch_gather_grad<1>(b, c, n, k, idx, grad_out, grad_x, st)
+              : launch_gather_grad<0>(b, c, n, k, idx, grad_out, grad_x, st);
+}

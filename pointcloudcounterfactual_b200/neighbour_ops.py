@@ -8,8 +8,11 @@ for callers that ask for them by name.
 """
 from __future__ import annotations
 
+from typing import Any
+
 import numpy as np
 import torch
+from torch.autograd import Function
 
 from . import _lib as L
 from .keops import LazyTensor, SquareDistance
@@ -80,11 +83,48 @@ def torch_knn(x: torch.Tensor, k: int) -> torch.Tensor:
     return self_square_distance(x).topk(k=k, largest=False)[1]
 
 
+class _GraphGather(Function):
+    """x (B,C,N), idx (B,N,k) int64 -> neighbours (B,C,N,k) [mode 0] or graph features (B,2C,N,k) [mode 1] in ONE
+    kernel that writes the result once (pcc_graph_gather); backward = one scatter-add kernel (pcc_graph_gather_grad)."""
+
+    @staticmethod
+    def forward(ctx: Any, x: torch.Tensor, idx: torch.Tensor, mode: int) -> torch.Tensor:
+        b, c, n = x.shape
+        k = idx.shape[2]
+        with torch.cuda.device(x.device):
+            out = torch.empty((b, (2 * c) if mode else c, n, k), dtype=torch.float32, device=x.device)
+            L.check(L.load().pcc_graph_gather(b, c, n, k, L.ptr(x), L.ptr(idx), mode, L.ptr(out), L.stream_of(x)),
+                    "graph_gather")
+        ctx.save_for_backward(idx)
+        ctx.dims = (b, c, n, k, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor):
+        (idx,) = ctx.saved_tensors
+        b, c, n, k, mode = ctx.dims
+        g = grad_out.contiguous()
+        with torch.cuda.device(g.device):
+            gx = torch.empty((b, c, n), dtype=torch.float32, device=g.device)
+            L.check(L.load().pcc_graph_gather_grad(b, c, n, k, L.ptr(idx), mode, L.ptr(g), L.ptr(gx), L.stream_of(g)),
+                    "graph_gather_grad")
+        return gx, None, None
+
+
+def _fused_gather_ok(x: torch.Tensor, indices: torch.Tensor, k: int) -> bool:
+    """The fused kernels cover CUDA fp32 features, int64 (B,N,k) indices, k <= 32, N <= 8192; anything else (and
+    empty batches) takes the reference's torch composition."""
+    return (x.is_cuda and x.dtype == torch.float32 and indices.dtype == torch.int64 and indices.dim() == 3
+            and x.shape[0] > 0 and k <= 32 and x.shape[2] <= 8192 and tuple(indices.shape) == (x.shape[0], x.shape[2], k))
+
+
 def get_neighbours(x: torch.Tensor, indices: torch.Tensor, k: int):
     """(:85-94) -> (indices (B,N,k), neighbours (B,C,N,k))."""
     batch, n_feat, n_points = x.size()
     if not indices.numel():
         indices = knn(x, k)
+    if _fused_gather_ok(x, indices, k):
+        return indices, _GraphGather.apply(x.contiguous(), indices.contiguous(), 0)
     flat = indices.contiguous().view(batch, 1, k * n_points).expand(-1, n_feat, -1)
     neighbours = torch.gather(x, 2, flat).view(batch, n_feat, n_points, k)
     return indices, neighbours
@@ -105,6 +145,10 @@ def graph_max_pooling(x: torch.Tensor, indices: torch.Tensor, k: int = 16) -> to
 
 def get_graph_features(x: torch.Tensor, indices: torch.Tensor, k: int = 20) -> tuple[torch.Tensor, torch.Tensor]:
     """(:113-119) EdgeConv input: cat(neighbour - centre, centre) -> (B, 2C, N, k)."""
+    if not indices.numel():
+        indices = knn(x, k)
+    if _fused_gather_ok(x, indices, k):
+        return indices, _GraphGather.apply(x.contiguous(), indices.contiguous(), 1)
     indices_out, neighbours = get_neighbours(x, indices, k)
     centre = x.unsqueeze(3).expand(-1, -1, -1, k)
     return indices_out, torch.cat([neighbours - centre, centre], dim=1).contiguous()

@@ -137,3 +137,31 @@ def test_errors(cuda):
     assert neighbour_ops.knn(torch.zeros(0, 3, 8, device=cuda), 2).shape == (0, 8, 2)
     idx = neighbour_ops.index_k_neighbours([np.random.default_rng(0).random((64, 3)).astype(np.float32)], 4)
     assert idx.shape == (1, 64, 4) and (idx[0, :, 0] == np.arange(64)).all()
+
+
+@pytest.mark.parametrize("b,c,n,k", [(2, 3, 300, 4), (2, 64, 1024, 20), (1, 128, 2048, 25), (3, 16, 77, 32), (1, 7, 8192, 3)])
+def test_fused_graph_gather_forward_backward(cuda, b, c, n, k):
+    """get_neighbours / get_graph_features run as one gather kernel (+ one scatter-add kernel backward); they must
+    reproduce the reference's torch composition (neighbour_ops.py:85-94,113-119): forward bit for bit, the gradient to
+    fp32 rounding (atomics change the summation order)."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(b, c, n, generator=g).to(cuda)
+    idx = torch.randint(0, n, (b, n, k), generator=g).to(cuda)
+    flat = idx.view(b, 1, k * n).expand(-1, c, -1)
+
+    def composed(t, mode):
+        nb = torch.gather(t, 2, flat).view(b, c, n, k)
+        if not mode:
+            return nb
+        centre = t.unsqueeze(3).expand(-1, -1, -1, k)
+        return torch.cat([nb - centre, centre], dim=1).contiguous()
+
+    for mode, fn in ((0, lambda t: neighbour_ops.get_neighbours(t, idx, k)[1]),
+                     (1, lambda t: neighbour_ops.get_graph_features(t, idx, k)[1])):
+        a, r = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        out, ref = fn(a), composed(r, mode)
+        assert torch.equal(out, ref)
+        w = torch.randn(ref.shape, generator=g).to(cuda)
+        (out * w).sum().backward()
+        (ref * w).sum().backward()
+        assert rel_err(a.grad.cpu().numpy(), r.grad.cpu().numpy()) < 1e-5
