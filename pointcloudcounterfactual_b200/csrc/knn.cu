@@ -643,14 +643,52 @@ static int launch_knn3(int b, int n, int k, const float *x, int64_t *idx, float 
   return rc;
 }
 
+// ---- tiny argmin (vector quantisation, src/module/quantize.py:26-28) ---------------------------------------------
+// The nearest-codeword search is (B * n_codes) independent problems of ONE query against a 16-entry book of 4-dim
+// codes: a CTA per problem (the general kernels) would be 99 % idle.  One thread per query instead; the references of
+// a problem are a few hundred bytes read through L1.  Same arithmetic (sequential fma over channels) and the same
+// lowest-index tie rule as the general path.
+__global__ void __launch_bounds__(256)
+argmin_small_kernel(int b, int nq, int nr, int c, const float *__restrict__ q, const float *__restrict__ r,
+                    int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= (size_t)b * nq) return;
+  const size_t cloud = t / nq;
+  const float *qp = q + t * c;
+  const float *rp = r + cloud * (size_t)nr * c;
+  float best = __int_as_float(0x7f800000);
+  int bi = 0;
+  bool any = false;
+  for (int j = 0; j < nr; ++j) {
+    float d = 0.f;
+    for (int ch = 0; ch < c; ++ch) {
+      const float df = qp[ch] - rp[(size_t)j * c + ch];
+      d = fmaf(df, df, d);
+    }
+    if (d < best || (!any && d == best)) {  // strict: the lowest index wins ties; +inf distances still select index 0
+      best = d;
+      bi = j;
+      any = true;
+    }
+  }
+  idx_out[t] = bi;
+  if (dist_out) dist_out[t] = best;
+}
+
 template <bool PM>
 static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const float *r, int64_t *idx,
                       float *dist, cudaStream_t st) {
   if (b < 0 || c <= 0 || nq < 0 || nr < 0 || k <= 0) return PCC_EINVAL;
   if (k > nr) return PCC_EINVAL;  // torch.topk / argKmin cannot return more neighbours than points
+  if (PM && k == 1 && nr <= 64 && c <= 16 && nq <= 8 && b > 0 && nq > 0 && getenv("PCC_KNN_SIMT") == nullptr) {
+    const size_t total = (size_t)b * nq;  // no 65535-cloud grid limit on this path (B * n_codes problems)
+    argmin_small_kernel<<<(unsigned int)((total + 255) / 256), 256, 0, st>>>(b, nq, nr, c, q, r, idx, dist);
+    return finish_launch(1);
+  }
   if (k > PCC_KNN_MAX_K || b > 65535) return PCC_ENOTSUP;
   if (b == 0 || nq == 0) return PCC_OK;
   static const bool force_simt = getenv("PCC_KNN_SIMT") != nullptr;  // test hook: exact SIMT kernels only
+
   if (!PM && c == 3 && q == r && nq == nr && k <= 32) return launch_knn3(b, nq, k, q, idx, dist, st);
   if (!PM && !force_simt && q == r && nq == nr && c % 32 == 0) {
     static const bool tc_v1 = getenv("PCC_KNN_TC1") != nullptr;  // test hook: first-generation tcgen05 kernel only

@@ -98,7 +98,8 @@ class SquareDistance:
         return self.argKmin(1, dim=axis if axis is not None else dim)
 
     def _dense(self) -> torch.Tensor:
-        # TODO(next): dedicated reduction kernel; only quantize.py's tiny (.,1,16) case uses it
+        # only quantize.py's tiny (B*n_codes, 1, 16) case reaches this; dense torch keeps it differentiable (the
+        # arg-reductions of the same expression run argmin_small_kernel / the argKmin kernels)
         diff = self.ti[:, :, None, :] - self.tj[:, None, :, :]
         return (diff * diff).sum(-1)
 

@@ -165,3 +165,20 @@ def test_fused_graph_gather_forward_backward(cuda, b, c, n, k):
         (out * w).sum().backward()
         (ref * w).sum().backward()
         assert rel_err(a.grad.cpu().numpy(), r.grad.cpu().numpy()) < 1e-5
+
+
+def test_vq_nearest_codeword_pattern_large_batch(cuda):
+    """quantize.py:20-32 at training size: B * n_codes = 131072 one-query problems against a repeated 16 x 4 book
+    (more problems than the 65535-cloud grid limit of the general kernels) run on the one-thread-per-query kernel."""
+    g = torch.Generator().manual_seed(5)
+    batch, n_codes, book, dim = 512, 256, 16, 4
+    x = torch.randn(batch, n_codes * dim, generator=g)
+    codebook = torch.randn(n_codes, book, dim, generator=g)
+    codebook[3, 7] = codebook[3, 2]  # an exact tie: the lower index must win
+    x_flat = x.view(batch * n_codes, 1, dim)
+    rep = codebook.repeat(batch, 1, 1)
+    d = neighbour_ops.pykeops_square_distance(x_flat.to(cuda), rep.to(cuda))
+    idx = d.argmin(axis=2).cpu().numpy()[:, 0, 0]
+    exp = oracle.square_distance(x_flat.numpy(), rep.numpy())
+    assert np.array_equal(idx, np.argsort(exp, 2, kind="stable")[:, 0, 0])
+    assert rel_err(d.sum(1).cpu().numpy()[..., 0], exp.sum(1)) < 1e-5
