@@ -361,11 +361,13 @@ def run_b200(args) -> None:
         f128 = synthetic.knn_features(B_PER_GPU, 128, N_POINTS, seed=3200 + rank).to(dev)
         grad_buf = torch.zeros(45 * (1 << 20) // 4, device=dev)  # ~45 MB of fp32 autoencoder gradients
 
+        layers = [t.detach().requires_grad_(True) for t in (x25, f64a, f64b, f128)]  # EdgeConv inputs: C = 3, 64, 64, 128
+
         def ae_step():
-            neighbour_ops.knn(x25, 25)      # encoder EdgeConv 1 (xyz)
-            neighbour_ops.knn(f64a, 25)     # EdgeConv 2, 3 (64 channels)
-            neighbour_ops.knn(f64b, 25)
-            neighbour_ops.knn(f128, 25)     # EdgeConv 4 (128 channels)
+            for t in layers:  # encoder: kNN graph (k=25) + EdgeConv gather forward and backward per layer
+                feat = neighbour_ops.get_graph_features(t, torch.empty(0), 25)[1]
+                torch.autograd.grad(feat, t, feat)
+                del feat
             neighbour_ops.knn(rr.detach().transpose(1, 2).contiguous(), 4)  # decoder graph_filtering
             loss = losses.chamfer_emd(rr, ref_d)
             torch.autograd.grad(loss.sum(), rr)
@@ -375,7 +377,8 @@ def run_b200(args) -> None:
         ms = ev_time(ae_step, 10) if world > 1 else graph_or_eager(ae_step, reps=10)[0]
         sub["ae_step_hotpath"] = {
             "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": world == 1,
-            "note": "stand-in for configs[3]: kNN k=25 N=2048 on C=3,64,64,128 + decoder kNN k=4 + ChamferEMD fwd+bwd"
+            "note": "stand-in for configs[3]: per EdgeConv layer (C=3,64,64,128; N=2048; k=25) kNN + get_graph_features "
+                    "forward and backward, + decoder kNN k=4 + ChamferEMD fwd+bwd"
                     + (" + NCCL all-reduce of 45 MB fp32 gradients" if world > 1 else "") + "; 32 clouds per GPU"}
 
         leaf = recon_d.detach().clone().requires_grad_(True)
