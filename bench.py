@@ -353,6 +353,17 @@ def run_b200(args) -> None:
                                     "note": "the (B,2C,N,k) feature tensor crosses HBM once; x and idx stay in L2"}}
         del feat, gfeat
 
+        # ---- decoder-output smoothing: kNN k=4 + fused graph_filtering forward and backward -------------
+        xg = x25.detach().requires_grad_(True)
+
+        def gfilt():
+            out = neighbour_ops.graph_filtering(xg, 4)
+            torch.autograd.grad(out, xg, out)
+
+        ms, gr = graph_or_eager(gfilt, reps=20)
+        sub["graph_filtering_n2048_fwd_bwd"] = {"ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
+                                                "note": "kNN k=4 (knn3w_kernel) + one launch forward + one launch backward"}
+
         # ---- BASELINE configs[3] / [4]: the reference's models cannot be instantiated here (drytorch / hydra are not
         # installed), so these are the hot-path op sequences of one training step / one latent-optimisation
         # iteration, per GPU, with the step's real collective ------------------------------------------------------
@@ -368,7 +379,7 @@ def run_b200(args) -> None:
                 feat = neighbour_ops.get_graph_features(t, torch.empty(0), 25)[1]
                 torch.autograd.grad(feat, t, feat)
                 del feat
-            neighbour_ops.knn(rr.detach().transpose(1, 2).contiguous(), 4)  # decoder graph_filtering
+            gfilt()  # decoder graph_filtering (kNN k=4 + smoothing forward / backward)
             loss = losses.chamfer_emd(rr, ref_d)
             torch.autograd.grad(loss.sum(), rr)
             if world > 1:
@@ -378,15 +389,15 @@ def run_b200(args) -> None:
         sub["ae_step_hotpath"] = {
             "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": world == 1,
             "note": "stand-in for configs[3]: per EdgeConv layer (C=3,64,64,128; N=2048; k=25) kNN + get_graph_features "
-                    "forward and backward, + decoder kNN k=4 + ChamferEMD fwd+bwd"
+                    "forward and backward, + decoder graph_filtering (kNN k=4) fwd+bwd + ChamferEMD fwd+bwd"
                     + (" + NCCL all-reduce of 45 MB fp32 gradients" if world > 1 else "") + "; 32 clouds per GPU"}
 
         leaf = recon_d.detach().clone().requires_grad_(True)
         opt = torch.optim.Adam([leaf], lr=1e-3, capturable=True)
 
         def generate_iter():
-            neighbour_ops.knn(leaf.detach().transpose(1, 2).contiguous(), 4)
-            loss = losses.pykeops_chamfer(leaf, ref_d)
+            smooth = neighbour_ops.graph_filtering(leaf.transpose(1, 2).contiguous(), 4).transpose(1, 2)
+            loss = losses.pykeops_chamfer(smooth.contiguous(), ref_d)
             opt.zero_grad(set_to_none=False)
             loss.sum().backward()
             opt.step()
@@ -394,8 +405,8 @@ def run_b200(args) -> None:
         ms, gr = graph_or_eager(generate_iter, reps=20)
         sub["generate_loop_iter"] = {
             "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
-            "note": "synthetic stand-in for configs[4] (the reference's generate.py has no optimisation loop): kNN k=4 + "
-                    "Chamfer fwd+bwd w.r.t. the cloud + Adam on a (32,2048,3) leaf per GPU"}
+            "note": "synthetic stand-in for configs[4] (the reference's generate.py has no optimisation loop): graph_filtering "
+                    "(kNN k=4) + Chamfer, forward and backward w.r.t. the cloud, + Adam on a (32,2048,3) leaf per GPU"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

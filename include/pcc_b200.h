@@ -119,6 +119,15 @@ int pcc_graph_gather(int b, int c, int n, int k, const float *x, const int64_t *
 int pcc_graph_gather_grad(int b, int c, int n, int k, const int64_t *idx, int mode, const float *grad_out,
                           float *grad_x, pcc_stream_t stream);
 
+/* Decoder-output smoothing `graph_filtering` (src/utils/neighbour_ops.py:122-133), one launch per
+ * direction.  x (b,3,n), idx (b,n,k) int64 = the kNN list of x itself (column 0 is the point), 2 <= k <= 8, n <= 6144.
+ * out (b,3,n); mean_dist (b) receives the per-cloud mean nearest-neighbour distance (sigma before the 0.005 clamp),
+ * which the backward takes back.  Duplicate points contribute no distance gradient (torch yields NaN there). */
+int pcc_graph_filtering(int b, int n, int k, const float *x, const int64_t *idx, float *out, float *mean_dist,
+                        pcc_stream_t stream);
+int pcc_graph_filtering_grad(int b, int n, int k, const float *x, const int64_t *idx, const float *mean_dist,
+                             const float *grad_out, float *grad_x, pcc_stream_t stream);
+
 /* ---- Auction EMD ------------------------------------------------------------------------------------
  * Replaces `int emd_cuda_forward(at::Tensor xyz1, ..., float eps, int iters)` (external/emd/src/emd.cpp:14-21,
  * emd_cuda.cu:227-281) with the tensors passed as raw pointers in the same order.  The caller allocates and

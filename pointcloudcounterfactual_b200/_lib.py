@@ -37,6 +37,8 @@ _SIGNATURES = {
     "pcc_argkmin": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pcc_graph_gather": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "pcc_graph_gather_grad": (_i, [_i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "pcc_graph_filtering": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pcc_graph_filtering_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_emd_forward": (_i, [_i, _i, _i] + [_vp] * 14 + [ctypes.c_float, _i, _vp]),
     "pcc_emd_backward": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

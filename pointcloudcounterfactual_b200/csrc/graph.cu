@@ -146,6 +146,128 @@ static int launch_gather_grad(int b, int c, int n, int k, const int64_t *idx, co
   return finish_launch(1);
 }
 
+// ---- decoder-output smoothing (graph_filtering, src/utils/neighbour_ops.py:122-133) ----------------------------------
+// out_i = (1 + sum_t w_it) x_i - sum_t w_it x_{j_it},  w_it = exp(-d_it / sigma),  d_it = |x_i - x_{j_it}| over the k-1
+// nearest neighbours (column 0 of the kNN list is the point itself),  sigma = max(mean_i d_i1, 0.005) per cloud.
+// The reference runs ~15 elementwise / gather / reduce kernels forward and twice that backward on (B,3,N,3) tensors;
+// here one CTA per cloud keeps the cloud in shared memory and does each direction in one launch.
+constexpr int GF_THREADS = 256;
+constexpr int GF_MAXK = 8;
+
+__device__ __forceinline__ float gf_block_sum(float v, float *red) {  // fixed order: deterministic
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < GF_THREADS / 32; ++w) s += red[w];
+  __syncthreads();
+  return s;
+}
+
+__global__ void __launch_bounds__(GF_THREADS)
+graph_filter_kernel(int n, int k, const float *__restrict__ x, const int64_t *__restrict__ idx, float *__restrict__ out,
+                    float *__restrict__ mean_out) {
+  extern __shared__ __align__(16) float gf_sm[];  // xs[3][n]
+  __shared__ float red[GF_THREADS / 32];
+  float *xs = gf_sm, *ys = xs + n, *zs = ys + n;
+  const size_t cloud = blockIdx.x;
+  const float *xb = x + cloud * (size_t)3 * n;
+  const int64_t *ib = idx + cloud * (size_t)n * k;
+  for (int i = threadIdx.x; i < 3 * n; i += GF_THREADS) gf_sm[i] = xb[i];
+  __syncthreads();
+  float s0 = 0.f;
+  for (int i = threadIdx.x; i < n; i += GF_THREADS) {
+    const int j = (int)min(max(ib[(size_t)i * k + 1], (int64_t)0), (int64_t)n - 1);
+    const float dx = xs[i] - xs[j], dy = ys[i] - ys[j], dz = zs[i] - zs[j];
+    s0 += sqrtf(fabsf(dx * dx + dy * dy + dz * dz));
+  }
+  const float mean = gf_block_sum(s0, red) / (float)n;
+  const float sigma = fmaxf(mean, 0.005f);
+  if (threadIdx.x == 0) mean_out[cloud] = mean;
+  float *ob = out + cloud * (size_t)3 * n;
+  for (int i = threadIdx.x; i < n; i += GF_THREADS) {
+    const float xi = xs[i], yi = ys[i], zi = zs[i];
+    float wsum = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    for (int t = 1; t < k; ++t) {
+      const int j = (int)min(max(ib[(size_t)i * k + t], (int64_t)0), (int64_t)n - 1);
+      const float xj = xs[j], yj = ys[j], zj = zs[j];
+      const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
+      const float w = expf(-(sqrtf(fabsf(dx * dx + dy * dy + dz * dz)) / sigma));
+      wsum += w;
+      ax += w * xj;
+      ay += w * yj;
+      az += w * zj;
+    }
+    ob[i] = (1.f + wsum) * xi - ax;
+    ob[(size_t)n + i] = (1.f + wsum) * yi - ay;
+    ob[(size_t)2 * n + i] = (1.f + wsum) * zi - az;
+  }
+}
+
+// grad_x of the above.  Duplicate points (d = 0) contribute no distance gradient (torch yields NaN there).
+__global__ void __launch_bounds__(GF_THREADS)
+graph_filter_grad_kernel(int n, int k, const float *__restrict__ x, const int64_t *__restrict__ idx,
+                         const float *__restrict__ mean_in, const float *__restrict__ gout, float *__restrict__ gx) {
+  extern __shared__ __align__(16) float gf_sm[];  // xs[3][n], gs[3][n], acc[3][n]
+  __shared__ float red[GF_THREADS / 32];
+  float *xs = gf_sm, *ys = xs + n, *zs = ys + n;
+  float *gxs = zs + n, *gys = gxs + n, *gzs = gys + n;
+  float *acc = gzs + n;
+  const size_t cloud = blockIdx.x;
+  const float *xb = x + cloud * (size_t)3 * n, *gb = gout + cloud * (size_t)3 * n;
+  const int64_t *ib = idx + cloud * (size_t)n * k;
+  for (int i = threadIdx.x; i < 3 * n; i += GF_THREADS) {
+    gf_sm[i] = xb[i];
+    gxs[i] = gb[i];
+    acc[i] = 0.f;
+  }
+  __syncthreads();
+  const float mean = mean_in[cloud];
+  const float sigma = fmaxf(mean, 0.005f);
+  // dL/dsigma = sum_{i,t} (g_i . diff_it) w_it d_it / sigma^2   (only while the clamp is inactive)
+  float ds = 0.f;
+  for (int i = threadIdx.x; i < n; i += GF_THREADS) {
+    for (int t = 1; t < k; ++t) {
+      const int j = (int)min(max(ib[(size_t)i * k + t], (int64_t)0), (int64_t)n - 1);
+      const float dx = xs[i] - xs[j], dy = ys[i] - ys[j], dz = zs[i] - zs[j];
+      const float d = sqrtf(fabsf(dx * dx + dy * dy + dz * dz));
+      const float w = expf(-(d / sigma));
+      ds += (gxs[i] * dx + gys[i] * dy + gzs[i] * dz) * w * d;
+    }
+  }
+  const float dLds = (mean >= 0.005f) ? gf_block_sum(ds, red) / (sigma * sigma) : (gf_block_sum(ds, red), 0.f);
+  const float per_point = dLds / (float)n;  // d sigma / d d_i1
+  for (int i = threadIdx.x; i < n; i += GF_THREADS) {
+    const float xi = xs[i], yi = ys[i], zi = zs[i];
+    const float gi0 = gxs[i], gi1 = gys[i], gi2 = gzs[i];
+    float wsum = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+    for (int t = 1; t < k; ++t) {
+      const int j = (int)min(max(ib[(size_t)i * k + t], (int64_t)0), (int64_t)n - 1);
+      const float dx = xi - xs[j], dy = yi - ys[j], dz = zi - zs[j];
+      const float d = sqrtf(fabsf(dx * dx + dy * dy + dz * dz));
+      const float w = expf(-(d / sigma));
+      wsum += w;
+      // through the distance: dL/dd = (g . diff) * (-w / sigma) [+ the sigma path for the nearest neighbour]
+      float dLdd = (gi0 * dx + gi1 * dy + gi2 * dz) * (-w / sigma);
+      if (t == 1) dLdd += per_point;
+      const float coef = d > 0.f ? dLdd / d : 0.f;
+      ox += coef * dx;
+      oy += coef * dy;
+      oz += coef * dz;
+      atomicAdd(&acc[j], -(gi0 * w) - coef * dx);
+      atomicAdd(&acc[n + j], -(gi1 * w) - coef * dy);
+      atomicAdd(&acc[2 * n + j], -(gi2 * w) - coef * dz);
+    }
+    atomicAdd(&acc[i], gi0 * (1.f + wsum) + ox);
+    atomicAdd(&acc[n + i], gi1 * (1.f + wsum) + oy);
+    atomicAdd(&acc[2 * n + i], gi2 * (1.f + wsum) + oz);
+  }
+  __syncthreads();
+  float *gr = gx + cloud * (size_t)3 * n;
+  for (int i = threadIdx.x; i < 3 * n; i += GF_THREADS) gr[i] = acc[i];
+}
+
 }  // namespace pcc
 
 using namespace pcc;
@@ -168,4 +290,37 @@ extern "C" __attribute__((visibility("default"))) int pcc_graph_gather_grad(int 
   cudaStream_t st = (cudaStream_t)stream;
   return mode ? launch_gather_grad<1>(b, c, n, k, idx, grad_out, grad_x, st)
               : launch_gather_grad<0>(b, c, n, k, idx, grad_out, grad_x, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_graph_filtering(int b, int n, int k, const float *x, const int64_t *idx, float *out,
+                                                                           float *mean_dist, pcc_stream_t stream) {
+  if (b < 0 || n <= 0 || k < 2) return PCC_EINVAL;
+  if (b == 0) return PCC_OK;
+  if (k > GF_MAXK || n > 6144) return PCC_ENOTSUP;
+  const size_t smem = sizeof(float) * 3 * n;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(graph_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  graph_filter_kernel<<<b, GF_THREADS, smem, (cudaStream_t)stream>>>(n, k, x, idx, out, mean_dist);
+  return finish_launch(1);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_graph_filtering_grad(int b, int n, int k, const float *x, const int64_t *idx,
+                                                                                const float *mean_dist, const float *grad_out,
+                                                                                float *grad_x, pcc_stream_t stream) {
+  if (b < 0 || n <= 0 || k < 2) return PCC_EINVAL;
+  if (b == 0) return PCC_OK;
+  if (k > GF_MAXK || n > 6144) return PCC_ENOTSUP;
+  const size_t smem = sizeof(float) * 9 * n;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(graph_filter_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  graph_filter_grad_kernel<<<b, GF_THREADS, smem, (cudaStream_t)stream>>>(n, k, x, idx, mean_dist, grad_out, grad_x);
+  return finish_launch(1);
 }

@@ -154,8 +154,39 @@ def get_graph_features(x: torch.Tensor, indices: torch.Tensor, k: int = 20) -> t
     return indices_out, torch.cat([neighbours - centre, centre], dim=1).contiguous()
 
 
+class _GraphFiltering(Function):
+    """x (B,3,N), idx (B,N,k) -> smoothed cloud (B,3,N): one launch forward, one backward (pcc_graph_filtering*)."""
+
+    @staticmethod
+    def forward(ctx: Any, x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        b, _, n = x.shape
+        k = idx.shape[2]
+        with torch.cuda.device(x.device):
+            out = torch.empty_like(x)
+            mean = torch.empty((b,), dtype=torch.float32, device=x.device)
+            L.check(L.load().pcc_graph_filtering(b, n, k, L.ptr(x), L.ptr(idx), L.ptr(out), L.ptr(mean), L.stream_of(x)),
+                    "graph_filtering")
+        ctx.save_for_backward(x, idx, mean)
+        return out
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor):
+        x, idx, mean = ctx.saved_tensors
+        b, _, n = x.shape
+        g = grad_out.contiguous()
+        with torch.cuda.device(x.device):
+            gx = torch.empty_like(x)
+            L.check(L.load().pcc_graph_filtering_grad(b, n, idx.shape[2], L.ptr(x), L.ptr(idx), L.ptr(mean), L.ptr(g),
+                                                      L.ptr(gx), L.stream_of(x)), "graph_filtering_grad")
+        return gx, None
+
+
 def graph_filtering(x: torch.Tensor, k: int = 4) -> torch.Tensor:
     """(:122-133) decoder-output smoothing; relies on ascending kNN with the point itself in column 0."""
+    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[1] == 3 and x.shape[0] > 0
+            and 2 <= k <= 8 and k <= x.shape[2] <= 6144):
+        xc = x.contiguous()
+        return _GraphFiltering.apply(xc, knn(xc.detach(), k))
     neighbours = get_neighbours(x, indices=torch.empty(0), k=k)[1][..., 1:]
     diff = x.unsqueeze(-1) - neighbours
     dist = torch.sqrt((diff * diff).sum(1).abs())

@@ -182,3 +182,36 @@ def test_vq_nearest_codeword_pattern_large_batch(cuda):
     exp = oracle.square_distance(x_flat.numpy(), rep.numpy())
     assert np.array_equal(idx, np.argsort(exp, 2, kind="stable")[:, 0, 0])
     assert rel_err(d.sum(1).cpu().numpy()[..., 0], exp.sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("b,n,k", [(3, 512, 4), (2, 2048, 4), (2, 300, 6), (1, 5000, 3)])
+def test_fused_graph_filtering_forward_backward(cuda, b, n, k):
+    """graph_filtering (neighbour_ops.py:122-133) as one launch per direction against the reference's torch
+    composition (same kNN indices), value and gradient, including the path through sigma (a per-cloud mean)."""
+    x = synthetic.knn_xyz(b, n).to(cuda)
+    idx = neighbour_ops.knn(x, k)
+
+    def composed(t):
+        nb = torch.gather(t, 2, idx.view(b, 1, k * n).expand(-1, 3, -1)).view(b, 3, n, k)[..., 1:]
+        diff = t.unsqueeze(-1).expand(-1, -1, -1, k - 1) - nb
+        dist = torch.sqrt(abs((diff ** 2).sum(1)))
+        sigma = torch.clamp(dist[..., 0:1].mean(1, keepdim=True), min=0.005)
+        weights = torch.exp(-(dist / sigma))
+        x_weight = weights.sum(2).unsqueeze(1).expand(-1, 3, -1)
+        return (1 + x_weight) * t - (weights.unsqueeze(1).expand(-1, 3, -1, -1) * nb).sum(-1)
+
+    a, r = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    out, ref = neighbour_ops.graph_filtering(a, k), composed(r)
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-5
+    w8 = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3)).to(cuda)
+    (out * w8).sum().backward()
+    (ref * w8).sum().backward()
+    assert rel_err(a.grad.cpu().numpy(), r.grad.cpu().numpy()) < 1e-4  # fp32 sums of ~N terms through sigma
+    # tiny cloud scale: the 0.005 clamp is active and blocks the sigma path
+    sc = 2.0 ** -10  # a power of two: the kNN lists of the scaled cloud are identical
+    a2, r2 = (x * sc).clone().requires_grad_(True), (x * sc).clone().requires_grad_(True)
+    o2, f2 = neighbour_ops.graph_filtering(a2, k), composed(r2)
+    (o2 * w8).sum().backward()
+    (f2 * w8).sum().backward()
+    assert rel_err(o2.detach().cpu().numpy(), f2.detach().cpu().numpy()) < 1e-5
+    assert rel_err(a2.grad.cpu().numpy(), r2.grad.cpu().numpy()) < 1e-4
