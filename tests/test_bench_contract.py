@@ -1,0 +1,33 @@
+"""CPU: bench.py's reference arm prints exactly one JSON line on stdout carrying the contract's keys (the GPU arm is
+exercised on the GPU box by the driver and by tools/gpu_round.sh)."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_reference_arm_emits_one_json_line():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1  # library banners go to stderr
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "chamfer_emd_fwd_bwd_clouds_per_sec" and d["unit"] == "clouds/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_gpu_arm_refuses_to_run_without_cuda():
+    """No CPU fallback: without a GPU the product arm must fail loudly, not print a number."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True,
+                       text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0 and not r.stdout.strip()
+    assert "needs CUDA" in r.stderr or "CUDA" in r.stderr
