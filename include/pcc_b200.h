@@ -119,6 +119,30 @@ int pcc_graph_gather(int b, int c, int n, int k, const float *x, const int64_t *
 int pcc_graph_gather_grad(int b, int c, int n, int k, const int64_t *idx, int mode, const float *grad_out,
                           float *grad_x, pcc_stream_t stream);
 
+/* ---- Fused EdgeConv layer ----------------------------------------------------------------
+ * Replaces get_graph_features (src/utils/neighbour_ops.py:113-119) -> EdgeConvLayer.forward (src/module/layers.py:
+ * 159-203: Conv2d 1x1 without bias, BatchNorm2d, activation) -> max over the k neighbours (src/module/encoders.py:
+ * 49-54) without the (b,2c,n,k) and (b,cout,n,k) tensors.  The caller supplies uv (b,n,2*cout) point-major,
+ * uv[.., :cout] = W1 x, uv[.., cout:] = (W2 - W1) x with W = [W1 | W2] the (cout, 2c) convolution weight (one plain
+ * GEMM), and idx (b,n,k) int64.  Edge value y(i,t) = u[idx[i][t]] + v[i].
+ *   bn_mode 1: batch statistics over all b*n*k edges (training); running_mean/var (may be NULL) are updated with
+ *              `momentum` (unbiased variance), mean/invstd (cout) are returned for the backward
+ *   bn_mode 0: running statistics (eval);   bn_mode 2: no normalisation, out = act(gamma*y + beta) (gamma/beta may be NULL)
+ *   act 0: identity, 1: leaky ReLU with `slope` >= 0 (0 = ReLU)
+ * out (b,cout,n) channels-first.  exty, sy (b,n,cout) fp32 and slot (b,n,cout) uint8 are saved for the backward
+ * (sy only written in bn_mode 1).  PCC_ENOTSUP: k > 64, n > 8192, cout % 4 != 0 or cout > 1024. */
+int pcc_edgeconv_forward(int b, int n, int k, int cout, const float *uv, const int64_t *idx, const float *gamma,
+                         const float *beta, float *running_mean, float *running_var, int bn_mode, float momentum,
+                         float eps, int act, float slope, float *out, float *exty, float *sy, unsigned char *slot,
+                         float *mean, float *invstd, pcc_stream_t stream);
+/* Backward: grad_out (b,cout,n) -> grad_uv (b,n,2*cout), grad_gamma, grad_beta (cout; may be NULL).  In bn_mode 1 every
+ * edge receives a gradient through the batch statistics.  Deterministic: the edges are sorted by target once per call
+ * and summed in a fixed order (no float atomics). */
+int pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int64_t *idx, const float *gamma,
+                          const float *beta, const float *mean, const float *invstd, int bn_mode, int act, float slope,
+                          const float *exty, const float *sy, const unsigned char *slot, const float *grad_out,
+                          float *grad_uv, float *grad_gamma, float *grad_beta, pcc_stream_t stream);
+
 /* Decoder-output smoothing `graph_filtering` (src/utils/neighbour_ops.py:122-133), one launch per
  * direction.  x (b,3,n), idx (b,n,k) int64 = the kNN list of x itself (column 0 is the point), 2 <= k <= 8, n <= 6144.
  * out (b,3,n); mean_dist (b) receives the per-cloud mean nearest-neighbour distance (sigma before the 0.005 clamp),

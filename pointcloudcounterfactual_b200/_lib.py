@@ -37,6 +37,9 @@ _SIGNATURES = {
     "pcc_argkmin": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pcc_graph_gather": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "pcc_graph_gather_grad": (_i, [_i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "pcc_edgeconv_forward": (_i, [_i, _i, _i, _i] + [_vp] * 6 + [_i, ctypes.c_float, ctypes.c_float, _i, ctypes.c_float]
+                             + [_vp] * 7),
+    "pcc_edgeconv_backward": (_i, [_i, _i, _i, _i] + [_vp] * 6 + [_i, _i, ctypes.c_float] + [_vp] * 8),
     "pcc_graph_filtering": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pcc_graph_filtering_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_emd_forward": (_i, [_i, _i, _i] + [_vp] * 14 + [ctypes.c_float, _i, _vp]),

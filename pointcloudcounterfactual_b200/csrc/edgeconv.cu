@@ -1,0 +1,516 @@
+// Fused EdgeConv layer (full row): graph features -> 1x1 conv -> BatchNorm2d -> activation -> max over k,
+// without the (B,2C,N,k) edge tensor and without the (B,Cout,N,k) convolution output.
+//
+// Replaces the sequence  get_graph_features (src/utils/neighbour_ops.py:113-119)  ->  EdgeConvLayer.forward
+// (src/module/layers.py:159-203: Conv2d 1x1 without bias, BatchNorm2d, activation)  ->  x.max(dim=3)
+// (src/module/encoders.py:49-54, classifier.py:55-60).  The convolution is linear, so for edge (i -> j)
+//     y[o][i][j] = W[o] . [x_j - x_i ; x_i] = u[o][j] + v[o][i],   u = W1 x,  v = (W2 - W1) x,  W = [W1 | W2]
+// and the host computes [u | v] for all points with ONE plain library GEMM (B,N,C) x (C,2Cout) -- 1/k of the
+// reference's convolution work.  Everything after that is this file:
+//   ec_reduce_kernel    one pass over the edges: per (point, channel) sum_e y, the extremum of y over the k neighbours
+//                       (max where gamma >= 0, min where gamma < 0: BatchNorm is a per-channel affine map whose slope
+//                       has the sign of gamma and the supported activations are non-decreasing, so
+//                       max_k act(bn(y)) = act(bn(ext_k y))) and its slot; per-CTA partial sums of y and y^2 in fp64
+//   ec_stats_kernel     batch statistics over all B*N*k edges (what BatchNorm2d sees), running-stat update, the
+//                       per-channel affine map
+//   ec_finalize_kernel  out (B,Cout,N) = act(scale * ext + shift), transposed through shared memory
+// Backward (all edges get a gradient through the batch statistics, not only the arg-max edge):
+//     dL/dy_e = a [e == e*] dz - c1 - c2 (y_e - mean),  a = gamma invstd, c1 = a dbeta / E, c2 = a invstd dgamma / E
+//   ec_bwd_point_kernel dz = g act'(z) per (point, channel) + fp64 partials of dbeta, dgamma
+//   ec_bwd_stats_kernel dbeta, dgamma, (a, c1, c2)
+//   ec_csr_kernel       edges sorted by TARGET (counting sort per cloud, each run ordered by edge id), so that
+//   ec_bwd_edge_kernel  grad u_j = sum over the edges that point at j is a gather in a fixed order: deterministic,
+//                       no float atomics (torch's own backward of gather is an atomic scatter-add)
+// All per-point tensors are point-major (B,N,Cout): one neighbour = one contiguous row, L2-resident (0.5-2 MB per cloud).
+#include "common.cuh"
+
+namespace pcc {
+
+constexpr int EC_THREADS = 256;
+constexpr int EC_PTS = 64;       // points per CTA in the edge kernels
+constexpr int EC_MAX_K = 64;
+constexpr int EC_MAX_N = 8192;   // two int arrays of n live in the CSR kernel's shared memory
+
+enum { EC_BN_EVAL = 0, EC_BN_TRAIN = 1, EC_AFFINE = 2 };
+enum { EC_ACT_NONE = 0, EC_ACT_LEAKY = 1 };
+
+__device__ __forceinline__ int ec_clamp(long long j, int n) { return (int)min(max(j, 0LL), (long long)n - 1); }
+
+// ---- forward: one pass over the edges -------------------------------------------------------------------------
+// thread = (point slot, quad of 4 channels); a CTA walks EC_PTS points of one cloud.
+template <bool STATS>
+__global__ void __launch_bounds__(EC_THREADS)
+ec_reduce_kernel(int n, int k, int cout, const float *__restrict__ uv, const int64_t *__restrict__ idx,
+                 const float *__restrict__ gamma, float *__restrict__ exty, float *__restrict__ sy_out,
+                 unsigned char *__restrict__ slot_out, double *__restrict__ partials, int nparts) {
+  __shared__ int sidx[EC_PTS * EC_MAX_K];
+  __shared__ double red[2][EC_THREADS * 4];
+  const int cloud = blockIdx.y;
+  const int i0 = blockIdx.x * EC_PTS;
+  const int npts = min(EC_PTS, n - i0);
+  const int tpp = cout >> 2;               // threads per point
+  const int groups = EC_THREADS / tpp;     // point slots per iteration
+  const int grp = threadIdx.x / tpp, quad = threadIdx.x - grp * tpp;
+  const bool active = grp < groups;
+  const int64_t *ib = idx + ((size_t)cloud * n + i0) * k;
+  for (int e = threadIdx.x; e < npts * k; e += EC_THREADS) sidx[e] = ec_clamp(ib[e], n);
+  __syncthreads();
+  const float *uvb = uv + (size_t)cloud * n * 2 * cout;
+  bool wantmax[4];
+  {
+    const float4 g4 = (active && gamma) ? reinterpret_cast<const float4 *>(gamma)[quad] : make_float4(1.f, 1.f, 1.f, 1.f);
+    wantmax[0] = !(g4.x < 0.f);
+    wantmax[1] = !(g4.y < 0.f);
+    wantmax[2] = !(g4.z < 0.f);
+    wantmax[3] = !(g4.w < 0.f);
+  }
+  double a1[4] = {0., 0., 0., 0.}, a2[4] = {0., 0., 0., 0.};
+  if (active) {
+    for (int p = grp; p < npts; p += groups) {
+      const int i = i0 + p;
+      const float4 v4 = *reinterpret_cast<const float4 *>(uvb + (size_t)i * 2 * cout + cout + 4 * quad);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, ext[4] = {0.f, 0.f, 0.f, 0.f};
+      int slot[4] = {0, 0, 0, 0};
+      const int *nb = sidx + p * k;
+#pragma unroll 5
+      for (int t = 0; t < k; ++t) {
+        const float4 u4 = *reinterpret_cast<const float4 *>(uvb + (size_t)nb[t] * 2 * cout + 4 * quad);
+        const float y[4] = {u4.x + v[0], u4.y + v[1], u4.z + v[2], u4.w + v[3]};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (STATS) {
+            s1[c] += y[c];
+            s2[c] = fmaf(y[c], y[c], s2[c]);
+          }
+          const bool better = wantmax[c] ? (y[c] > ext[c]) : (y[c] < ext[c]);  // strict: first slot wins a tie
+          if (t == 0 || better) {
+            ext[c] = y[c];
+            slot[c] = t;
+          }
+        }
+      }
+      const size_t o = ((size_t)cloud * n + i) * cout + 4 * quad;
+      *reinterpret_cast<float4 *>(exty + o) = make_float4(ext[0], ext[1], ext[2], ext[3]);
+      *reinterpret_cast<uchar4 *>(slot_out + o) =
+          make_uchar4((unsigned char)slot[0], (unsigned char)slot[1], (unsigned char)slot[2], (unsigned char)slot[3]);
+      if (STATS) {
+        *reinterpret_cast<float4 *>(sy_out + o) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          a1[c] += (double)s1[c];
+          a2[c] += (double)s2[c];
+        }
+      }
+    }
+  }
+  if (STATS) {
+    // per-CTA partial sums: fixed order over the point slots -> deterministic
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      red[0][threadIdx.x * 4 + c] = a1[c];
+      red[1][threadIdx.x * 4 + c] = a2[c];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * cout; o += EC_THREADS) {
+      const int s = o / cout, ch = o - s * cout;
+      double acc = 0.;
+      for (int g = 0; g < groups; ++g) acc += red[s][(g * tpp + (ch >> 2)) * 4 + (ch & 3)];
+      const int part = blockIdx.y * gridDim.x + blockIdx.x;
+      partials[((size_t)s * cout + ch) * nparts + part] = acc;  // [2][cout][nparts]
+    }
+  }
+}
+
+// deterministic block sum of doubles (fixed tree)
+template <int T>
+__device__ __forceinline__ double ec_block_sum(double v, double *sm) {
+  sm[threadIdx.x] = v;
+  __syncthreads();
+#pragma unroll
+  for (int s = T / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double r = sm[0];
+  __syncthreads();
+  return r;
+}
+
+// one CTA per channel: statistics over all E = B*N*k edges, running-stat update, per-channel affine map
+__global__ void __launch_bounds__(128)
+ec_stats_kernel(int cout, int nparts, double edges, int bn_mode, const double *__restrict__ partials,
+                const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ running_mean,
+                float *__restrict__ running_var, float momentum, float eps, float *__restrict__ mean_out,
+                float *__restrict__ invstd_out, float *__restrict__ scale, float *__restrict__ shift) {
+  __shared__ double sm[128];
+  const int o = blockIdx.x;
+  float mean = 0.f, invstd = 1.f;
+  if (bn_mode == EC_BN_TRAIN) {
+    double s1 = 0., s2 = 0.;
+    for (int p = threadIdx.x; p < nparts; p += 128) {
+      s1 += partials[(size_t)o * nparts + p];
+      s2 += partials[((size_t)cout + o) * nparts + p];
+    }
+    s1 = ec_block_sum<128>(s1, sm);
+    s2 = ec_block_sum<128>(s2, sm);
+    const double m = s1 / edges;
+    const double var = fmax(s2 / edges - m * m, 0.);  // biased, what BatchNorm normalises with
+    mean = (float)m;
+    invstd = (float)(1. / sqrt(var + (double)eps));
+    if (threadIdx.x == 0 && running_mean && running_var) {
+      const double unbiased = edges > 1. ? var * edges / (edges - 1.) : var;
+      running_mean[o] = (1.f - momentum) * running_mean[o] + momentum * mean;
+      running_var[o] = (1.f - momentum) * running_var[o] + momentum * (float)unbiased;
+    }
+  } else if (bn_mode == EC_BN_EVAL) {
+    mean = running_mean[o];
+    invstd = 1.f / sqrtf(running_var[o] + eps);
+  }
+  if (threadIdx.x == 0) {
+    const float g = gamma ? gamma[o] : 1.f, b = beta ? beta[o] : 0.f;
+    const float a = g * invstd;
+    mean_out[o] = mean;
+    invstd_out[o] = invstd;
+    scale[o] = a;
+    shift[o] = fmaf(-mean, a, b);
+  }
+}
+
+__device__ __forceinline__ float ec_act(float z, int act, float slope) {
+  return (act == EC_ACT_LEAKY && !(z > 0.f)) ? z * slope : z;
+}
+
+// out (B,Cout,N) = act(scale * exty + shift); tile of 32 points x 32 channels transposed through shared memory
+__global__ void __launch_bounds__(256)
+ec_finalize_kernel(int n, int cout, const float *__restrict__ exty, const float *__restrict__ scale,
+                   const float *__restrict__ shift, int act, float slope, float *__restrict__ out) {
+  __shared__ float tile[32][33];
+  const int cloud = blockIdx.z, i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int o = o0 + tx;
+  const float a = o < cout ? scale[o] : 0.f, sh = o < cout ? shift[o] : 0.f;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r;
+    if (i < n && o < cout) tile[r][tx] = ec_act(fmaf(a, exty[((size_t)cloud * n + i) * cout + o], sh), act, slope);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int oo = o0 + r, i = i0 + tx;
+    if (oo < cout && i < n) out[((size_t)cloud * cout + oo) * n + i] = tile[tx][r];
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------------------------------------
+// dz (B,N,Cout) = grad_out (B,Cout,N)^T * act'(z), + fp64 partials of sum dz and sum dz * yhat per channel
+__global__ void __launch_bounds__(256)
+ec_bwd_point_kernel(int n, int cout, const float *__restrict__ gout, const float *__restrict__ exty,
+                    const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
+                    const float *__restrict__ beta, int act, float slope, float *__restrict__ dz,
+                    double *__restrict__ partials, int nparts) {
+  __shared__ float tile[32][33];
+  __shared__ double red[2][8][32];
+  const int cloud = blockIdx.z, i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int oo = o0 + r, i = i0 + tx;
+    tile[r][tx] = (oo < cout && i < n) ? gout[((size_t)cloud * cout + oo) * n + i] : 0.f;
+  }
+  __syncthreads();
+  const int o = o0 + tx;
+  double sb = 0., sg = 0.;
+  if (o < cout) {
+    const float mu = mean[o], is = invstd[o];
+    const float a = (gamma ? gamma[o] : 1.f) * is, sh = fmaf(-mu, a, beta ? beta[o] : 0.f);
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int i = i0 + r;
+      if (i < n) {
+        const size_t at = ((size_t)cloud * n + i) * cout + o;
+        const float e = exty[at];
+        const float z = fmaf(a, e, sh);
+        const float d = tile[tx][r] * ((act == EC_ACT_LEAKY && !(z > 0.f)) ? slope : 1.f);
+        dz[at] = d;
+        sb += (double)d;
+        sg += (double)(d * ((e - mu) * is));
+      }
+    }
+  }
+  red[0][ty][tx] = sb;
+  red[1][ty][tx] = sg;
+  __syncthreads();
+  if (ty < 2 && o < cout) {
+    double acc = 0.;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc += red[ty][r][tx];
+    const int part = blockIdx.z * gridDim.x + blockIdx.x;
+    partials[((size_t)ty * cout + o) * nparts + part] = acc;
+  }
+}
+
+// dbeta, dgamma and the three per-channel coefficients of dL/dy_e
+__global__ void __launch_bounds__(128)
+ec_bwd_stats_kernel(int cout, int nparts, double edges, int bn_mode, const double *__restrict__ partials,
+                    const float *__restrict__ gamma, const float *__restrict__ invstd, float *__restrict__ dgamma,
+                    float *__restrict__ dbeta, float *__restrict__ coef) {
+  __shared__ double sm[128];
+  const int o = blockIdx.x;
+  double sb = 0., sg = 0.;
+  for (int p = threadIdx.x; p < nparts; p += 128) {
+    sb += partials[(size_t)o * nparts + p];
+    sg += partials[((size_t)cout + o) * nparts + p];
+  }
+  sb = ec_block_sum<128>(sb, sm);
+  sg = ec_block_sum<128>(sg, sm);
+  if (threadIdx.x == 0) {
+    if (dbeta) dbeta[o] = (float)sb;
+    if (dgamma) dgamma[o] = (float)sg;
+    const double is = (double)invstd[o];
+    const double a = (double)(gamma ? gamma[o] : 1.f) * is;
+    coef[o] = (float)a;
+    coef[cout + o] = bn_mode == EC_BN_TRAIN ? (float)(a * sb / edges) : 0.f;
+    coef[2 * cout + o] = bn_mode == EC_BN_TRAIN ? (float)(a * is * sg / edges) : 0.f;
+  }
+}
+
+// Edges of one cloud sorted by target: off (n+1) run starts, rev (n*k) packed (source << 8 | slot), ascending inside
+// each run.  One CTA per cloud; counting sort in shared memory, runs ordered by rank counting with warp shuffles.
+__global__ void __launch_bounds__(1024)
+ec_csr_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ off, int *__restrict__ rev_tmp,
+              int *__restrict__ rev) {
+  extern __shared__ int csm[];  // cnt[n] | cursor[n]
+  __shared__ int wsum[32];
+  int *cnt = csm, *cursor = csm + n;
+  const int cloud = blockIdx.x;
+  const int total = n * k;
+  const int64_t *ib = idx + (size_t)cloud * total;
+  int *offb = off + (size_t)cloud * (n + 1);
+  int *tmpb = rev_tmp + (size_t)cloud * total;
+  int *revb = rev + (size_t)cloud * total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = threadIdx.x; j < n; j += 1024) cnt[j] = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < total; e += 1024) atomicAdd(&cnt[ec_clamp(ib[e], n)], 1);
+  __syncthreads();
+  // exclusive scan: each thread owns a contiguous chunk
+  const int chunk = (n + 1023) / 1024;
+  const int j0 = threadIdx.x * chunk, j1 = min(n, j0 + chunk);
+  int local = 0;
+  for (int j = j0; j < j1; ++j) local += cnt[j];
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    wsum[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  int run = incl - local + (warp ? wsum[warp - 1] : 0);
+  for (int j = j0; j < j1; ++j) {
+    cursor[j] = run;
+    offb[j] = run;
+    run += cnt[j];
+  }
+  if (threadIdx.x == 0) offb[n] = total;
+  __syncthreads();
+  for (int e = threadIdx.x; e < total; e += 1024) {
+    const int j = ec_clamp(ib[e], n);
+    const int i = e / k, t = e - i * k;
+    tmpb[atomicAdd(&cursor[j], 1)] = (i << 8) | t;
+  }
+  __syncthreads();  // the block's global writes are visible to the block
+  for (int j = warp; j < n; j += 32) {
+    const int len = cnt[j], beg = cursor[j] - len;
+    for (int base = 0; base < len; base += 32) {
+      const int mine = base + lane < len ? tmpb[beg + base + lane] : 0x7fffffff;
+      int rank = 0;
+      for (int cb = 0; cb < len; cb += 32) {
+        const int other = cb + lane < len ? tmpb[beg + cb + lane] : 0x7fffffff;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) rank += (__shfl_sync(0xffffffffu, other, s) < mine) ? 1 : 0;
+      }
+      if (base + lane < len) revb[beg + rank] = mine;
+    }
+  }
+}
+
+// grad [u | v] (B,N,2Cout); thread = (point slot, quad of channels), the point is the TARGET for grad u and the SOURCE
+// for grad v.
+template <bool TRAIN>
+__global__ void __launch_bounds__(EC_THREADS)
+ec_bwd_edge_kernel(int n, int k, int cout, const float *__restrict__ uv, const int *__restrict__ off,
+                   const int *__restrict__ rev, const float *__restrict__ dz, const unsigned char *__restrict__ slot,
+                   const float *__restrict__ sy, const float *__restrict__ mean, const float *__restrict__ coef,
+                   float *__restrict__ guv) {
+  const int cloud = blockIdx.y;
+  const int i0 = blockIdx.x * EC_PTS;
+  const int npts = min(EC_PTS, n - i0);
+  const int tpp = cout >> 2;
+  const int groups = EC_THREADS / tpp;
+  const int grp = threadIdx.x / tpp, quad = threadIdx.x - grp * tpp;
+  if (grp >= groups) return;
+  const float4 a4 = reinterpret_cast<const float4 *>(coef)[quad];
+  const float4 c14 = reinterpret_cast<const float4 *>(coef + cout)[quad];
+  const float4 c24 = reinterpret_cast<const float4 *>(coef + 2 * cout)[quad];
+  const float4 mu4 = reinterpret_cast<const float4 *>(mean)[quad];
+  const float a[4] = {a4.x, a4.y, a4.z, a4.w}, c1[4] = {c14.x, c14.y, c14.z, c14.w},
+              c2[4] = {c24.x, c24.y, c24.z, c24.w}, mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
+  const size_t pbase = (size_t)cloud * n;
+  const int *offb = off + (size_t)cloud * (n + 1);
+  const int *revb = rev + (size_t)cloud * n * k;
+  for (int p = grp; p < npts; p += groups) {
+    const int j = i0 + p;
+    const int beg = offb[j], end = offb[j + 1];
+    float gd[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int s = beg; s < end; ++s) {
+      const int pk = revb[s];
+      const int i = pk >> 8, t = pk & 255;
+      const size_t at = (pbase + i) * cout + 4 * quad;
+      const float4 d4 = *reinterpret_cast<const float4 *>(dz + at);
+      const uchar4 s4 = *reinterpret_cast<const uchar4 *>(slot + at);
+      gd[0] += (s4.x == t) ? d4.x : 0.f;
+      gd[1] += (s4.y == t) ? d4.y : 0.f;
+      gd[2] += (s4.z == t) ? d4.z : 0.f;
+      gd[3] += (s4.w == t) ? d4.w : 0.f;
+      if (TRAIN) {
+        const float4 v4 = *reinterpret_cast<const float4 *>(uv + (pbase + i) * 2 * cout + cout + 4 * quad);
+        gv[0] += v4.x;
+        gv[1] += v4.y;
+        gv[2] += v4.z;
+        gv[3] += v4.w;
+      }
+    }
+    const size_t at = (pbase + j) * cout + 4 * quad;
+    const float4 dj4 = *reinterpret_cast<const float4 *>(dz + at);
+    const float dj[4] = {dj4.x, dj4.y, dj4.z, dj4.w};
+    float gu[4], gvv[4];
+    if (TRAIN) {
+      const float deg = (float)(end - beg), kf = (float)k;
+      const float4 u4 = *reinterpret_cast<const float4 *>(uv + (pbase + j) * 2 * cout + 4 * quad);
+      const float4 sy4 = *reinterpret_cast<const float4 *>(sy + at);
+      const float u[4] = {u4.x, u4.y, u4.z, u4.w}, syj[4] = {sy4.x, sy4.y, sy4.z, sy4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        // sum over incoming edges of (y_e - mean) = deg (u_j - mean) + sum v_i
+        gu[c] = a[c] * gd[c] - deg * c1[c] - c2[c] * fmaf(deg, u[c] - mu[c], gv[c]);
+        // sum over outgoing edges of (y_e - mean) = sy_j - k mean
+        gvv[c] = a[c] * dj[c] - kf * c1[c] - c2[c] * fmaf(-kf, mu[c], syj[c]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        gu[c] = a[c] * gd[c];
+        gvv[c] = a[c] * dj[c];
+      }
+    }
+    float *g = guv + (pbase + j) * 2 * cout + 4 * quad;
+    *reinterpret_cast<float4 *>(g) = make_float4(gu[0], gu[1], gu[2], gu[3]);
+    *reinterpret_cast<float4 *>(g + cout) = make_float4(gvv[0], gvv[1], gvv[2], gvv[3]);
+  }
+}
+
+static bool ec_shape_ok(int b, int n, int k, int cout) {
+  return b > 0 && b <= 65535 && n > 0 && n <= EC_MAX_N && k > 0 && k <= EC_MAX_K && cout >= 4 && cout <= 1024 &&
+         cout % 4 == 0;
+}
+
+}  // namespace pcc
+
+using namespace pcc;
+
+extern "C" __attribute__((visibility("default"))) int
+pcc_edgeconv_forward(int b, int n, int k, int cout, const float *uv, const int64_t *idx, const float *gamma,
+                     const float *beta, float *running_mean, float *running_var, int bn_mode, float momentum, float eps,
+                     int act, float slope, float *out, float *exty, float *sy, unsigned char *slot, float *mean,
+                     float *invstd, pcc_stream_t stream) {
+  if (b == 0 || n == 0) return PCC_OK;
+  if (!ec_shape_ok(b, n, k, cout)) return PCC_ENOTSUP;
+  if (bn_mode < 0 || bn_mode > 2 || act < 0 || act > 1 || (act == EC_ACT_LEAKY && slope < 0.f)) return PCC_EINVAL;
+  if (bn_mode == EC_BN_EVAL && (!running_mean || !running_var)) return PCC_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((n + EC_PTS - 1) / EC_PTS, b);
+  const int nparts = (int)(grid.x * grid.y);
+  char *ws = nullptr;
+  const size_t part_bytes = sizeof(double) * 2 * cout * nparts, aff_bytes = sizeof(float) * 2 * cout;
+  cudaError_t e = cudaMallocAsync((void **)&ws, part_bytes + aff_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  double *partials = reinterpret_cast<double *>(ws);
+  float *scale = reinterpret_cast<float *>(ws + part_bytes), *shift = scale + cout;
+  if (bn_mode == EC_BN_TRAIN)
+    ec_reduce_kernel<true><<<grid, EC_THREADS, 0, st>>>(n, k, cout, uv, idx, gamma, exty, sy, slot, partials, nparts);
+  else
+    ec_reduce_kernel<false><<<grid, EC_THREADS, 0, st>>>(n, k, cout, uv, idx, gamma, exty, sy, slot, partials, nparts);
+  ec_stats_kernel<<<cout, 128, 0, st>>>(cout, nparts, (double)b * n * k, bn_mode, partials, gamma, beta, running_mean,
+                                        running_var, momentum, eps, mean, invstd, scale, shift);
+  ec_finalize_kernel<<<dim3((n + 31) / 32, (cout + 31) / 32, b), 256, 0, st>>>(n, cout, exty, scale, shift, act, slope,
+                                                                              out);
+  cudaFreeAsync(ws, st);
+  return finish_launch(3);
+}
+
+extern "C" __attribute__((visibility("default"))) int
+pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int64_t *idx, const float *gamma,
+                      const float *beta, const float *mean, const float *invstd, int bn_mode, int act, float slope,
+                      const float *exty, const float *sy, const unsigned char *slot, const float *grad_out,
+                      float *grad_uv, float *grad_gamma, float *grad_beta, pcc_stream_t stream) {
+  if (b == 0 || n == 0) return PCC_OK;
+  if (!ec_shape_ok(b, n, k, cout)) return PCC_ENOTSUP;
+  if (bn_mode < 0 || bn_mode > 2 || act < 0 || act > 1) return PCC_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(ec_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(2 * EC_MAX_N * sizeof(int)));
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const dim3 tgrid((n + 31) / 32, (cout + 31) / 32, b);
+  const int nparts = (int)(tgrid.x * b);
+  const size_t total = (size_t)b * n * k;
+  const size_t part_bytes = sizeof(double) * 2 * cout * nparts, dz_bytes = sizeof(float) * (size_t)b * n * cout,
+               coef_bytes = sizeof(float) * 4 * cout, off_bytes = sizeof(int) * (size_t)b * (n + 1),
+               rev_bytes = sizeof(int) * total;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  char *ws = nullptr;
+  cudaError_t e = cudaMallocAsync(
+      (void **)&ws, up(part_bytes) + up(dz_bytes) + up(coef_bytes) + up(off_bytes) + 2 * up(rev_bytes), st);
+  if (e != cudaSuccess) return (int)e;
+  char *w = ws;
+  double *partials = reinterpret_cast<double *>(w);
+  w += up(part_bytes);
+  float *dz = reinterpret_cast<float *>(w);
+  w += up(dz_bytes);
+  float *coef = reinterpret_cast<float *>(w);
+  w += up(coef_bytes);
+  int *off = reinterpret_cast<int *>(w);
+  w += up(off_bytes);
+  int *rev_tmp = reinterpret_cast<int *>(w);
+  w += up(rev_bytes);
+  int *rev = reinterpret_cast<int *>(w);
+  ec_bwd_point_kernel<<<tgrid, 256, 0, st>>>(n, cout, grad_out, exty, mean, invstd, gamma, beta, act, slope, dz,
+                                             partials, nparts);
+  ec_bwd_stats_kernel<<<cout, 128, 0, st>>>(cout, nparts, (double)b * n * k, bn_mode, partials, gamma, invstd,
+                                            grad_gamma, grad_beta, coef);
+  ec_csr_kernel<<<b, 1024, 2 * n * sizeof(int), st>>>(n, k, idx, off, rev_tmp, rev);
+  const dim3 grid((n + EC_PTS - 1) / EC_PTS, b);
+  if (bn_mode == EC_BN_TRAIN)
+    ec_bwd_edge_kernel<true><<<grid, EC_THREADS, 0, st>>>(n, k, cout, uv, off, rev, dz, slot, sy, mean, coef, grad_uv);
+  else
+    ec_bwd_edge_kernel<false><<<grid, EC_THREADS, 0, st>>>(n, k, cout, uv, off, rev, dz, slot, sy, mean, coef, grad_uv);
+  cudaFreeAsync(ws, st);
+  return finish_launch(4);
+}

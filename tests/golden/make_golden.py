@@ -8,6 +8,8 @@ What is executed from the reference, unmodified:
   * ``src/utils/neighbour_ops.py`` loaded by path (torch_knn, self_square_distance, torch_square_distance,
     pykeops_knn, pykeops_square_distance, get_neighbours, get_graph_features, graph_max_pooling,
     get_local_covariance, graph_filtering).
+  * ``src/module/layers.py`` loaded by path (EdgeConvLayer: Conv2d 1x1 + BatchNorm2d + activation), run after the
+    reference's get_graph_features and followed by the max over k exactly as ``src/module/encoders.py:49-54`` does.
   * ``pykeops_chamfer`` and ``torch_chamfer`` -- their function bodies are extracted with ``ast`` from
     ``src/train/metrics_and_losses.py`` (the module itself cannot be imported: drytorch/torcheval are absent)
     and exec'd against the imported neighbour_ops functions.
@@ -86,6 +88,13 @@ def _install_pykeops_stub() -> None:
 def load_reference_neighbour_ops():
     _install_pykeops_stub()
     spec = importlib.util.spec_from_file_location("ref_neighbour_ops", REF / "src/utils/neighbour_ops.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_reference_layers():
+    spec = importlib.util.spec_from_file_location("ref_layers", REF / "src/module/layers.py")
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
@@ -172,6 +181,42 @@ def main() -> None:
     graph.update(f=_np(f), gf16_idx=_np(idx), gf16_feat=_np(feat))
     nops.knn = nops_knn
     np.savez_compressed(OUT / "graph.npz", **graph)
+
+    # ---- EdgeConv layer: get_graph_features -> EdgeConvLayer -> max over k, forward and backward ----
+    layers = load_reference_layers()
+    nops.knn = nops.pykeops_knn
+    ec = {}
+    ecases = {
+        # name: (input (B,C,N), k, Cout, activation factory or None)
+        "xyz": (synthetic.knn_xyz(2, 128), 8, 16, None),                                   # first DGCNN layer: no act
+        "feat": (synthetic.knn_features(2, 16, 128), 6, 32, lambda: torch.nn.LeakyReLU(0.2)),
+    }
+    for name, (x0, k, cout, act_cls) in ecases.items():
+        torch.manual_seed(11)
+        layer = layers.EdgeConvLayer(2 * x0.shape[1], cout, act_cls=act_cls)
+        with torch.no_grad():  # non-trivial affine parameters, some channels with NEGATIVE gamma (max becomes min)
+            layer.bn.weight.copy_(torch.linspace(-0.7, 1.3, cout))
+            layer.bn.bias.copy_(torch.linspace(0.4, -0.4, cout))
+        layer.train()
+        x = x0.clone().requires_grad_(True)
+        idx, feat = nops.get_graph_features(x, torch.empty(0), k=k)
+        out = layer(feat).max(dim=3, keepdim=False)[0]
+        gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+        out.backward(gout)
+        ec.update({
+            f"{name}_x": _np(x0), f"{name}_k": np.int64(k), f"{name}_idx": _np(idx),
+            f"{name}_weight": _np(layer.dense.weight).reshape(cout, -1), f"{name}_gamma": _np(layer.bn.weight),
+            f"{name}_beta": _np(layer.bn.bias), f"{name}_slope": np.float32(-1.0 if act_cls is None else 0.2),
+            f"{name}_train_out": _np(out), f"{name}_gout": _np(gout), f"{name}_gx": _np(x.grad),
+            f"{name}_gw": _np(layer.dense.weight.grad).reshape(cout, -1), f"{name}_ggamma": _np(layer.bn.weight.grad),
+            f"{name}_gbeta": _np(layer.bn.bias.grad), f"{name}_running_mean": _np(layer.bn.running_mean),
+            f"{name}_running_var": _np(layer.bn.running_var),
+        })
+        layer.eval()  # running statistics as left by the one training step above
+        with torch.no_grad():
+            ec[f"{name}_eval_out"] = _np(layer(nops.get_graph_features(x0, idx, k=k)[1]).max(dim=3)[0])
+    nops.knn = nops_knn
+    np.savez_compressed(OUT / "edgeconv.npz", **ec)
 
     for p in sorted(OUT.glob("*.npz")):
         print(p.name, p.stat().st_size, "bytes")

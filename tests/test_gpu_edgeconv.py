@@ -1,0 +1,164 @@
+"""GPU: the fused EdgeConv layer (pcc_edgeconv_forward / _backward behind edgeconv.edge_conv_max / fused_edge_conv)
+against (a) the fixture produced by the reference's own layers.py + neighbour_ops.py, (b) the float64 CPU oracle at
+larger shapes, (c) the reference's op sequence run by torch on the same GPU through an EdgeConvLayer-shaped module.
+
+Tolerances (max-norm relative, per tensor): the fused path sums the convolution as W1 x_j + (W2-W1) x_i instead of
+W.[x_j - x_i; x_i] and reduces the statistics in a different order, so results agree to fp32 rounding, not bit for
+bit: 2e-5 on outputs / statistics, 1e-4 on gradients (they pass through 1/sigma and the cancelling u + v)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from conftest import rel_err
+from oracle import edgeconv_ref
+from pointcloudcounterfactual_b200 import edgeconv, neighbour_ops, synthetic
+
+pytestmark = pytest.mark.gpu
+G = np.load(Path(__file__).parent / "golden" / "edgeconv.npz")
+OUT_TOL, GRAD_TOL = 2e-5, 1e-4
+
+
+def case(name):
+    t = {k[len(name) + 1:]: torch.from_numpy(np.asarray(G[k])) for k in G.files if k.startswith(name + "_")}
+    t["slope"] = None if float(t["slope"]) < 0 else float(t["slope"])
+    return t
+
+
+@pytest.mark.parametrize("name", ["xyz", "feat"])
+def test_fused_layer_matches_reference_fixture(cuda, name):
+    c = case(name)
+    cout = c["weight"].shape[0]
+    x = c["x"].to(cuda).requires_grad_(True)
+    w = c["weight"].to(cuda).requires_grad_(True)
+    gamma = c["gamma"].to(cuda).requires_grad_(True)
+    beta = c["beta"].to(cuda).requires_grad_(True)
+    rm, rv = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+    out = edgeconv.edge_conv_max(x, c["idx"].to(cuda), w, gamma, beta, rm, rv, edgeconv.BN_TRAIN, 0.1, 1e-5, c["slope"])
+    out.backward(c["gout"].to(cuda))
+    assert out.shape == c["train_out"].shape
+    assert rel_err(out.detach().cpu(), c["train_out"]) < OUT_TOL
+    assert rel_err(rm.cpu(), c["running_mean"]) < OUT_TOL and rel_err(rv.cpu(), c["running_var"]) < OUT_TOL
+    assert rel_err(x.grad.cpu(), c["gx"]) < GRAD_TOL and rel_err(w.grad.cpu(), c["gw"]) < GRAD_TOL
+    assert rel_err(gamma.grad.cpu(), c["ggamma"]) < GRAD_TOL and rel_err(beta.grad.cpu(), c["gbeta"]) < GRAD_TOL
+    with torch.no_grad():
+        ev = edgeconv.edge_conv_max(c["x"].to(cuda), c["idx"].to(cuda), c["weight"].to(cuda), c["gamma"].to(cuda),
+                                    c["beta"].to(cuda), c["running_mean"].to(cuda), c["running_var"].to(cuda),
+                                    edgeconv.BN_EVAL, 0.1, 1e-5, c["slope"])
+    assert rel_err(ev.cpu(), c["eval_out"]) < OUT_TOL
+
+
+@pytest.mark.parametrize("b,c,n,k,cout,slope,mode", [
+    (2, 3, 300, 25, 64, None, "train"),      # first DGCNN layer, ragged N
+    (2, 64, 512, 20, 64, 0.2, "train"),
+    (1, 64, 1000, 25, 128, 0.2, "train"),
+    (1, 128, 257, 25, 256, 0.2, "train"),    # last DGCNN layer (64 threads per point)
+    (2, 16, 130, 7, 20, 0.0, "train"),       # ReLU, Cout = 20 (5 threads per point, idle tail threads)
+    (2, 32, 200, 9, 32, 0.2, "eval"),
+    (2, 32, 200, 9, 32, None, "affine"),
+])
+def test_fused_layer_matches_float64_oracle(cuda, b, c, n, k, cout, slope, mode):
+    gen = torch.Generator().manual_seed(100 + n)
+    x0 = synthetic.knn_xyz(b, n) if c == 3 else synthetic.knn_features(b, c, n)
+    idx = neighbour_ops.knn(x0.to(cuda), k)
+    w0 = torch.randn(cout, 2 * c, generator=gen) / (2 * c) ** 0.5
+    g0 = torch.randn(cout, generator=gen)   # about half the channels get a negative gamma
+    b0 = torch.randn(cout, generator=gen) * 0.3
+    rm0, rv0 = torch.randn(cout, generator=gen) * 0.1, torch.rand(cout, generator=gen) + 0.5
+    gout = torch.randn(b, cout, n, generator=gen)
+    bn_mode = {"train": edgeconv.BN_TRAIN, "eval": edgeconv.BN_EVAL, "affine": edgeconv.AFFINE}[mode]
+
+    x, w, gm, bt = (t.to(cuda).requires_grad_(True) for t in (x0, w0, g0, b0))
+    rm, rv = rm0.to(cuda), rv0.to(cuda)
+    out = edgeconv.edge_conv_max(x, idx, w, gm, bt, rm, rv, bn_mode, 0.1, 1e-5, slope)
+    out.backward(gout.to(cuda))
+
+    xr, wr, gr, br = (t.double().requires_grad_(True) for t in (x0, w0, g0, b0))
+    if mode == "affine":   # no normalisation: the oracle's eval branch with mean 0, var 1 - eps
+        ref, nrm, nrv = edgeconv_ref.edge_conv_max(xr, idx.cpu(), wr, gr, br, torch.zeros(cout), torch.ones(cout) - 1e-5,
+                                                   False, 0.1, 1e-5, slope)
+    else:
+        ref, nrm, nrv = edgeconv_ref.edge_conv_max(xr, idx.cpu(), wr, gr, br, rm0, rv0, mode == "train", 0.1, 1e-5, slope)
+    ref.backward(gout.double())
+    assert rel_err(out.detach().cpu(), ref.detach()) < OUT_TOL
+    if mode == "train":
+        assert rel_err(rm.cpu(), nrm) < OUT_TOL and rel_err(rv.cpu(), nrv) < OUT_TOL
+    else:
+        assert torch.equal(rm.cpu(), rm0) and torch.equal(rv.cpu(), rv0)
+    for got, want in ((x.grad, xr.grad), (w.grad, wr.grad), (gm.grad, gr.grad), (bt.grad, br.grad)):
+        assert rel_err(got.cpu(), want) < GRAD_TOL
+
+
+class _EdgeConvLayer(nn.Module):
+    """Same attributes and forward as the reference's EdgeConvLayer (src/module/layers.py:159-203), default options."""
+
+    def __init__(self, cin, cout, act=None):
+        super().__init__()
+        self.dense = nn.Conv2d(cin, cout, kernel_size=1, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+        self.act = act
+        self.residual = False
+
+    def forward(self, x):
+        y = self.bn(self.dense(x))
+        return self.act(y) if self.act is not None else y
+
+
+def test_module_drop_in_matches_torch_composition_on_gpu(cuda):
+    """fused_edge_conv(layer, x, indices, k) against the three reference lines run by torch on the same device (fp32
+    convolution: TF32 off), two consecutive training steps (running statistics, num_batches_tracked) and eval."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(3)
+        fused = _EdgeConvLayer(128, 64, nn.LeakyReLU(0.2, inplace=True)).to(cuda)
+        plain = _EdgeConvLayer(128, 64, nn.LeakyReLU(0.2, inplace=True)).to(cuda)
+        plain.load_state_dict(fused.state_dict())
+        for step in range(2):
+            x0 = synthetic.knn_features(2, 64, 640).to(cuda) + step
+            xa, xb = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+            idx, out = edgeconv.fused_edge_conv(fused, xa, torch.empty(0), 20)
+            feat = neighbour_ops.get_graph_features(xb, idx, 20)[1]
+            ref = plain(feat).max(dim=3, keepdim=False)[0]
+            gout = torch.randn_like(ref)
+            out.backward(gout)
+            ref.backward(gout)
+            assert rel_err(out.detach().cpu(), ref.detach().cpu()) < OUT_TOL
+            assert rel_err(xa.grad.cpu(), xb.grad.cpu()) < GRAD_TOL
+            assert rel_err(fused.dense.weight.grad.cpu(), plain.dense.weight.grad.cpu()) < GRAD_TOL
+            assert rel_err(fused.bn.weight.grad.cpu(), plain.bn.weight.grad.cpu()) < GRAD_TOL
+            assert rel_err(fused.bn.bias.grad.cpu(), plain.bn.bias.grad.cpu()) < GRAD_TOL
+            assert rel_err(fused.bn.running_mean.cpu(), plain.bn.running_mean.cpu()) < OUT_TOL
+            assert rel_err(fused.bn.running_var.cpu(), plain.bn.running_var.cpu()) < OUT_TOL
+            assert int(fused.bn.num_batches_tracked) == int(plain.bn.num_batches_tracked) == step + 1
+            for m in (fused, plain):
+                m.zero_grad()
+        fused.eval()
+        plain.eval()
+        with torch.no_grad():
+            x0 = synthetic.knn_features(1, 64, 333).to(cuda)
+            idx, out = edgeconv.fused_edge_conv(fused, x0, torch.empty(0), 20)
+            ref = plain(neighbour_ops.get_graph_features(x0, idx, 20)[1]).max(dim=3)[0]
+        assert rel_err(out.cpu(), ref.cpu()) < OUT_TOL
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_backward_is_deterministic_and_limits_fall_back(cuda):
+    x0 = synthetic.knn_features(2, 64, 512).to(cuda)
+    layer = _EdgeConvLayer(128, 64, nn.LeakyReLU(0.2)).to(cuda)
+    grads = []
+    for _ in range(2):
+        x = x0.clone().requires_grad_(True)
+        _, out = edgeconv.fused_edge_conv(layer, x, torch.empty(0), 20)
+        out.square().sum().backward()
+        grads.append((x.grad.clone(), layer.dense.weight.grad.clone()))
+        layer.zero_grad()
+    assert torch.equal(grads[0][0], grads[1][0])          # no float atomics anywhere in the fused backward
+    gelu = _EdgeConvLayer(128, 64, nn.GELU()).to(cuda)    # not monotone: the reference op sequence runs instead
+    _, out = edgeconv.fused_edge_conv(gelu, x0, torch.empty(0), 20)
+    assert out.shape == (2, 64, 512) and int(gelu.bn.num_batches_tracked) == 1
+    with pytest.raises(RuntimeError):
+        edgeconv.edge_conv_max(x0.cpu(), torch.zeros(2, 512, 20, dtype=torch.int64), layer.dense.weight.cpu())
