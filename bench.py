@@ -129,7 +129,7 @@ def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from pointcloudcounterfactual_b200 import _lib, losses, neighbour_ops, sharding, synthetic
+    from pointcloudcounterfactual_b200 import _lib, edgeconv, losses, neighbour_ops, sharding, synthetic
     from pointcloudcounterfactual_b200.structural_losses import match_cost, nn_distance
     from pointcloudcounterfactual_b200.structural_losses.structural_losses_backend import NNDistance
 
@@ -366,18 +366,71 @@ def run_b200(args) -> None:
         # ---- BASELINE configs[3] / [4]: the reference's models cannot be instantiated here (drytorch / hydra are not
         # installed), so these are the hot-path op sequences of one training step / one latent-optimisation
         # iteration, per GPU, with the step's real collective ------------------------------------------------------
-        f64a = f64a_
-        f64b = synthetic.knn_features(B_PER_GPU, 64, N_POINTS, seed=3100 + rank).to(dev)
-        f128 = synthetic.knn_features(B_PER_GPU, 128, N_POINTS, seed=3200 + rank).to(dev)
         grad_buf = torch.zeros(45 * (1 << 20) // 4, device=dev)  # ~45 MB of fp32 autoencoder gradients
 
-        layers = [t.detach().requires_grad_(True) for t in (x25, f64a, f64b, f128)]  # EdgeConv inputs: C = 3, 64, 64, 128
+        # ---- fused EdgeConv layer (full row) and the DGCNN edge-convolution stack built from it ----------
+        class _EdgeConv(torch.nn.Module):
+            """Attribute names and forward of the reference's EdgeConvLayer (src/module/layers.py:159-203)."""
+
+            def __init__(self, cin, cout, act):
+                super().__init__()
+                self.dense = torch.nn.Conv2d(cin, cout, kernel_size=1, bias=False)
+                self.bn = torch.nn.BatchNorm2d(cout)
+                self.act, self.residual = act, False
+
+            def forward(self, x):
+                y = self.bn(self.dense(x))
+                return self.act(y) if self.act is not None else y
+
+        torch.manual_seed(7)
+        h_dim = (64, 64, 128, 256)  # DGCNN.h_dim (src/module/encoders.py:36); first layer without activation (:37)
+        enc = torch.nn.ModuleList(
+            [_EdgeConv(6, h_dim[0], None)] +
+            [_EdgeConv(2 * i, o, torch.nn.LeakyReLU(0.2, inplace=True)) for i, o in zip(h_dim[:-1], h_dim[1:])]).to(dev)
+        enc_params = [p for p in enc.parameters()]
+        x_enc = x25.detach().requires_grad_(True)
+
+        def encoder(fused: bool):
+            xs, h = [], x_enc
+            for layer in enc:
+                if fused:
+                    h = edgeconv.fused_edge_conv(layer, h, torch.empty(0), 25)[1]
+                else:  # the reference's three lines (encoders.py:49-54) on top of the fused gather
+                    h = layer(neighbour_ops.get_graph_features(h, torch.empty(0), 25)[1]).max(dim=3, keepdim=False)[0]
+                xs.append(h)
+            return torch.cat(xs, dim=1)  # (B, 512, N), the input of DGCNN.final_conv
+
+        def encoder_fb(fused: bool = True):
+            feat = encoder(fused)
+            torch.autograd.grad(feat, [x_enc] + enc_params, feat)
+
+        def layer_fb(fused: bool):
+            x = f64a_.detach().requires_grad_(True)
+            if fused:
+                out = edgeconv.fused_edge_conv(enc[1], x, idx25, 25)[1]
+            else:
+                out = enc[1](neighbour_ops.get_graph_features(x, idx25, 25)[1]).max(dim=3, keepdim=False)[0]
+            torch.autograd.grad(out, [x] + list(enc[1].parameters()), out)
+
+        ms, gr = graph_or_eager(lambda: layer_fb(True), reps=10)
+        ms_t = ev_time(lambda: layer_fb(False), 5)
+        edge_bytes = B_PER_GPU * N_POINTS * 25 * 64 * 4  # one 64-channel row of u per edge, gathered from L2
+        sub["edgeconv_layer_c64_cout64_n2048_k25_fwd_bwd"] = {
+            "ms": ms, "cuda_graph": gr, "torch_composition_ms": ms_t, "speedup_vs_torch_composition": ms_t / ms,
+            "note": "kNN given; graph features -> Conv2d 1x1 -> BatchNorm2d (batch statistics) -> LeakyReLU -> max over k, "
+                    "forward and backward w.r.t. input, weight, gamma, beta.  Fused: conv applied to the points (one GEMM), "
+                    f"edge pass gathers {edge_bytes / 1e6:.0f} MB of rows from L2; torch composition: the reference's op "
+                    "sequence (cudnn TF32 conv on the (B,2C,N,k) tensor) on top of the fused gather"}
+        ms, gr = graph_or_eager(lambda: encoder_fb(True), reps=10)
+        ms_t = ev_time(lambda: encoder_fb(False), 3)
+        sub["dgcnn_edgeconv_stack_fwd_bwd"] = {
+            "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr, "torch_composition_ms": ms_t,
+            "speedup_vs_torch_composition": ms_t / ms,
+            "note": "the four chained EdgeConv layers of DGCNN (3->64->64->128->256, N=2048, k=25, dynamic kNN per layer), "
+                    "forward and backward; torch composition = same kNN and gather kernels, reference op sequence after"}
 
         def ae_step():
-            for t in layers:  # encoder: kNN graph (k=25) + EdgeConv gather forward and backward per layer
-                feat = neighbour_ops.get_graph_features(t, torch.empty(0), 25)[1]
-                torch.autograd.grad(feat, t, feat)
-                del feat
+            encoder_fb(True)  # encoder: per layer kNN graph (k=25) + fused EdgeConv layer, forward and backward
             gfilt()  # decoder graph_filtering (kNN k=4 + smoothing forward / backward)
             loss = losses.chamfer_emd(rr, ref_d)
             torch.autograd.grad(loss.sum(), rr)
@@ -387,9 +440,10 @@ def run_b200(args) -> None:
         ms = ev_time(ae_step, 10) if world > 1 else graph_or_eager(ae_step, reps=10)[0]
         sub["ae_step_hotpath"] = {
             "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": world == 1,
-            "note": "stand-in for configs[3]: per EdgeConv layer (C=3,64,64,128; N=2048; k=25) kNN + get_graph_features "
-                    "forward and backward, + decoder graph_filtering (kNN k=4) fwd+bwd + ChamferEMD fwd+bwd"
-                    + (" + NCCL all-reduce of 45 MB fp32 gradients" if world > 1 else "") + "; 32 clouds per GPU"}
+            "note": "stand-in for configs[3]: DGCNN edge-convolution stack (4 layers, dynamic kNN k=25, fused EdgeConv) "
+                    "forward and backward + decoder graph_filtering (kNN k=4) fwd+bwd + ChamferEMD fwd+bwd"
+                    + (" + NCCL all-reduce of 45 MB fp32 gradients" if world > 1 else "") + "; 32 clouds per GPU.  "
+                    "Not included (plain torch layers of the reference): final_conv, the PCGen decoder MLPs, optimizer"}
 
         leaf = recon_d.detach().clone().requires_grad_(True)
         opt = torch.optim.Adam([leaf], lr=1e-3, capturable=True)

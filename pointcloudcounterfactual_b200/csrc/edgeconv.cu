@@ -18,9 +18,11 @@
 //     dL/dy_e = a [e == e*] dz - c1 - c2 (y_e - mean),  a = gamma invstd, c1 = a dbeta / E, c2 = a invstd dgamma / E
 //   ec_bwd_point_kernel dz = g act'(z) per (point, channel) + fp64 partials of dbeta, dgamma
 //   ec_bwd_stats_kernel dbeta, dgamma, (a, c1, c2)
-//   ec_csr_kernel       edges sorted by TARGET (counting sort per cloud, each run ordered by edge id), so that
-//   ec_bwd_edge_kernel  grad u_j = sum over the edges that point at j is a gather in a fixed order: deterministic,
-//                       no float atomics (torch's own backward of gather is an atomic scatter-add)
+//   ec_hist/scan/fill/sort_kernel  edges sorted by TARGET (counting sort per cloud, each run ordered by edge id), so that
+//   ec_bwd_chunk/finish_kernel  grad u_j = sum over the edges that point at j is a segmented sum over that list in a
+//                       fixed order: deterministic, no float atomics (torch's backward of gather is an atomic
+//                       scatter-add), and balanced whatever the in-degrees are (hubs of several hundred edges in
+//                       feature space)
 // All per-point tensors are point-major (B,N,Cout): one neighbour = one contiguous row, L2-resident (0.5-2 MB per cloud).
 #include "common.cuh"
 
@@ -29,7 +31,7 @@ namespace pcc {
 constexpr int EC_THREADS = 256;
 constexpr int EC_PTS = 64;       // points per CTA in the edge kernels
 constexpr int EC_MAX_K = 64;
-constexpr int EC_MAX_N = 8192;   // two int arrays of n live in the CSR kernel's shared memory
+constexpr int EC_MAX_N = 8192;   // (source << 8 | slot) must fit an int; the gather kernel shares the limit
 
 enum { EC_BN_EVAL = 0, EC_BN_TRAIN = 1, EC_AFFINE = 2 };
 enum { EC_ACT_NONE = 0, EC_ACT_LEAKY = 1 };
@@ -276,30 +278,27 @@ ec_bwd_stats_kernel(int cout, int nparts, double edges, int bn_mode, const doubl
   }
 }
 
-// Edges of one cloud sorted by target: off (n+1) run starts, rev (n*k) packed (source << 8 | slot), ascending inside
-// each run.  One CTA per cloud; counting sort in shared memory, runs ordered by rank counting with warp shuffles.
+// Edges sorted by TARGET, per cloud: off (n+1) run starts, rev (n*k) packed (source << 8 | slot), ascending inside each
+// run.  Four small full-grid launches (histogram by integer atomics, per-cloud scan, fill, per-run rank sort); the
+// integer atomics make the order inside a run arbitrary, the rank sort fixes it again.
+__global__ void __launch_bounds__(256)
+ec_hist_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ cnt) {
+  const int cloud = blockIdx.y, total = n * k;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < total) atomicAdd(&cnt[(size_t)cloud * n + ec_clamp(idx[(size_t)cloud * total + e], n)], 1);
+}
+
 __global__ void __launch_bounds__(1024)
-ec_csr_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ off, int *__restrict__ rev_tmp,
-              int *__restrict__ rev) {
-  extern __shared__ int csm[];  // cnt[n] | cursor[n]
+ec_scan_kernel(int n, int total, const int *__restrict__ cnt, int *__restrict__ off, int *__restrict__ cursor) {
   __shared__ int wsum[32];
-  int *cnt = csm, *cursor = csm + n;
   const int cloud = blockIdx.x;
-  const int total = n * k;
-  const int64_t *ib = idx + (size_t)cloud * total;
-  int *offb = off + (size_t)cloud * (n + 1);
-  int *tmpb = rev_tmp + (size_t)cloud * total;
-  int *revb = rev + (size_t)cloud * total;
+  const int *c = cnt + (size_t)cloud * n;
+  int *offb = off + (size_t)cloud * (n + 1), *cur = cursor + (size_t)cloud * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = threadIdx.x; j < n; j += 1024) cnt[j] = 0;
-  __syncthreads();
-  for (int e = threadIdx.x; e < total; e += 1024) atomicAdd(&cnt[ec_clamp(ib[e], n)], 1);
-  __syncthreads();
-  // exclusive scan: each thread owns a contiguous chunk
-  const int chunk = (n + 1023) / 1024;
+  const int chunk = (n + 1023) / 1024;  // each thread owns a contiguous chunk
   const int j0 = threadIdx.x * chunk, j1 = min(n, j0 + chunk);
   int local = 0;
-  for (int j = j0; j < j1; ++j) local += cnt[j];
+  for (int j = j0; j < j1; ++j) local += c[j];
   int incl = local;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -320,41 +319,126 @@ ec_csr_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ o
   __syncthreads();
   int run = incl - local + (warp ? wsum[warp - 1] : 0);
   for (int j = j0; j < j1; ++j) {
-    cursor[j] = run;
+    cur[j] = run;
     offb[j] = run;
-    run += cnt[j];
+    run += c[j];
   }
   if (threadIdx.x == 0) offb[n] = total;
-  __syncthreads();
-  for (int e = threadIdx.x; e < total; e += 1024) {
-    const int j = ec_clamp(ib[e], n);
-    const int i = e / k, t = e - i * k;
-    tmpb[atomicAdd(&cursor[j], 1)] = (i << 8) | t;
-  }
-  __syncthreads();  // the block's global writes are visible to the block
-  for (int j = warp; j < n; j += 32) {
-    const int len = cnt[j], beg = cursor[j] - len;
-    for (int base = 0; base < len; base += 32) {
-      const int mine = base + lane < len ? tmpb[beg + base + lane] : 0x7fffffff;
-      int rank = 0;
-      for (int cb = 0; cb < len; cb += 32) {
-        const int other = cb + lane < len ? tmpb[beg + cb + lane] : 0x7fffffff;
+}
+
+__global__ void __launch_bounds__(256)
+ec_fill_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ cursor, int *__restrict__ rev_tmp) {
+  const int cloud = blockIdx.y, total = n * k;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= total) return;
+  const int j = ec_clamp(idx[(size_t)cloud * total + e], n);
+  const int i = e / k, t = e - i * k;
+  rev_tmp[(size_t)cloud * total + atomicAdd(&cursor[(size_t)cloud * n + j], 1)] = (i << 8) | t;
+}
+
+// one thread per entry: its rank inside its target's run by counting (entries are distinct).  Entries of one run are
+// neighbours in rev_tmp, so a warp walks one or two runs together (broadcast loads); hub targets (in-degree of several
+// hundred in feature space) are spread over many warps instead of serialising one.
+__global__ void __launch_bounds__(256)
+ec_sort_kernel(int n, int k, const int64_t *__restrict__ idx, const int *__restrict__ off,
+               const int *__restrict__ rev_tmp, int *__restrict__ rev, int *__restrict__ tgt) {
+  const int cloud = blockIdx.y, total = n * k;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= total) return;
+  const int *src = rev_tmp + (size_t)cloud * total;
+  const int mine = src[p];
+  const int j = ec_clamp(idx[(size_t)cloud * total + (mine >> 8) * k + (mine & 255)], n);
+  const int *offb = off + (size_t)cloud * (n + 1);
+  const int beg = offb[j], end = offb[j + 1];
+  int rank = 0;
+#pragma unroll 4
+  for (int s2 = beg; s2 < end; ++s2) rank += (src[s2] < mine) ? 1 : 0;
+  rev[(size_t)cloud * total + beg + rank] = mine;
+  tgt[(size_t)cloud * total + beg + rank] = j;
+}
+
+// Segmented sum over the target-sorted edge list in CHUNKS of EC_CHUNK consecutive edges -- uniform work per group
+// whatever the in-degrees are.  thread = (chunk slot, quad of channels).  For every run piece inside the chunk the sums
+//     gd = sum [slot(i,o) == t] dz(i,o)      gv = sum v(i,o)        over the piece's edges (i,t), in list order
+// go to raw[target] when the run STARTS in this chunk, to pbuf[chunk] when it continues from the previous chunk (at most
+// one such piece per chunk, the first).  ec_bwd_finish_kernel adds the pieces of a run in chunk order: deterministic.
+constexpr int EC_CHUNK = 32;
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(EC_THREADS)
+ec_bwd_chunk_kernel(int n, int k, int cout, int nchunks, const float *__restrict__ uv, const int *__restrict__ rev,
+                    const int *__restrict__ tgt, const float *__restrict__ dz, const unsigned char *__restrict__ slot,
+                    float *__restrict__ raw, float *__restrict__ pbuf) {
+  const int cloud = blockIdx.y;
+  const int tpp = cout >> 2;
+  const int groups = EC_THREADS / tpp;
+  const int grp = threadIdx.x / tpp, quad = threadIdx.x - grp * tpp;
+  const int q = blockIdx.x * groups + grp;
+  if (grp >= groups || q >= nchunks) return;
+  const int total = n * k;
+  const int pos0 = q * EC_CHUNK, cnt = min(EC_CHUNK, total - pos0);
+  const int *revb = rev + (size_t)cloud * total + pos0;
+  const int *tgtb = tgt + (size_t)cloud * total + pos0;
+  const size_t pbase = (size_t)cloud * n;
+  int cur = tgtb[0];
+  bool cont = pos0 > 0 && tgtb[-1] == cur;  // the first piece continues a run of the previous chunk
+  float gd[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+  auto flush = [&]() {
+    float *dst = cont ? pbuf + ((size_t)cloud * nchunks + q) * 2 * cout : raw + (pbase + cur) * 2 * cout;
+    *reinterpret_cast<float4 *>(dst + 4 * quad) = make_float4(gd[0], gd[1], gd[2], gd[3]);
+    if (TRAIN) *reinterpret_cast<float4 *>(dst + cout + 4 * quad) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+  };
+  for (int base = 0; base < cnt; base += 4) {
+    int pk[4], tj[4];
+    uchar4 s4[4];
+    float4 v4[4];
 #pragma unroll
-        for (int s = 0; s < 32; ++s) rank += (__shfl_sync(0xffffffffu, other, s) < mine) ? 1 : 0;
+    for (int u = 0; u < 4; ++u) {
+      const int e = min(base + u, cnt - 1);
+      pk[u] = revb[e];
+      tj[u] = tgtb[e];
+      const size_t row = pbase + (pk[u] >> 8);
+      s4[u] = *reinterpret_cast<const uchar4 *>(slot + row * cout + 4 * quad);
+      if (TRAIN) v4[u] = *reinterpret_cast<const float4 *>(uv + row * 2 * cout + cout + 4 * quad);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (base + u < cnt) {
+        if (tj[u] != cur) {
+          flush();
+          cur = tj[u];
+          cont = false;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) gd[c] = gv[c] = 0.f;
+        }
+        const int t = pk[u] & 255;
+        if (s4[u].x == t || s4[u].y == t || s4[u].z == t || s4[u].w == t) {  // ~4 in k quads: dz is read where it lands
+          const float4 d4 = *reinterpret_cast<const float4 *>(dz + (pbase + (pk[u] >> 8)) * cout + 4 * quad);
+          gd[0] += (s4[u].x == t) ? d4.x : 0.f;
+          gd[1] += (s4[u].y == t) ? d4.y : 0.f;
+          gd[2] += (s4[u].z == t) ? d4.z : 0.f;
+          gd[3] += (s4[u].w == t) ? d4.w : 0.f;
+        }
+        if (TRAIN) {
+          gv[0] += v4[u].x;
+          gv[1] += v4[u].y;
+          gv[2] += v4[u].z;
+          gv[3] += v4[u].w;
+        }
       }
-      if (base + lane < len) revb[beg + rank] = mine;
     }
   }
+  flush();
 }
 
 // grad [u | v] (B,N,2Cout); thread = (point slot, quad of channels), the point is the TARGET for grad u and the SOURCE
 // for grad v.
 template <bool TRAIN>
 __global__ void __launch_bounds__(EC_THREADS)
-ec_bwd_edge_kernel(int n, int k, int cout, const float *__restrict__ uv, const int *__restrict__ off,
-                   const int *__restrict__ rev, const float *__restrict__ dz, const unsigned char *__restrict__ slot,
-                   const float *__restrict__ sy, const float *__restrict__ mean, const float *__restrict__ coef,
-                   float *__restrict__ guv) {
+ec_bwd_finish_kernel(int n, int k, int cout, int nchunks, const float *__restrict__ uv, const int *__restrict__ off,
+                     const float *__restrict__ raw, const float *__restrict__ pbuf, const float *__restrict__ dz,
+                     const float *__restrict__ sy, const float *__restrict__ mean, const float *__restrict__ coef,
+                     float *__restrict__ guv) {
   const int cloud = blockIdx.y;
   const int i0 = blockIdx.x * EC_PTS;
   const int npts = min(EC_PTS, n - i0);
@@ -370,28 +454,26 @@ ec_bwd_edge_kernel(int n, int k, int cout, const float *__restrict__ uv, const i
               c2[4] = {c24.x, c24.y, c24.z, c24.w}, mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w};
   const size_t pbase = (size_t)cloud * n;
   const int *offb = off + (size_t)cloud * (n + 1);
-  const int *revb = rev + (size_t)cloud * n * k;
   for (int p = grp; p < npts; p += groups) {
     const int j = i0 + p;
     const int beg = offb[j], end = offb[j + 1];
     float gd[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int s = beg; s < end; ++s) {
-      const int pk = revb[s];
-      const int i = pk >> 8, t = pk & 255;
-      const size_t at = (pbase + i) * cout + 4 * quad;
-      const float4 d4 = *reinterpret_cast<const float4 *>(dz + at);
-      const uchar4 s4 = *reinterpret_cast<const uchar4 *>(slot + at);
-      gd[0] += (s4.x == t) ? d4.x : 0.f;
-      gd[1] += (s4.y == t) ? d4.y : 0.f;
-      gd[2] += (s4.z == t) ? d4.z : 0.f;
-      gd[3] += (s4.w == t) ? d4.w : 0.f;
+    if (end > beg) {
+      const float *r = raw + (pbase + j) * 2 * cout + 4 * quad;
+      const float4 d4 = *reinterpret_cast<const float4 *>(r);
+      gd[0] = d4.x, gd[1] = d4.y, gd[2] = d4.z, gd[3] = d4.w;
       if (TRAIN) {
-        const float4 v4 = *reinterpret_cast<const float4 *>(uv + (pbase + i) * 2 * cout + cout + 4 * quad);
-        gv[0] += v4.x;
-        gv[1] += v4.y;
-        gv[2] += v4.z;
-        gv[3] += v4.w;
+        const float4 v4 = *reinterpret_cast<const float4 *>(r + cout);
+        gv[0] = v4.x, gv[1] = v4.y, gv[2] = v4.z, gv[3] = v4.w;
+      }
+      for (int q = beg / EC_CHUNK + 1; q <= (end - 1) / EC_CHUNK; ++q) {  // pieces in later chunks, in order
+        const float *pp = pbuf + ((size_t)cloud * nchunks + q) * 2 * cout + 4 * quad;
+        const float4 e4 = *reinterpret_cast<const float4 *>(pp);
+        gd[0] += e4.x, gd[1] += e4.y, gd[2] += e4.z, gd[3] += e4.w;
+        if (TRAIN) {
+          const float4 w4 = *reinterpret_cast<const float4 *>(pp + cout);
+          gv[0] += w4.x, gv[1] += w4.y, gv[2] += w4.z, gv[3] += w4.w;
+        }
       }
     }
     const size_t at = (pbase + j) * cout + 4 * quad;
@@ -471,46 +553,58 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   if (!ec_shape_ok(b, n, k, cout)) return PCC_ENOTSUP;
   if (bn_mode < 0 || bn_mode > 2 || act < 0 || act > 1) return PCC_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(ec_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(2 * EC_MAX_N * sizeof(int)));
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
   const dim3 tgrid((n + 31) / 32, (cout + 31) / 32, b);
   const int nparts = (int)(tgrid.x * b);
-  const size_t total = (size_t)b * n * k;
-  const size_t part_bytes = sizeof(double) * 2 * cout * nparts, dz_bytes = sizeof(float) * (size_t)b * n * cout,
-               coef_bytes = sizeof(float) * 4 * cout, off_bytes = sizeof(int) * (size_t)b * (n + 1),
-               rev_bytes = sizeof(int) * total;
+  const int per_cloud = n * k, nchunks = (per_cloud + EC_CHUNK - 1) / EC_CHUNK;
+  const size_t total = (size_t)b * per_cloud;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t part_bytes = up(sizeof(double) * 2 * cout * nparts), dz_bytes = up(sizeof(float) * (size_t)b * n * cout),
+               coef_bytes = up(sizeof(float) * 4 * cout), off_bytes = up(sizeof(int) * (size_t)b * (n + 1)),
+               cnt_bytes = up(sizeof(int) * (size_t)b * n), rev_bytes = up(sizeof(int) * total),
+               raw_bytes = up(sizeof(float) * (size_t)b * n * 2 * cout),
+               pbuf_bytes = up(sizeof(float) * (size_t)b * nchunks * 2 * cout);
   char *ws = nullptr;
-  cudaError_t e = cudaMallocAsync(
-      (void **)&ws, up(part_bytes) + up(dz_bytes) + up(coef_bytes) + up(off_bytes) + 2 * up(rev_bytes), st);
+  cudaError_t e = cudaMallocAsync((void **)&ws, part_bytes + dz_bytes + coef_bytes + off_bytes + 2 * cnt_bytes +
+                                                    3 * rev_bytes + raw_bytes + pbuf_bytes, st);
   if (e != cudaSuccess) return (int)e;
   char *w = ws;
-  double *partials = reinterpret_cast<double *>(w);
-  w += up(part_bytes);
-  float *dz = reinterpret_cast<float *>(w);
-  w += up(dz_bytes);
-  float *coef = reinterpret_cast<float *>(w);
-  w += up(coef_bytes);
-  int *off = reinterpret_cast<int *>(w);
-  w += up(off_bytes);
-  int *rev_tmp = reinterpret_cast<int *>(w);
-  w += up(rev_bytes);
-  int *rev = reinterpret_cast<int *>(w);
+  auto take = [&](size_t bytes) {
+    char *r = w;
+    w += bytes;
+    return r;
+  };
+  double *partials = reinterpret_cast<double *>(take(part_bytes));
+  float *dz = reinterpret_cast<float *>(take(dz_bytes));
+  float *coef = reinterpret_cast<float *>(take(coef_bytes));
+  int *off = reinterpret_cast<int *>(take(off_bytes));
+  int *cnt = reinterpret_cast<int *>(take(cnt_bytes));
+  int *cursor = reinterpret_cast<int *>(take(cnt_bytes));
+  int *rev_tmp = reinterpret_cast<int *>(take(rev_bytes));
+  int *rev = reinterpret_cast<int *>(take(rev_bytes));
+  int *tgt = reinterpret_cast<int *>(take(rev_bytes));
+  float *raw = reinterpret_cast<float *>(take(raw_bytes));
+  float *pbuf = reinterpret_cast<float *>(take(pbuf_bytes));
   ec_bwd_point_kernel<<<tgrid, 256, 0, st>>>(n, cout, grad_out, exty, mean, invstd, gamma, beta, act, slope, dz,
                                              partials, nparts);
   ec_bwd_stats_kernel<<<cout, 128, 0, st>>>(cout, nparts, (double)b * n * k, bn_mode, partials, gamma, invstd,
                                             grad_gamma, grad_beta, coef);
-  ec_csr_kernel<<<b, 1024, 2 * n * sizeof(int), st>>>(n, k, idx, off, rev_tmp, rev);
-  const dim3 grid((n + EC_PTS - 1) / EC_PTS, b);
-  if (bn_mode == EC_BN_TRAIN)
-    ec_bwd_edge_kernel<true><<<grid, EC_THREADS, 0, st>>>(n, k, cout, uv, off, rev, dz, slot, sy, mean, coef, grad_uv);
-  else
-    ec_bwd_edge_kernel<false><<<grid, EC_THREADS, 0, st>>>(n, k, cout, uv, off, rev, dz, slot, sy, mean, coef, grad_uv);
+  const dim3 egrid((per_cloud + 255) / 256, b);
+  cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)b * n, st);
+  ec_hist_kernel<<<egrid, 256, 0, st>>>(n, k, idx, cnt);
+  ec_scan_kernel<<<b, 1024, 0, st>>>(n, per_cloud, cnt, off, cursor);
+  ec_fill_kernel<<<egrid, 256, 0, st>>>(n, k, idx, cursor, rev_tmp);
+  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, idx, off, rev_tmp, rev, tgt);
+  const int groups = EC_THREADS / (cout >> 2);
+  const dim3 cgrid((nchunks + groups - 1) / groups, b), grid((n + EC_PTS - 1) / EC_PTS, b);
+  if (bn_mode == EC_BN_TRAIN) {
+    ec_bwd_chunk_kernel<true><<<cgrid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, rev, tgt, dz, slot, raw, pbuf);
+    ec_bwd_finish_kernel<true><<<grid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, off, raw, pbuf, dz, sy, mean, coef,
+                                                            grad_uv);
+  } else {
+    ec_bwd_chunk_kernel<false><<<cgrid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, rev, tgt, dz, slot, raw, pbuf);
+    ec_bwd_finish_kernel<false><<<grid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, off, raw, pbuf, dz, sy, mean,
+                                                             coef, grad_uv);
+  }
   cudaFreeAsync(ws, st);
-  return finish_launch(4);
+  return finish_launch(8);
 }

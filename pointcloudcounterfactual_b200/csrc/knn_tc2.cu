@@ -11,14 +11,21 @@
 //   warps 2+ epilogue, one thread per query (tcgen05.ld of its accumulator row), two sweeps over the key tiles:
 //     sweep 1  score = |x_j|^2 - 2 x_i.x_j; one minimum per group of 16 or 32 keys (at most 64 groups).  tau = k-th smallest group minimum
 //              (bitonic network in registers) bounds the k-th smallest score from above.
-//     sweep 2  the accumulators are recomputed (the tensor pipe is idle otherwise); keys with score <= tau + 2 eps are
+//     sweep 2  the accumulators are recomputed (the tensor pipe is idle otherwise); keys whose score can be <= tau are
 //              candidates.  The warp compacts its (query, key) pairs and spreads them evenly over its lanes; each
 //              pair's EXACT distance is evaluated at once from the key tile that is still resident in shared memory
 //              (the tile that fed the MMA) and the resident query tile.
 //     finally  the ~1.5 k candidates of a query are ranked by counting, one query per warp step and one candidate per
 //              lane; rank r < k is output slot r.
-// The candidate set provably contains the exact top-k (see knn_tc.cu); a query whose candidates overflow the list
-// (massive exact ties) is redone by exact brute force.
+// The candidate set provably contains the exact top-k: the TF32 score s~ of pair (i,j) is off by at most
+//     eps_ij = 2^-7.5 |x_i| |x_j| + 4e-5 (|x_i|^2 + |x_j|^2)
+// (truncation of both operands, Cauchy-Schwarz, 41 % slack; second term: fp32 rounding of norms / distances), a bound
+// PER KEY: sweep 1 takes the k-th smallest group minimum of the UPPER bounds s~ + eps_ij (at least k keys are truly
+// below it), sweep 2 keeps the keys whose LOWER bound s~ - eps_ij does not exceed it.  With one bound per cloud
+// (max norm) instead, heavy-tailed features -- a dense core plus a few far outliers, what chained EdgeConv layers
+// produce -- put hundreds of core points inside the band of every core query (measured: C=128, N=2048 kNN 1.1 ms on
+// iid features, 7.3 ms on the third DGCNN layer's input).  A query whose candidates overflow the list (massive exact
+// ties) is redone by exact brute force.
 #include "tc_ptx.cuh"
 
 namespace pcc {
@@ -38,8 +45,59 @@ struct T2 {
   static constexpr int CHUNKS = R / 32;                // 32-column TMEM loads per tile
   static constexpr int TMEM_COLS = HALVES * 2 * R;
   static constexpr size_t SMEM =
-      A_BYTES + 2 * B_BYTES + 2 * R * 4 + (size_t)QUERIES * W * 4 + (size_t)NEPI * (PCAP + 64) * 4 + 256;
+      A_BYTES + 2 * B_BYTES + 2 * 3 * R * 4 + (size_t)QUERIES * W * 4 + (size_t)NEPI * (PCAP + 64) * 4 + 256;
 };
+
+constexpr float T2_C1 = 0.0055242717f;  // 2^-7.5
+constexpr float T2_C2 = 4e-5f;
+
+// transpose (B,C,N) -> (B,N,C), squared norms, and per key the three factors of the score bounds:
+// bounds[(cloud*npad + j)/R tile][3][R] = { n_j (1+c2), n_j (1-c2), c1 sqrt(n_j) }, padding keys {inf, inf, 0}
+template <int R>
+__global__ void __launch_bounds__(256)
+knn_tc2_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict__ xT, float *__restrict__ norms,
+                    float *__restrict__ bounds, int npad) {
+  __shared__ float t[64][33];
+  const size_t cloud = blockIdx.y;
+  const int n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float *xb = x + cloud * (size_t)c * n;
+  float *xo = xT + cloud * (size_t)n * c;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // thread (tx = channel lane, ty) accumulates points ty, ty+8, ty+16, ty+24
+  for (int c0 = 0; c0 < c; c0 += 64) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {  // rows = channels c0 + ty + 8r, columns = points n0 + tx: 8 loads in flight
+      const int ch = c0 + ty + 8 * r;
+      t[ty + 8 * r][tx] = (ch < c && n0 + tx < n) ? xb[(size_t)ch * n + n0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {  // rows = points, columns = channels
+      const int p = ty + 8 * r;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float v = t[tx + 32 * h][p];
+        if (n0 + p < n && c0 + tx + 32 * h < c) xo[(size_t)(n0 + p) * c + c0 + tx + 32 * h] = v;
+        acc[r] = fmaf(v, v, acc[r]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float s = warp_sum(acc[r]);
+    const int p = n0 + ty + 8 * r;
+    if (tx == 0 && p < npad) {
+      const bool real = p < n;
+      const float INF = __int_as_float(0x7f800000);
+      norms[cloud * (size_t)npad + p] = real ? s : INF;
+      float *bt = bounds + (cloud * (size_t)npad + (size_t)(p / R) * R) * 3 + (p % R);
+      bt[0] = real ? s * (1.f + T2_C2) : INF;
+      bt[R] = real ? s * (1.f - T2_C2) : INF;
+      bt[2 * R] = real ? T2_C1 * sqrtf(s) : 0.f;
+    }
+  }
+}
 
 struct T2Ctl {
   uint64_t full[2], empty[2], tfull[2], tempty[2], afull;
@@ -83,14 +141,14 @@ template <int KB, int HALVES, int R>
 __global__ void __launch_bounds__(T2<KB, HALVES, R>::THREADS, 1)
 knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int n, int k,
                int npad, const float *__restrict__ xT, const float *__restrict__ norms,
-               const unsigned int *__restrict__ nmax_bits, int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
+               const float *__restrict__ bounds, int64_t *__restrict__ idx_out, float *__restrict__ dist_out) {
   using Cfg = T2<KB, HALVES, R>;
   constexpr int C = Cfg::C, Q = Cfg::QUERIES, CAP = Cfg::CAP, CHUNKS = Cfg::CHUNKS, W = Cfg::W;
   extern __shared__ __align__(1024) unsigned char smem[];  // the 128B swizzle atoms need 1024-byte alignment
   unsigned char *sA = smem;                                        // [KB][Q][128 B]
   unsigned char *sB = sA + Cfg::A_BYTES;                           // [2][KB][R][128 B]
-  float *rn = reinterpret_cast<float *>(sB + 2 * Cfg::B_BYTES);    // [2][R] squared norms of the staged keys
-  uint32_t *recs = reinterpret_cast<uint32_t *>(rn + 2 * R);       // [Q][W] per-query records
+  float *rn = reinterpret_cast<float *>(sB + 2 * Cfg::B_BYTES);    // [2][3][R] per staged key: n(1+c2), n(1-c2), c1 sqrt(n)
+  uint32_t *recs = reinterpret_cast<uint32_t *>(rn + 2 * 3 * R);   // [Q][W] per-query records
   uint32_t *plist = recs + Q * W;                                  // [NEPI][PCAP]
   uint32_t *scratch = plist + Cfg::NEPI * Cfg::PCAP;               // [NEPI][64], 16-byte aligned
   T2Ctl *ctl = reinterpret_cast<T2Ctl *>(scratch + Cfg::NEPI * 64);
@@ -127,10 +185,10 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int s = i & 1, par = (i >> 1) & 1;
         const int r0 = (i % ntile) * R;
         mbar_wait(&ctl->empty[s], par ^ 1);
-        mbar_expect_tx(&ctl->full[s], Cfg::B_BYTES + R * 4);
+        mbar_expect_tx(&ctl->full[s], Cfg::B_BYTES + 3 * R * 4);
         unsigned char *st = sB + s * Cfg::B_BYTES;
         for (int kb = 0; kb < KB; ++kb) tma_load_3d(st + kb * (R * 128), &tmap_r, &ctl->full[s], kb * 32, r0, cloud);
-        bulk_load_1d(rn + s * R, norms + (size_t)cloud * npad + r0, R * 4, &ctl->full[s]);
+        bulk_load_1d(rn + s * 3 * R, bounds + ((size_t)cloud * npad + r0) * 3, 3 * R * 4, &ctl->full[s]);
       }
     }
   } else if (warp == 1) {
@@ -168,10 +226,9 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const int q = q0 + e;
     const float INF = __int_as_float(0x7f800000);
     const float nq = (q < n) ? norms[(size_t)cloud * npad + q] : 0.f;
-    const float nmax = __uint_as_float(nmax_bits[cloud]);
-    // |score + |x_q|^2 - exact| <= eps: TF32 truncation of both operands (2^-9 relative on every product), x2 for the
-    // -2 x.y term, Cauchy-Schwarz; 2^-7.5 leaves 41 % slack, the second term covers fp32 rounding of norms / distances
-    const float eps = 0.0055242717f * sqrtf(nq * nmax) + 4e-5f * (nq + nmax);
+    // eps_ij = cq * (c1 sqrt(n_j)) + c2 n_j + c2 |x_q|^2: the key-side factors come precomputed (knn_tc2_prep_kernel),
+    // the query side is cq = |x_q| and the constant c2 |x_q|^2, which moves into the threshold
+    const float cq = sqrtf(nq), c2nq = T2_C2 * nq;
     float thr = INF;
     int cnt = 0;
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 2 * R);
@@ -216,7 +273,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_wait(&ctl->tfull[s], par);
       fence_after();
       const uint32_t taddr = tlane + (uint32_t)(s * R);
-      const float *rns = rn + s * R;
+      const float *rns = rn + s * 3 * R;   // [0] upper norms, [R] lower norms, [2R] c1 sqrt(n)
       if (!second) {
         // ---- sweep 1: group minima ----
 #pragma unroll
@@ -228,8 +285,12 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 w = *reinterpret_cast<const float4 *>(rns + ch * 32 + 4 * g);
-            const float z0 = fmaf(-2.f, __uint_as_float(v[4 * g + 0]), w.x), z1 = fmaf(-2.f, __uint_as_float(v[4 * g + 1]), w.y),
-                        z2 = fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z), z3 = fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w);
+            const float4 sn = *reinterpret_cast<const float4 *>(rns + 2 * R + ch * 32 + 4 * g);
+            // upper bound of the true score: s~ + eps_ij (without the per-query constant c2 |x_q|^2)
+            const float z0 = fmaf(cq, sn.x, fmaf(-2.f, __uint_as_float(v[4 * g + 0]), w.x)),
+                        z1 = fmaf(cq, sn.y, fmaf(-2.f, __uint_as_float(v[4 * g + 1]), w.y)),
+                        z2 = fmaf(cq, sn.z, fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z)),
+                        z3 = fmaf(cq, sn.w, fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w));
             if (g < 4)
               mlo = fminf(fminf(z0, z1), fminf(fminf(z2, z3), mlo));
             else
@@ -267,8 +328,10 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           float tau = -INF;
 #pragma unroll
           for (int u = 0; u < 32; ++u) tau = (u < k) ? fmaxf(tau, a[u]) : tau;
-          // strict compare below: inflate by a few ulps so that score == tau + 2 eps is still a candidate
-          thr = (tau + 2.f * eps) * 1.000001f + 1e-30f;
+          // lower bound <= upper bound of the k-th: both sides dropped c2 |x_q|^2, hence twice that.  Strict compare
+          // below: move the threshold up by a few ulps so that equality is still a candidate
+          thr = tau + 2.f * c2nq;
+          thr = thr * (thr > 0.f ? 1.000001f : 0.999999f) + 1e-30f;
           mbar_wait(&ctl->afull, 0);  // the query tile is read by the exact re-rank
         }
       } else {
@@ -283,9 +346,13 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           unsigned int mk = 0;
 #pragma unroll
           for (int g = 7; g >= 0; --g) {
-            const float4 w = *reinterpret_cast<const float4 *>(rns + ch * 32 + 4 * g);
-            const float z3 = fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w) - thr, z2 = fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z) - thr,
-                        z1 = fmaf(-2.f, __uint_as_float(v[4 * g + 1]), w.y) - thr, z0 = fmaf(-2.f, __uint_as_float(v[4 * g + 0]), w.x) - thr;
+            const float4 w = *reinterpret_cast<const float4 *>(rns + R + ch * 32 + 4 * g);
+            const float4 sn = *reinterpret_cast<const float4 *>(rns + 2 * R + ch * 32 + 4 * g);
+            // lower bound of the true score, minus the threshold
+            const float z3 = fmaf(-cq, sn.w, fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w)) - thr,
+                        z2 = fmaf(-cq, sn.z, fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z)) - thr,
+                        z1 = fmaf(-cq, sn.y, fmaf(-2.f, __uint_as_float(v[4 * g + 1]), w.y)) - thr,
+                        z0 = fmaf(-cq, sn.x, fmaf(-2.f, __uint_as_float(v[4 * g + 0]), w.x)) - thr;
             mk = __funnelshift_l(__float_as_uint(z3), mk, 1);
             mk = __funnelshift_l(__float_as_uint(z2), mk, 1);
             mk = __funnelshift_l(__float_as_uint(z1), mk, 1);
@@ -312,9 +379,10 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             rix[p] = vi;
           }
           cnt = k;
-          // the k-th best exact distance so far bounds the final one: a key of the final top-k has
-          // score <= d - |x_q|^2 + eps <= rd[k-1] - |x_q|^2 + eps, usually far below tau + 2 eps
-          thr = fminf(thr, (rd[k - 1] - nq + eps) * (rd[k - 1] - nq + eps > 0.f ? 1.000001f : 0.999999f) + 1e-30f);
+          // the k-th best exact distance so far bounds the final one: a key of the final top-k has a true score
+          // <= rd[k-1] - |x_q|^2, so its lower bound (which dropped c2 |x_q|^2) is <= rd[k-1] - |x_q|^2 + c2 |x_q|^2
+          const float tk = rd[k - 1] - nq + c2nq;
+          thr = fminf(thr, tk * (tk > 0.f ? 1.000001f : 0.999999f) + 1e-30f);
         }
         __syncwarp();
         // ---- (query, key) pairs of the whole warp, compacted so that the exact re-rank is spread evenly over the
@@ -468,7 +536,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
 // ---- host ----------------------------------------------------------------------------------------------------
 template <int KB, int HALVES, int R>
-static int launch_tc2(int b, int n, int k, int npad, const float *xT, const float *norms, const unsigned int *nmax,
+static int launch_tc2(int b, int c, int n, int k, int npad, const float *x, float *xT, float *norms, float *bounds,
                       int64_t *idx, float *dist, cudaStream_t st) {
   using Cfg = T2<KB, HALVES, R>;
   static bool attr = false;
@@ -478,12 +546,13 @@ static int launch_tc2(int b, int n, int k, int npad, const float *xT, const floa
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
+  knn_tc2_prep_kernel<R><<<dim3((npad + 31) / 32, b), 256, 0, st>>>(c, n, x, xT, norms, bounds, npad);
   CUtensorMap mq, mr;
   int rc = tc_make_map(&mq, xT, b, n, Cfg::C, Cfg::QUERIES);
   if (rc == 0) rc = tc_make_map(&mr, xT, b, n, Cfg::C, R);
   if (rc != 0) return rc;
   dim3 grid((n + Cfg::QUERIES - 1) / Cfg::QUERIES, b);
-  knn_tc2_kernel<KB, HALVES, R><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mq, mr, n, k, npad, xT, norms, nmax, idx, dist);
+  knn_tc2_kernel<KB, HALVES, R><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mq, mr, n, k, npad, xT, norms, bounds, idx, dist);
   return (int)cudaGetLastError();
 }
 
@@ -495,18 +564,15 @@ int knn_tc2_launch(int b, int c, int n, int k, const float *x, int64_t *idx, flo
   const int npad = (n + r - 1) / r * r;
   float *ws = nullptr;
   const size_t nxt = (size_t)b * n * c, nn = (size_t)b * npad;
-  cudaError_t e = cudaMallocAsync((void **)&ws, sizeof(float) * (nxt + nn) + sizeof(unsigned int) * b, st);
+  cudaError_t e = cudaMallocAsync((void **)&ws, sizeof(float) * (nxt + 4 * nn), st);
   if (e != cudaSuccess) return (int)e;
-  float *xT = ws, *norms = ws + nxt;
-  unsigned int *nmax = reinterpret_cast<unsigned int *>(norms + nn);
-  cudaMemsetAsync(nmax, 0, sizeof(unsigned int) * b, st);
-  knn_tc_prep_kernel<<<dim3((npad + 31) / 32, b), 256, 0, st>>>(c, n, x, xT, norms, npad, nmax);
+  float *xT = ws, *norms = ws + nxt, *bounds = norms + nn;
   int rc;
   switch (c / 32) {
-    case 1: rc = launch_tc2<1, 2, 128>(b, n, k, npad, xT, norms, nmax, idx, dist, st); break;
-    case 2: rc = launch_tc2<2, 2, 128>(b, n, k, npad, xT, norms, nmax, idx, dist, st); break;
-    case 3: rc = launch_tc2<3, 1, 64>(b, n, k, npad, xT, norms, nmax, idx, dist, st); break;
-    default: rc = launch_tc2<4, 1, 64>(b, n, k, npad, xT, norms, nmax, idx, dist, st); break;
+    case 1: rc = launch_tc2<1, 2, 128>(b, c, n, k, npad, x, xT, norms, bounds, idx, dist, st); break;
+    case 2: rc = launch_tc2<2, 2, 128>(b, c, n, k, npad, x, xT, norms, bounds, idx, dist, st); break;
+    case 3: rc = launch_tc2<3, 1, 64>(b, c, n, k, npad, x, xT, norms, bounds, idx, dist, st); break;
+    default: rc = launch_tc2<4, 1, 64>(b, c, n, k, npad, x, xT, norms, bounds, idx, dist, st); break;
   }
   cudaFreeAsync(ws, st);
   if (rc == 0) g_launches.fetch_add(2, std::memory_order_relaxed);

@@ -33,18 +33,26 @@ BN_EVAL, BN_TRAIN, AFFINE = 0, 1, 2
 ACT_NONE, ACT_LEAKY = 0, 1
 
 
-class _EdgeConvAggregate(Function):
-    """uv (B,N,2*Cout) = [W1 x | (W2-W1) x] point-major, idx (B,N,k) int64 -> out (B,Cout,N)."""
+class _EdgeConvMax(Function):
+    """x (B,C,N) channels-first, weight (Cout,2C), idx (B,N,k) int64 -> out (B,Cout,N).
+
+    The two GEMMs around the edge kernels are plain library calls (torch.bmm -> cuBLAS fp32), written out here instead of
+    left to autograd so that the weight gradient is a BATCHED product over clouds (K = N per problem) rather than one
+    GEMM with K = B*N and two output tiles, and so that no transposed copy of x or of the gradient is made."""
 
     @staticmethod
-    def forward(ctx: Any, uv: torch.Tensor, idx: torch.Tensor, gamma: torch.Tensor | None, beta: torch.Tensor | None,
-                running_mean: torch.Tensor | None, running_var: torch.Tensor | None, bn_mode: int, momentum: float,
-                eps: float, act: int, slope: float) -> torch.Tensor:
-        b, n, c2 = uv.shape
-        cout = c2 // 2
+    def forward(ctx: Any, x: torch.Tensor, weight: torch.Tensor, idx: torch.Tensor, gamma: torch.Tensor | None,
+                beta: torch.Tensor | None, running_mean: torch.Tensor | None, running_var: torch.Tensor | None,
+                bn_mode: int, momentum: float, eps: float, act: int, slope: float) -> torch.Tensor:
+        b, c, n = x.shape
+        cout = weight.shape[0]
         k = idx.shape[2]
-        dev = uv.device
+        dev = x.device
+        w1 = weight[:, :c]
+        ws = torch.cat([w1, weight[:, c:] - w1], dim=0)            # (2Cout, C): [W1 ; W2 - W1]
         with torch.cuda.device(dev):
+            # uv[b,i,:] = [W1 x_i | (W2-W1) x_i], point-major rows: x^T (B,N,C) is a strided view, no copy
+            uv = torch.bmm(x.transpose(1, 2), ws.t().unsqueeze(0).expand(b, -1, -1))
             out = torch.empty((b, cout, n), dtype=torch.float32, device=dev)
             exty = torch.empty((b, n, cout), dtype=torch.float32, device=dev)
             sy = torch.empty((b, n, cout), dtype=torch.float32, device=dev) if bn_mode == BN_TRAIN else None
@@ -55,16 +63,17 @@ class _EdgeConvAggregate(Function):
                 b, n, k, cout, L.ptr(uv), L.ptr(idx), L.ptr(gamma), L.ptr(beta), L.ptr(running_mean),
                 L.ptr(running_var), bn_mode, momentum, eps, act, slope, L.ptr(out), L.ptr(exty), L.ptr(sy),
                 L.ptr(slot), L.ptr(mean), L.ptr(invstd), L.stream_of(uv)), "edgeconv_forward")
-        ctx.save_for_backward(uv, idx, gamma, beta, mean, invstd, exty, sy, slot)
+        ctx.save_for_backward(x, ws, uv, idx, gamma, beta, mean, invstd, exty, sy, slot)
         ctx.cfg = (bn_mode, act, slope)
         return out
 
     @staticmethod
     def backward(ctx: Any, grad_out: torch.Tensor):
-        uv, idx, gamma, beta, mean, invstd, exty, sy, slot = ctx.saved_tensors
+        x, ws, uv, idx, gamma, beta, mean, invstd, exty, sy, slot = ctx.saved_tensors
         bn_mode, act, slope = ctx.cfg
         b, n, c2 = uv.shape
         cout = c2 // 2
+        c = x.shape[1]
         g = grad_out.contiguous()
         dev = uv.device
         with torch.cuda.device(dev):
@@ -75,7 +84,14 @@ class _EdgeConvAggregate(Function):
                 b, n, idx.shape[2], cout, L.ptr(uv), L.ptr(idx), L.ptr(gamma), L.ptr(beta), L.ptr(mean), L.ptr(invstd),
                 bn_mode, act, slope, L.ptr(exty), L.ptr(sy), L.ptr(slot), L.ptr(g), L.ptr(guv), L.ptr(ggamma),
                 L.ptr(gbeta), L.stream_of(uv)), "edgeconv_backward")
-        return guv, None, ggamma, gbeta, None, None, None, None, None, None, None
+            gx = gw = None
+            if ctx.needs_input_grad[0]:   # (B,C,N) = ws^T (C,2Cout) . guv^T (2Cout,N)
+                gx = torch.bmm(ws.t().unsqueeze(0).expand(b, -1, -1), guv.transpose(1, 2))
+            if ctx.needs_input_grad[1]:   # per cloud (2Cout,N) . (N,C), then summed over the clouds
+                gws = torch.bmm(guv.transpose(1, 2), x.transpose(1, 2)).sum(0)
+                gw = torch.cat([gws[:cout] - gws[cout:], gws[cout:]], dim=1)
+        return (gx, gw, None, ggamma if ctx.needs_input_grad[3] else None, gbeta if ctx.needs_input_grad[4] else None,
+                None, None, None, None, None, None, None)
 
 
 def _act_code(act: nn.Module | None) -> tuple[int, float] | None:
@@ -105,15 +121,10 @@ def edge_conv_max(x: torch.Tensor, indices: torch.Tensor, weight: torch.Tensor, 
     (running stats updated in place), BN_EVAL running statistics, AFFINE no normalisation (``bn_bias`` = conv bias).
     """
     L.require_cuda(x, contiguous=False)
-    b, c, n = x.shape
     cout = weight.shape[0]
-    w = weight.reshape(cout, 2 * c)
-    w1 = w[:, :c]
-    ws = torch.cat([w1, w[:, c:] - w1], dim=0)                # (2Cout, C): [W1 ; W2 - W1]
-    uv = torch.matmul(x.transpose(1, 2), ws.t()).contiguous()  # (B,N,2Cout): library GEMM, autograd handles its backward
     act, slope = (ACT_NONE, 0.0) if negative_slope is None else (ACT_LEAKY, float(negative_slope))
-    return _EdgeConvAggregate.apply(uv, indices.contiguous(), bn_weight, bn_bias, running_mean, running_var, bn_mode,
-                                    float(momentum), float(eps), act, slope)
+    return _EdgeConvMax.apply(x, weight.reshape(cout, 2 * x.shape[1]), indices.contiguous(), bn_weight, bn_bias,
+                              running_mean, running_var, bn_mode, float(momentum), float(eps), act, slope)
 
 
 def fused_edge_conv(layer: nn.Module, x: torch.Tensor, indices: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
