@@ -129,8 +129,8 @@ int pcc_graph_gather_grad(int b, int c, int n, int k, const int64_t *idx, int mo
  *              `momentum` (unbiased variance), mean/invstd (cout) are returned for the backward
  *   bn_mode 0: running statistics (eval);   bn_mode 2: no normalisation, out = act(gamma*y + beta) (gamma/beta may be NULL)
  *   act 0: identity, 1: leaky ReLU with `slope` >= 0 (0 = ReLU)
- * out (b,cout,n) channels-first.  exty, sy (b,n,cout) fp32 and slot (b,n,cout) uint8 are saved for the backward
- * (sy only written in bn_mode 1).  PCC_ENOTSUP: k > 64, n > 8192, cout % 4 != 0 or cout > 1024. */
+ * out (b,cout,n) channels-first.  exty, sy (b,n,cout) fp32 and slot (b,ceil(cout/8),n,8) uint8 (private layout) are saved
+ * for the backward (sy only written in bn_mode 1).  PCC_ENOTSUP: k > 64, n > 8192, cout % 4 != 0 or cout > 1024. */
 int pcc_edgeconv_forward(int b, int n, int k, int cout, const float *uv, const int64_t *idx, const float *gamma,
                          const float *beta, float *running_mean, float *running_var, int bn_mode, float momentum,
                          float eps, int act, float slope, float *out, float *exty, float *sy, unsigned char *slot,

@@ -38,6 +38,13 @@ enum { EC_ACT_NONE = 0, EC_ACT_LEAKY = 1 };
 
 __device__ __forceinline__ int ec_clamp(long long j, int n) { return (int)min(max(j, 0LL), (long long)n - 1); }
 
+// slot (uint8) and dz (fp32) are SLICE-major: [cloud][slice of 8 channels][point][8], so that a CTA that owns one slice
+// of one cloud (the shared-memory staged kernels below) reads them as one contiguous block.  Offset of channel ch:
+__host__ __device__ __forceinline__ int ec_nslice(int cout) { return (cout + 7) >> 3; }
+__device__ __forceinline__ size_t ec_sl(int cloud, int n, int cout, int i, int ch) {
+  return (((size_t)cloud * ec_nslice(cout) + (ch >> 3)) * n + i) * 8 + (ch & 7);
+}
+
 // ---- forward: one pass over the edges -------------------------------------------------------------------------
 // thread = (point slot, quad of 4 channels); a CTA walks EC_PTS points of one cloud.
 template <bool STATS>
@@ -58,45 +65,48 @@ ec_reduce_kernel(int n, int k, int cout, const float *__restrict__ uv, const int
   for (int e = threadIdx.x; e < npts * k; e += EC_THREADS) sidx[e] = ec_clamp(ib[e], n);
   __syncthreads();
   const float *uvb = uv + (size_t)cloud * n * 2 * cout;
-  bool wantmax[4];
-  {
-    const float4 g4 = (active && gamma) ? reinterpret_cast<const float4 *>(gamma)[quad] : make_float4(1.f, 1.f, 1.f, 1.f);
-    wantmax[0] = !(g4.x < 0.f);
-    wantmax[1] = !(g4.y < 0.f);
-    wantmax[2] = !(g4.z < 0.f);
-    wantmax[3] = !(g4.w < 0.f);
+  // channels with a negative gamma need the MINIMUM over the neighbours: track max(sg * y) with sg = -1 there.  sg * y
+  // = fma(u, sg, sg * v) is exact, so the result equals the direct min / max bit for bit.
+  float sg[4] = {1.f, 1.f, 1.f, 1.f};
+  if (active && gamma) {
+    const float4 g4 = reinterpret_cast<const float4 *>(gamma)[quad];
+    sg[0] = g4.x < 0.f ? -1.f : 1.f;
+    sg[1] = g4.y < 0.f ? -1.f : 1.f;
+    sg[2] = g4.z < 0.f ? -1.f : 1.f;
+    sg[3] = g4.w < 0.f ? -1.f : 1.f;
   }
   double a1[4] = {0., 0., 0., 0.}, a2[4] = {0., 0., 0., 0.};
   if (active) {
     for (int p = grp; p < npts; p += groups) {
       const int i = i0 + p;
       const float4 v4 = *reinterpret_cast<const float4 *>(uvb + (size_t)i * 2 * cout + cout + 4 * quad);
-      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, ext[4] = {0.f, 0.f, 0.f, 0.f};
+      const float v[4] = {v4.x * sg[0], v4.y * sg[1], v4.z * sg[2], v4.w * sg[3]};
+      const float NINF = __int_as_float(0xff800000);
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, ext[4] = {NINF, NINF, NINF, NINF};
       int slot[4] = {0, 0, 0, 0};
       const int *nb = sidx + p * k;
 #pragma unroll 5
       for (int t = 0; t < k; ++t) {
         const float4 u4 = *reinterpret_cast<const float4 *>(uvb + (size_t)nb[t] * 2 * cout + 4 * quad);
-        const float y[4] = {u4.x + v[0], u4.y + v[1], u4.z + v[2], u4.w + v[3]};
+        const float y[4] = {fmaf(u4.x, sg[0], v[0]), fmaf(u4.y, sg[1], v[1]), fmaf(u4.z, sg[2], v[2]),
+                            fmaf(u4.w, sg[3], v[3])};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (STATS) {
             s1[c] += y[c];
             s2[c] = fmaf(y[c], y[c], s2[c]);
           }
-          const bool better = wantmax[c] ? (y[c] > ext[c]) : (y[c] < ext[c]);  // strict: first slot wins a tie
-          if (t == 0 || better) {
-            ext[c] = y[c];
-            slot[c] = t;
-          }
+          slot[c] = y[c] > ext[c] ? t : slot[c];  // strict: the first slot wins a tie
+          ext[c] = fmaxf(ext[c], y[c]);
         }
       }
       const size_t o = ((size_t)cloud * n + i) * cout + 4 * quad;
-      *reinterpret_cast<float4 *>(exty + o) = make_float4(ext[0], ext[1], ext[2], ext[3]);
-      *reinterpret_cast<uchar4 *>(slot_out + o) =
+      *reinterpret_cast<float4 *>(exty + o) = make_float4(ext[0] * sg[0], ext[1] * sg[1], ext[2] * sg[2], ext[3] * sg[3]);
+      *reinterpret_cast<uchar4 *>(slot_out + ec_sl(cloud, n, cout, i, 4 * quad)) =
           make_uchar4((unsigned char)slot[0], (unsigned char)slot[1], (unsigned char)slot[2], (unsigned char)slot[3]);
       if (STATS) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s1[c] *= sg[c];
         *reinterpret_cast<float4 *>(sy_out + o) = make_float4(s1[0], s1[1], s1[2], s1[3]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -120,6 +130,116 @@ ec_reduce_kernel(int n, int k, int cout, const float *__restrict__ uv, const int
       for (int g = 0; g < groups; ++g) acc += red[s][(g * tpp + (ch >> 2)) * 4 + (ch & 3)];
       const int part = blockIdx.y * gridDim.x + blockIdx.x;
       partials[((size_t)s * cout + ch) * nparts + part] = acc;  // [2][cout][nparts]
+    }
+  }
+}
+
+// Same pass with the gather served from SHARED memory: a CTA owns one slice of 8 channels of one cloud, stages that
+// slice of u for all n points (32 B per point) and walks all points.  The gathered bytes (k rows per point) then come
+// from shared memory instead of L2; L2 only delivers the slice once, the indices and the own v.  thread = (point slot,
+// quad of the slice).  Used while the slice fits (n <= EC_STAGE_MAX_N).
+constexpr int EC_STAGE_MAX_N = 2560;
+constexpr int EC_STHREADS = 512;            // threads of the staged kernels
+constexpr int EC_SPTS = EC_STHREADS / 2;    // points (chunks) per iteration
+
+template <bool STATS>
+__global__ void __launch_bounds__(EC_STHREADS, 2)
+ec_reduce_staged_kernel(int n, int k, int cout, const float *__restrict__ uv, const int64_t *__restrict__ idx,
+                        const float *__restrict__ gamma, float *__restrict__ exty, float *__restrict__ sy_out,
+                        unsigned char *__restrict__ slot_out, double *__restrict__ partials, int nparts) {
+  extern __shared__ __align__(16) float4 rows[];  // [n][2]; reused for the statistics reduction at the end
+  const int slice = blockIdx.x, cloud = blockIdx.y;
+  const int nquad = cout >> 2;
+  const float *uvb = uv + (size_t)cloud * n * 2 * cout;
+  const int ps = threadIdx.x >> 1, qq = threadIdx.x & 1;
+  const int quad = 2 * slice + qq;
+  const bool active = quad < nquad;
+  // channels with a negative gamma need the MINIMUM over the neighbours: the slice is staged as sg * u, sg = -1 there, and
+  // the maximum of sg * y = sg * u + sg * v is tracked (sign flips are exact: same bits as the direct min / max)
+  float sg[4] = {1.f, 1.f, 1.f, 1.f};
+  if (active && gamma) {
+    const float4 g4 = reinterpret_cast<const float4 *>(gamma)[quad];
+    sg[0] = g4.x < 0.f ? -1.f : 1.f;
+    sg[1] = g4.y < 0.f ? -1.f : 1.f;
+    sg[2] = g4.z < 0.f ? -1.f : 1.f;
+    sg[3] = g4.w < 0.f ? -1.f : 1.f;
+  }
+  for (int e = threadIdx.x; e < 2 * n; e += EC_STHREADS) {  // e & 1 == qq: this thread stages its own quad
+    float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) u4 = *reinterpret_cast<const float4 *>(uvb + (size_t)(e >> 1) * 2 * cout + 4 * quad);
+    rows[e] = make_float4(u4.x * sg[0], u4.y * sg[1], u4.z * sg[2], u4.w * sg[3]);
+  }
+  double a1[4] = {0., 0., 0., 0.}, a2[4] = {0., 0., 0., 0.};
+  const int64_t *ib = idx + (size_t)cloud * n * k;
+  // neighbour lists of the points of one iteration: read coalesced, kept as 16-bit indices (n <= EC_STAGE_MAX_N)
+  unsigned short *sidx = reinterpret_cast<unsigned short *>(rows + max(2 * n, 2 * EC_STHREADS * 4 * 8 / 16));
+  const float NINF = __int_as_float(0xff800000);
+  for (int it0 = 0; it0 < n; it0 += EC_SPTS) {
+    __syncthreads();
+    const int cnt = min(EC_SPTS, n - it0) * k;
+    for (int e = threadIdx.x; e < cnt; e += EC_STHREADS)
+      sidx[e] = (unsigned short)ec_clamp(ib[(size_t)it0 * k + e], n);
+    __syncthreads();
+    const int i = it0 + ps;
+    if (i >= n || !active) continue;
+    const float4 v4 = *reinterpret_cast<const float4 *>(uvb + (size_t)i * 2 * cout + cout + 4 * quad);
+    const float v[4] = {v4.x * sg[0], v4.y * sg[1], v4.z * sg[2], v4.w * sg[3]};
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, ext[4] = {NINF, NINF, NINF, NINF};
+    int slot[4] = {0, 0, 0, 0};
+    const unsigned short *nb = sidx + ps * k;
+    for (int t0 = 0; t0 < k; t0 += 4) {
+      float4 u8[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) u8[u] = rows[2 * (int)nb[min(t0 + u, k - 1)] + qq];  // 4 rows in flight
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u;
+        if (t < k) {
+          const float y[4] = {u8[u].x + v[0], u8[u].y + v[1], u8[u].z + v[2], u8[u].w + v[3]};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (STATS) {
+              s1[c] += y[c];
+              s2[c] = fmaf(y[c], y[c], s2[c]);
+            }
+            slot[c] = y[c] > ext[c] ? t : slot[c];  // strict: the first slot wins a tie
+            ext[c] = fmaxf(ext[c], y[c]);
+          }
+        }
+      }
+    }
+    const size_t o = ((size_t)cloud * n + i) * cout + 4 * quad;
+    *reinterpret_cast<float4 *>(exty + o) = make_float4(ext[0] * sg[0], ext[1] * sg[1], ext[2] * sg[2], ext[3] * sg[3]);
+    *reinterpret_cast<uchar4 *>(slot_out + ec_sl(cloud, n, cout, i, 4 * quad)) =
+        make_uchar4((unsigned char)slot[0], (unsigned char)slot[1], (unsigned char)slot[2], (unsigned char)slot[3]);
+    if (STATS) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s1[c] *= sg[c];
+      *reinterpret_cast<float4 *>(sy_out + o) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        a1[c] += (double)s1[c];
+        a2[c] += (double)s2[c];
+      }
+    }
+  }
+  if (STATS) {
+    __syncthreads();  // every gather is done: the slice buffer becomes the reduction scratch (32 KiB are always allocated)
+    double *red = reinterpret_cast<double *>(rows);  // [2][EC_STHREADS][4]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      red[threadIdx.x * 4 + c] = a1[c];
+      red[EC_STHREADS * 4 + threadIdx.x * 4 + c] = a2[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {  // (statistic, channel of the slice): fixed order over the point slots -> deterministic
+      const int st = threadIdx.x >> 3, ch8 = threadIdx.x & 7;
+      const int ch = 8 * slice + ch8;
+      if (ch < cout) {
+        double acc = 0.;
+        for (int g = 0; g < EC_SPTS; ++g) acc += red[st * EC_STHREADS * 4 + (2 * g + (ch8 >> 2)) * 4 + (ch8 & 3)];
+        partials[((size_t)st * cout + ch) * nparts + cloud] = acc;  // [2][cout][nparts = b]
+      }
     }
   }
 }
@@ -235,7 +355,7 @@ ec_bwd_point_kernel(int n, int cout, const float *__restrict__ gout, const float
         const float e = exty[at];
         const float z = fmaf(a, e, sh);
         const float d = tile[tx][r] * ((act == EC_ACT_LEAKY && !(z > 0.f)) ? slope : 1.f);
-        dz[at] = d;
+        dz[ec_sl(cloud, n, cout, i, o)] = d;
         sb += (double)d;
         sg += (double)(d * ((e - mu) * is));
       }
@@ -278,8 +398,8 @@ ec_bwd_stats_kernel(int cout, int nparts, double edges, int bn_mode, const doubl
   }
 }
 
-// Edges sorted by TARGET, per cloud: off (n+1) run starts, rev (n*k) packed (source << 8 | slot), ascending inside each
-// run.  Four small full-grid launches (histogram by integer atomics, per-cloud scan, fill, per-run rank sort); the
+// Edges sorted by TARGET, per cloud: off (n+1) run starts, rev (n*k, per-cloud stride padded to whole chunks) packed
+// (target << 19 | source << 6 | slot) -- 13 + 13 + 6 bits, n <= 8192, k <= 64 -- ascending inside each run.  Four small full-grid launches (histogram by integer atomics, per-cloud scan, fill, per-run rank sort); the
 // integer atomics make the order inside a run arbitrary, the rank sort fixes it again.
 __global__ void __launch_bounds__(256)
 ec_hist_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ cnt) {
@@ -327,34 +447,35 @@ ec_scan_kernel(int n, int total, const int *__restrict__ cnt, int *__restrict__ 
 }
 
 __global__ void __launch_bounds__(256)
-ec_fill_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ cursor, int *__restrict__ rev_tmp) {
+ec_fill_kernel(int n, int k, int stride, const int64_t *__restrict__ idx, int *__restrict__ cursor,
+               unsigned int *__restrict__ rev_tmp) {
   const int cloud = blockIdx.y, total = n * k;
   const int e = blockIdx.x * 256 + threadIdx.x;
   if (e >= total) return;
   const int j = ec_clamp(idx[(size_t)cloud * total + e], n);
   const int i = e / k, t = e - i * k;
-  rev_tmp[(size_t)cloud * total + atomicAdd(&cursor[(size_t)cloud * n + j], 1)] = (i << 8) | t;
+  rev_tmp[(size_t)cloud * stride + atomicAdd(&cursor[(size_t)cloud * n + j], 1)] =
+      ((unsigned int)j << 19) | ((unsigned int)i << 6) | (unsigned int)t;
 }
 
 // one thread per entry: its rank inside its target's run by counting (entries are distinct).  Entries of one run are
 // neighbours in rev_tmp, so a warp walks one or two runs together (broadcast loads); hub targets (in-degree of several
 // hundred in feature space) are spread over many warps instead of serialising one.
 __global__ void __launch_bounds__(256)
-ec_sort_kernel(int n, int k, const int64_t *__restrict__ idx, const int *__restrict__ off,
-               const int *__restrict__ rev_tmp, int *__restrict__ rev, int *__restrict__ tgt) {
+ec_sort_kernel(int n, int k, int stride, const int *__restrict__ off, const unsigned int *__restrict__ rev_tmp,
+               unsigned int *__restrict__ rev) {
   const int cloud = blockIdx.y, total = n * k;
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= total) return;
-  const int *src = rev_tmp + (size_t)cloud * total;
-  const int mine = src[p];
-  const int j = ec_clamp(idx[(size_t)cloud * total + (mine >> 8) * k + (mine & 255)], n);
+  const unsigned int *src = rev_tmp + (size_t)cloud * stride;
+  const unsigned int mine = src[p];
+  const int j = (int)(mine >> 19);
   const int *offb = off + (size_t)cloud * (n + 1);
   const int beg = offb[j], end = offb[j + 1];
   int rank = 0;
 #pragma unroll 4
   for (int s2 = beg; s2 < end; ++s2) rank += (src[s2] < mine) ? 1 : 0;
-  rev[(size_t)cloud * total + beg + rank] = mine;
-  tgt[(size_t)cloud * total + beg + rank] = j;
+  rev[(size_t)cloud * stride + beg + rank] = mine;
 }
 
 // Segmented sum over the target-sorted edge list in CHUNKS of EC_CHUNK consecutive edges -- uniform work per group
@@ -366,9 +487,9 @@ constexpr int EC_CHUNK = 32;
 
 template <bool TRAIN>
 __global__ void __launch_bounds__(EC_THREADS)
-ec_bwd_chunk_kernel(int n, int k, int cout, int nchunks, const float *__restrict__ uv, const int *__restrict__ rev,
-                    const int *__restrict__ tgt, const float *__restrict__ dz, const unsigned char *__restrict__ slot,
-                    float *__restrict__ raw, float *__restrict__ pbuf) {
+ec_bwd_chunk_kernel(int n, int k, int cout, int nchunks, const float *__restrict__ uv,
+                    const unsigned int *__restrict__ rev, const float *__restrict__ dz,
+                    const unsigned char *__restrict__ slot, float *__restrict__ raw, float *__restrict__ pbuf) {
   const int cloud = blockIdx.y;
   const int tpp = cout >> 2;
   const int groups = EC_THREADS / tpp;
@@ -377,11 +498,10 @@ ec_bwd_chunk_kernel(int n, int k, int cout, int nchunks, const float *__restrict
   if (grp >= groups || q >= nchunks) return;
   const int total = n * k;
   const int pos0 = q * EC_CHUNK, cnt = min(EC_CHUNK, total - pos0);
-  const int *revb = rev + (size_t)cloud * total + pos0;
-  const int *tgtb = tgt + (size_t)cloud * total + pos0;
+  const unsigned int *revb = rev + (size_t)cloud * nchunks * EC_CHUNK + pos0;
   const size_t pbase = (size_t)cloud * n;
-  int cur = tgtb[0];
-  bool cont = pos0 > 0 && tgtb[-1] == cur;  // the first piece continues a run of the previous chunk
+  int cur = (int)(revb[0] >> 19);
+  bool cont = pos0 > 0 && (int)(revb[-1] >> 19) == cur;  // the first piece continues a run of the previous chunk
   float gd[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
   auto flush = [&]() {
     float *dst = cont ? pbuf + ((size_t)cloud * nchunks + q) * 2 * cout : raw + (pbase + cur) * 2 * cout;
@@ -395,10 +515,11 @@ ec_bwd_chunk_kernel(int n, int k, int cout, int nchunks, const float *__restrict
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int e = min(base + u, cnt - 1);
-      pk[u] = revb[e];
-      tj[u] = tgtb[e];
+      const unsigned int w = revb[e];
+      tj[u] = (int)(w >> 19);
+      pk[u] = (int)(((w >> 6) & 8191u) << 8 | (w & 63u));  // source << 8 | slot
       const size_t row = pbase + (pk[u] >> 8);
-      s4[u] = *reinterpret_cast<const uchar4 *>(slot + row * cout + 4 * quad);
+      s4[u] = *reinterpret_cast<const uchar4 *>(slot + ec_sl(cloud, n, cout, pk[u] >> 8, 4 * quad));
       if (TRAIN) v4[u] = *reinterpret_cast<const float4 *>(uv + row * 2 * cout + cout + 4 * quad);
     }
 #pragma unroll
@@ -413,7 +534,7 @@ ec_bwd_chunk_kernel(int n, int k, int cout, int nchunks, const float *__restrict
         }
         const int t = pk[u] & 255;
         if (s4[u].x == t || s4[u].y == t || s4[u].z == t || s4[u].w == t) {  // ~4 in k quads: dz is read where it lands
-          const float4 d4 = *reinterpret_cast<const float4 *>(dz + (pbase + (pk[u] >> 8)) * cout + 4 * quad);
+          const float4 d4 = *reinterpret_cast<const float4 *>(dz + ec_sl(cloud, n, cout, pk[u] >> 8, 4 * quad));
           gd[0] += (s4[u].x == t) ? d4.x : 0.f;
           gd[1] += (s4[u].y == t) ? d4.y : 0.f;
           gd[2] += (s4[u].z == t) ? d4.z : 0.f;
@@ -429,6 +550,90 @@ ec_bwd_chunk_kernel(int n, int k, int cout, int nchunks, const float *__restrict
     }
   }
   flush();
+}
+
+// The same segmented sum with the per-edge operands served from SHARED memory: a CTA owns one slice of 8 channels of one
+// cloud, stages that slice of v (32 B per point) and of slot (8 B per point) and walks all chunks of the cloud's edge
+// list.  thread = (chunk slot, quad of the slice).
+template <bool TRAIN>
+__global__ void __launch_bounds__(EC_STHREADS)
+ec_bwd_chunk_staged_kernel(int n, int k, int cout, int nchunks, const float *__restrict__ uv,
+                           const unsigned int *__restrict__ rev, const float *__restrict__ dz,
+                           const unsigned char *__restrict__ slot, float *__restrict__ raw, float *__restrict__ pbuf) {
+  extern __shared__ __align__(16) float4 rows[];  // dz [n][2] float4 | TRAIN: v [n][2] float4 | slot [n][2] uchar4
+  const int slice = blockIdx.x, cloud = blockIdx.y;
+  const int nquad = cout >> 2;
+  const float4 *sdz = rows;
+  const float4 *sv = rows + 2 * n;
+  uchar4 *sslot = reinterpret_cast<uchar4 *>(rows + (TRAIN ? 4 * n : 2 * n));
+  const float *uvb = uv + (size_t)cloud * n * 2 * cout;
+  const uchar4 *gslot = reinterpret_cast<const uchar4 *>(slot + ec_sl(cloud, n, cout, 0, 8 * slice));
+  const float4 *gdz = reinterpret_cast<const float4 *>(dz + ec_sl(cloud, n, cout, 0, 8 * slice));
+  for (int e = threadIdx.x; e < 2 * n; e += EC_STHREADS) {
+    const bool ok = 2 * slice + (e & 1) < nquad;
+    rows[e] = ok ? gdz[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (TRAIN)
+      rows[2 * n + e] = ok ? *reinterpret_cast<const float4 *>(uvb + (size_t)(e >> 1) * 2 * cout + cout +
+                                                               4 * (2 * slice + (e & 1)))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    sslot[e] = ok ? gslot[e] : make_uchar4(255, 255, 255, 255);
+  }
+  __syncthreads();
+  const int cs = threadIdx.x >> 1, qq = threadIdx.x & 1;
+  const int quad = 2 * slice + qq;
+  if (quad >= nquad) return;
+  const int total = n * k;
+  const size_t pbase = (size_t)cloud * n;
+  for (int q = cs; q < nchunks; q += EC_SPTS) {
+    const int pos0 = q * EC_CHUNK, cnt = min(EC_CHUNK, total - pos0);
+    const unsigned int *revb = rev + (size_t)cloud * nchunks * EC_CHUNK + pos0;  // 128-byte aligned chunk
+    // the chunk's 32 entries: eight 16-byte loads issued together (the padding past the list is allocated)
+    unsigned int w[EC_CHUNK];
+#pragma unroll
+    for (int u = 0; u < EC_CHUNK / 4; ++u) {
+      const uint4 t4 = reinterpret_cast<const uint4 *>(revb)[u];
+      w[4 * u] = t4.x, w[4 * u + 1] = t4.y, w[4 * u + 2] = t4.z, w[4 * u + 3] = t4.w;
+    }
+    int cur = (int)(w[0] >> 19);
+    bool cont = pos0 > 0 && (int)(revb[-1] >> 19) == cur;  // the first piece continues a run of the previous chunk
+    float gd[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
+    auto flush = [&]() {
+      float *dst = cont ? pbuf + ((size_t)cloud * nchunks + q) * 2 * cout : raw + (pbase + cur) * 2 * cout;
+      *reinterpret_cast<float4 *>(dst + 4 * quad) = make_float4(gd[0], gd[1], gd[2], gd[3]);
+      if (TRAIN) *reinterpret_cast<float4 *>(dst + cout + 4 * quad) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    };
+#pragma unroll
+    for (int u = 0; u < EC_CHUNK; ++u) {
+      if (u < cnt) {
+        const int tj = (int)(w[u] >> 19);
+        if (tj != cur) {
+          flush();
+          cur = tj;
+          cont = false;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) gd[c] = gv[c] = 0.f;
+        }
+        const int i = (int)((w[u] >> 6) & 8191u);
+        const unsigned int t = w[u] & 63u;
+        const uchar4 s4 = sslot[2 * i + qq];
+        if (s4.x == t || s4.y == t || s4.z == t || s4.w == t) {  // ~4 in k quads: dz is read where it lands
+          const float4 d4 = sdz[2 * i + qq];
+          gd[0] += (s4.x == t) ? d4.x : 0.f;
+          gd[1] += (s4.y == t) ? d4.y : 0.f;
+          gd[2] += (s4.z == t) ? d4.z : 0.f;
+          gd[3] += (s4.w == t) ? d4.w : 0.f;
+        }
+        if (TRAIN) {
+          const float4 v4 = sv[2 * i + qq];
+          gv[0] += v4.x;
+          gv[1] += v4.y;
+          gv[2] += v4.z;
+          gv[3] += v4.w;
+        }
+      }
+    }
+    flush();
+  }
 }
 
 // grad [u | v] (B,N,2Cout); thread = (point slot, quad of channels), the point is the TARGET for grad u and the SOURCE
@@ -477,7 +682,7 @@ ec_bwd_finish_kernel(int n, int k, int cout, int nchunks, const float *__restric
       }
     }
     const size_t at = (pbase + j) * cout + 4 * quad;
-    const float4 dj4 = *reinterpret_cast<const float4 *>(dz + at);
+    const float4 dj4 = *reinterpret_cast<const float4 *>(dz + ec_sl(cloud, n, cout, j, 4 * quad));
     const float dj[4] = {dj4.x, dj4.y, dj4.z, dj4.w};
     float gu[4], gvv[4];
     if (TRAIN) {
@@ -524,15 +729,34 @@ pcc_edgeconv_forward(int b, int n, int k, int cout, const float *uv, const int64
   if (bn_mode < 0 || bn_mode > 2 || act < 0 || act > 1 || (act == EC_ACT_LEAKY && slope < 0.f)) return PCC_EINVAL;
   if (bn_mode == EC_BN_EVAL && (!running_mean || !running_var)) return PCC_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const dim3 grid((n + EC_PTS - 1) / EC_PTS, b);
-  const int nparts = (int)(grid.x * grid.y);
+  const bool staged = n <= EC_STAGE_MAX_N;
+  const dim3 grid((n + EC_PTS - 1) / EC_PTS, b), sgrid(ec_nslice(cout), b);
+  const int nparts = staged ? b : (int)(grid.x * grid.y);
+  const size_t stage_smem = (size_t)max(n * 32, 2 * EC_STHREADS * 4 * 8) + (size_t)EC_SPTS * k * 2;
+  if (staged) {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e1 = cudaFuncSetAttribute(ec_reduce_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            EC_STAGE_MAX_N * 32 + EC_SPTS * EC_MAX_K * 2);
+      cudaError_t e2 = cudaFuncSetAttribute(ec_reduce_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            EC_STAGE_MAX_N * 32 + EC_SPTS * EC_MAX_K * 2);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
+      attr = true;
+    }
+  }
   char *ws = nullptr;
   const size_t part_bytes = sizeof(double) * 2 * cout * nparts, aff_bytes = sizeof(float) * 2 * cout;
   cudaError_t e = cudaMallocAsync((void **)&ws, part_bytes + aff_bytes, st);
   if (e != cudaSuccess) return (int)e;
   double *partials = reinterpret_cast<double *>(ws);
   float *scale = reinterpret_cast<float *>(ws + part_bytes), *shift = scale + cout;
-  if (bn_mode == EC_BN_TRAIN)
+  if (staged && bn_mode == EC_BN_TRAIN)
+    ec_reduce_staged_kernel<true><<<sgrid, EC_STHREADS, stage_smem, st>>>(n, k, cout, uv, idx, gamma, exty, sy, slot,
+                                                                        partials, nparts);
+  else if (staged)
+    ec_reduce_staged_kernel<false><<<sgrid, EC_STHREADS, stage_smem, st>>>(n, k, cout, uv, idx, gamma, exty, sy, slot,
+                                                                         partials, nparts);
+  else if (bn_mode == EC_BN_TRAIN)
     ec_reduce_kernel<true><<<grid, EC_THREADS, 0, st>>>(n, k, cout, uv, idx, gamma, exty, sy, slot, partials, nparts);
   else
     ec_reduce_kernel<false><<<grid, EC_THREADS, 0, st>>>(n, k, cout, uv, idx, gamma, exty, sy, slot, partials, nparts);
@@ -558,14 +782,14 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   const int per_cloud = n * k, nchunks = (per_cloud + EC_CHUNK - 1) / EC_CHUNK;
   const size_t total = (size_t)b * per_cloud;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t part_bytes = up(sizeof(double) * 2 * cout * nparts), dz_bytes = up(sizeof(float) * (size_t)b * n * cout),
+  const size_t part_bytes = up(sizeof(double) * 2 * cout * nparts), dz_bytes = up(sizeof(float) * (size_t)b * ec_nslice(cout) * n * 8),
                coef_bytes = up(sizeof(float) * 4 * cout), off_bytes = up(sizeof(int) * (size_t)b * (n + 1)),
-               cnt_bytes = up(sizeof(int) * (size_t)b * n), rev_bytes = up(sizeof(int) * total),
+               cnt_bytes = up(sizeof(int) * (size_t)b * n), rev_bytes = up(sizeof(int) * (size_t)b * nchunks * EC_CHUNK),
                raw_bytes = up(sizeof(float) * (size_t)b * n * 2 * cout),
                pbuf_bytes = up(sizeof(float) * (size_t)b * nchunks * 2 * cout);
   char *ws = nullptr;
   cudaError_t e = cudaMallocAsync((void **)&ws, part_bytes + dz_bytes + coef_bytes + off_bytes + 2 * cnt_bytes +
-                                                    3 * rev_bytes + raw_bytes + pbuf_bytes, st);
+                                                    2 * rev_bytes + raw_bytes + pbuf_bytes, st);
   if (e != cudaSuccess) return (int)e;
   char *w = ws;
   auto take = [&](size_t bytes) {
@@ -579,9 +803,9 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   int *off = reinterpret_cast<int *>(take(off_bytes));
   int *cnt = reinterpret_cast<int *>(take(cnt_bytes));
   int *cursor = reinterpret_cast<int *>(take(cnt_bytes));
-  int *rev_tmp = reinterpret_cast<int *>(take(rev_bytes));
-  int *rev = reinterpret_cast<int *>(take(rev_bytes));
-  int *tgt = reinterpret_cast<int *>(take(rev_bytes));
+  unsigned int *rev_tmp = reinterpret_cast<unsigned int *>(take(rev_bytes));
+  unsigned int *rev = reinterpret_cast<unsigned int *>(take(rev_bytes));
+  const int estride = nchunks * EC_CHUNK;  // per-cloud stride of the edge lists
   float *raw = reinterpret_cast<float *>(take(raw_bytes));
   float *pbuf = reinterpret_cast<float *>(take(pbuf_bytes));
   ec_bwd_point_kernel<<<tgrid, 256, 0, st>>>(n, cout, grad_out, exty, mean, invstd, gamma, beta, act, slope, dz,
@@ -592,16 +816,42 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)b * n, st);
   ec_hist_kernel<<<egrid, 256, 0, st>>>(n, k, idx, cnt);
   ec_scan_kernel<<<b, 1024, 0, st>>>(n, per_cloud, cnt, off, cursor);
-  ec_fill_kernel<<<egrid, 256, 0, st>>>(n, k, idx, cursor, rev_tmp);
-  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, idx, off, rev_tmp, rev, tgt);
+  ec_fill_kernel<<<egrid, 256, 0, st>>>(n, k, estride, idx, cursor, rev_tmp);
+  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, estride, off, rev_tmp, rev);
   const int groups = EC_THREADS / (cout >> 2);
   const dim3 cgrid((nchunks + groups - 1) / groups, b), grid((n + EC_PTS - 1) / EC_PTS, b);
-  if (bn_mode == EC_BN_TRAIN) {
-    ec_bwd_chunk_kernel<true><<<cgrid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, rev, tgt, dz, slot, raw, pbuf);
+  const bool staged = n <= EC_STAGE_MAX_N;
+  const dim3 sgrid(ec_nslice(cout), b);
+  if (staged) {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e1 = cudaFuncSetAttribute(ec_bwd_chunk_staged_kernel<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, EC_STAGE_MAX_N * 72);
+      cudaError_t e2 = cudaFuncSetAttribute(ec_bwd_chunk_staged_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, EC_STAGE_MAX_N * 40);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaFreeAsync(ws, st);
+        return (int)(e1 != cudaSuccess ? e1 : e2);
+      }
+      attr = true;
+    }
+  }
+  if (staged && bn_mode == EC_BN_TRAIN) {
+    ec_bwd_chunk_staged_kernel<true><<<sgrid, EC_STHREADS, (size_t)n * 72, st>>>(n, k, cout, nchunks, uv, rev, dz, slot,
+                                                                                raw, pbuf);
+    ec_bwd_finish_kernel<true><<<grid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, off, raw, pbuf, dz, sy, mean, coef,
+                                                            grad_uv);
+  } else if (staged) {
+    ec_bwd_chunk_staged_kernel<false><<<sgrid, EC_STHREADS, (size_t)n * 40, st>>>(n, k, cout, nchunks, uv, rev, dz, slot,
+                                                                                raw, pbuf);
+    ec_bwd_finish_kernel<false><<<grid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, off, raw, pbuf, dz, sy, mean,
+                                                             coef, grad_uv);
+  } else if (bn_mode == EC_BN_TRAIN) {
+    ec_bwd_chunk_kernel<true><<<cgrid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, rev, dz, slot, raw, pbuf);
     ec_bwd_finish_kernel<true><<<grid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, off, raw, pbuf, dz, sy, mean, coef,
                                                             grad_uv);
   } else {
-    ec_bwd_chunk_kernel<false><<<cgrid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, rev, tgt, dz, slot, raw, pbuf);
+    ec_bwd_chunk_kernel<false><<<cgrid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, rev, dz, slot, raw, pbuf);
     ec_bwd_finish_kernel<false><<<grid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, off, raw, pbuf, dz, sy, mean,
                                                              coef, grad_uv);
   }

@@ -90,8 +90,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   unsigned char *stage_base = smem;                                               // TC_STAGES * 48 KiB, 1024-aligned
   float *candd = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES);    // [TC_CAP][128]
   unsigned short *cand = reinterpret_cast<unsigned short *>(candd + TC_CAP * TC_M);  // [TC_CAP][128], n <= 65535
-  float *rn = reinterpret_cast<float *>(cand + TC_CAP * TC_M);                    // [2][TC_N]
-  TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(rn + 2 * TC_N);
+  float *rn = reinterpret_cast<float *>(cand + TC_CAP * TC_M);                    // [2][TC_N] n_j (1 +- c2), [2][TC_N] +-c1 sqrt(n_j)
+  float *rs = rn + 2 * TC_N;
+  TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(rn + 4 * TC_N);
   int *qcnt = ctl->qcnt;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,10 +172,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const float INF = __int_as_float(0x7f800000);
     const float *nb = norms + (size_t)cloud * n;
     const float nq = (q < n) ? nb[q] : 0.f;
-    const float nmax = __uint_as_float(nmax_bits[cloud]);
-    // |score + |x_q|^2 - exact| <= eps: TF32 truncation of both operands (2^-9 relative on every product), x2 for the
-    // -2 x.y term, Cauchy-Schwarz; 2^-7.5 leaves 41 % slack, the second term covers fp32 rounding of norms / distances
-    const float eps = 0.0055242717f * sqrtf(nq * nmax) + 4e-5f * (nq + nmax);
+    // |score + |x_q|^2 - exact| <= eps_ij = c1 |x_q| |x_j| + c2 (|x_q|^2 + |x_j|^2): TF32 truncation of both operands (2^-9
+    // relative on every product), x2 for the -2 x.y term, Cauchy-Schwarz; c1 = 2^-7.5 leaves 41 % slack, the c2 terms
+    // cover fp32 rounding of norms / distances.  The bound is PER KEY (see knn_tc2.cu): pass 0 ranks upper bounds, pass
+    // 1 tests lower bounds; the per-query constant c2 |x_q|^2 moves into the threshold.
+    constexpr float C1 = 0.0055242717f, C2 = 4e-5f;
+    const float cq = sqrtf(nq), c2nq = C2 * nq;
     float L[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) L[i] = INF;
@@ -187,7 +190,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const int r0 = (it % ntile) * TC_N;
       // norms of this reference tile (+inf beyond the cloud => never selected)
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous user of rn[a] is done (two iterations back)
-      for (int j = e; j < TC_N; j += 128) rn[a * TC_N + j] = (r0 + j < n) ? nb[r0 + j] : INF;
+      for (int j = e; j < TC_N; j += 128) {
+        const bool real = r0 + j < n;
+        const float nj = real ? nb[r0 + j] : INF;
+        rn[a * TC_N + j] = real ? nj * (pass == 0 ? 1.f + C2 : 1.f - C2) : INF;
+        rs[a * TC_N + j] = real ? (pass == 0 ? C1 : -C1) * sqrtf(nj) : 0.f;
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&ctl->tfull[a], (it >> 1) & 1);
       fence_after();
@@ -197,13 +205,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         float v[32];
         tmem_ld32(taddr + (uint32_t)(ch * 32), v);
         const float4 *rn4 = reinterpret_cast<const float4 *>(rn + a * TC_N + ch * 32);
+        const float4 *rs4 = reinterpret_cast<const float4 *>(rs + a * TC_N + ch * 32);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const float4 w = rn4[g];
-          v[4 * g + 0] = fmaf(-2.f, v[4 * g + 0], w.x);
-          v[4 * g + 1] = fmaf(-2.f, v[4 * g + 1], w.y);
-          v[4 * g + 2] = fmaf(-2.f, v[4 * g + 2], w.z);
-          v[4 * g + 3] = fmaf(-2.f, v[4 * g + 3], w.w);
+          const float4 w = rn4[g], sn = rs4[g];
+          v[4 * g + 0] = fmaf(cq, sn.x, fmaf(-2.f, v[4 * g + 0], w.x));
+          v[4 * g + 1] = fmaf(cq, sn.y, fmaf(-2.f, v[4 * g + 1], w.y));
+          v[4 * g + 2] = fmaf(cq, sn.z, fmaf(-2.f, v[4 * g + 2], w.z));
+          v[4 * g + 3] = fmaf(cq, sn.w, fmaf(-2.f, v[4 * g + 3], w.w));
         }
         if (pass == 0) {
 #pragma unroll
@@ -236,7 +245,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         float t = -INF;
 #pragma unroll
         for (int i = 0; i < K; ++i) t = (i < k) ? fmaxf(t, L[i]) : t;  // k-th smallest group minimum
-        thr = t + 2.f * eps;
+        thr = t + 2.f * c2nq;
+        thr += 1e-6f * fabsf(thr) + 1e-30f;  // a few ulps up: equality stays a candidate
       }
     }
 
@@ -404,7 +414,7 @@ int tc_make_map(CUtensorMap *m, const float *xT, int b, int n, int c, int box_ro
 template <int K>
 static int launch_tc_k(const CUtensorMap &mq, const CUtensorMap &mr, int b, int c, int n, int k, const float *xT,
                        const float *norms, const unsigned int *nmax, int64_t *idx, float *dist, cudaStream_t st) {
-  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_CAP * TC_M * 6 + 2 * TC_N * 4 + sizeof(TcSmemCtl) + 64;
+  const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_CAP * TC_M * 6 + 4 * TC_N * 4 + sizeof(TcSmemCtl) + 64;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -56,7 +56,7 @@ class _EdgeConvMax(Function):
             out = torch.empty((b, cout, n), dtype=torch.float32, device=dev)
             exty = torch.empty((b, n, cout), dtype=torch.float32, device=dev)
             sy = torch.empty((b, n, cout), dtype=torch.float32, device=dev) if bn_mode == BN_TRAIN else None
-            slot = torch.empty((b, n, cout), dtype=torch.uint8, device=dev)
+            slot = torch.empty((b, (cout + 7) // 8, n, 8), dtype=torch.uint8, device=dev)  # slice-major, see edgeconv.cu
             mean = torch.empty((cout,), dtype=torch.float32, device=dev)
             invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
             L.check(L.load().pcc_edgeconv_forward(

@@ -56,6 +56,8 @@ def test_fused_layer_matches_reference_fixture(cuda, name):
     (1, 64, 1000, 25, 128, 0.2, "train"),
     (1, 128, 257, 25, 256, 0.2, "train"),    # last DGCNN layer (64 threads per point)
     (2, 16, 130, 7, 20, 0.0, "train"),       # ReLU, Cout = 20 (5 threads per point, idle tail threads)
+    (1, 8, 2600, 5, 12, 0.2, "train"),       # N above the shared-memory staging limit: L2-gather kernels, Cout % 8 != 0
+    (1, 8, 2600, 5, 12, 0.2, "eval"),
     (2, 32, 200, 9, 32, 0.2, "eval"),
     (2, 32, 200, 9, 32, None, "affine"),
 ])
