@@ -423,11 +423,17 @@ def run_b200(args) -> None:
                     "sequence (cudnn TF32 conv on the (B,2C,N,k) tensor) on top of the fused gather"}
         ms, gr = graph_or_eager(lambda: encoder_fb(True), reps=10)
         ms_t = ev_time(lambda: encoder_fb(False), 3)
+        tf32_was = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True  # what the reference's cudnn convolution uses by default
+        ms_tf32 = graph_or_eager(lambda: encoder_fb(True), reps=10)[0]
+        torch.backends.cuda.matmul.allow_tf32 = tf32_was
         sub["dgcnn_edgeconv_stack_fwd_bwd"] = {
             "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr, "torch_composition_ms": ms_t,
-            "speedup_vs_torch_composition": ms_t / ms,
+            "speedup_vs_torch_composition": ms_t / ms, "ms_with_tf32_point_gemms": ms_tf32,
             "note": "the four chained EdgeConv layers of DGCNN (3->64->64->128->256, N=2048, k=25, dynamic kNN per layer), "
-                    "forward and backward; torch composition = same kNN and gather kernels, reference op sequence after"}
+                    "forward and backward; torch composition = same kNN and gather kernels, reference op sequence after "
+                    "(its cudnn convolution runs TF32 by default; the fused path's point GEMMs are fp32 unless "
+                    "torch.backends.cuda.matmul.allow_tf32 is set -- ms_with_tf32_point_gemms)"}
 
         def ae_step():
             encoder_fb(True)  # encoder: per layer kNN graph (k=25) + fused EdgeConv layer, forward and backward
