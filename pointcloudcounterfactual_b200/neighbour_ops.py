@@ -32,14 +32,24 @@ def knn_indices(x: torch.Tensor, k: int, return_dist: bool = False):
     return (idx, dist) if return_dist else idx
 
 
-def index_k_neighbours(pcs: list[np.ndarray], k: int) -> np.ndarray:
-    """Dataset-side kNN (:16-24; the reference builds a KDTree per cloud on the CPU): list of (N,3) arrays ->
-    (len, N, k) indices, computed on the GPU."""
-    out = []
-    for pc in pcs:
-        x = torch.as_tensor(np.ascontiguousarray(pc), dtype=torch.float32).cuda().t().unsqueeze(0)
-        out.append(knn_indices(x, k)[0].cpu().numpy().reshape(-1, k))
-    return np.stack(out)
+def index_k_neighbours(pcs, k: int, chunk: int = 2048) -> np.ndarray:
+    """Dataset-side kNN (:16-24; the reference builds a scikit-learn KDTree per cloud on the CPU): sequence of (N,3)
+    arrays -> (len, N, k) int64 indices, self first, ascending by (distance, index).  Clouds of equal size are batched
+    (`chunk` clouds per launch); the caller stores them as int16 under ``index_{k}`` in the h5 file exactly as
+    ``src/data/modelnet.py:150-156`` does (``.astype(np.short)``)."""
+    pcs = [np.ascontiguousarray(pc, dtype=np.float32) for pc in pcs]
+    out: list[np.ndarray | None] = [None] * len(pcs)
+    by_size: dict[tuple[int, ...], list[int]] = {}
+    for i, pc in enumerate(pcs):
+        by_size.setdefault(pc.shape, []).append(i)
+    for ids in by_size.values():
+        for s0 in range(0, len(ids), chunk):
+            sel = ids[s0:s0 + chunk]
+            x = torch.from_numpy(np.stack([pcs[i] for i in sel])).cuda().transpose(1, 2).contiguous()  # (B,3,N)
+            idx = knn_indices(x, k).cpu().numpy()
+            for row, i in enumerate(sel):
+                out[i] = idx[row].reshape(-1, k)
+    return np.stack(out) if out else np.zeros((0, 0, k), dtype=np.int64)
 
 
 def square_distance(t1: torch.Tensor, t2: torch.Tensor) -> torch.Tensor | SquareDistance:

@@ -39,6 +39,24 @@ def test_feature_knn_tensor_core_path_edge_cases(cuda):
         assert np.array_equal(idx.cpu().numpy(), eidx) and np.array_equal(dist.cpu().numpy(), edist)
 
 
+@pytest.mark.parametrize("b,c,n,k", [(2, 64, 1024, 20), (1, 128, 2048, 25), (2, 32, 600, 8)])
+def test_feature_knn_structured_heavy_tailed_features(cuda, b, c, n, k):
+    """What chained EdgeConv layers feed the feature kNN: a low-dimensional manifold embedded in C channels, far from the
+    origin (distances tiny against the norms), plus a few outliers with huge norms.  The TF32 candidate bounds are per
+    key; the result must stay bit-identical to the exact fp32 oracle."""
+    g = torch.Generator().manual_seed(31 + n)
+    z = torch.randn(b, 3, n, generator=g)                                   # the cloud itself
+    a = torch.randn(1, c, 3, generator=g)
+    x = torch.nn.functional.leaky_relu(a @ z + torch.randn(1, c, 1, generator=g) * 2.0, 0.2)  # (b,c,n), rank <= 3 + relu
+    x[:, :, ::97] *= 30.0                                                   # outliers: norms ~1000x the typical one
+    x[:, :, 1::211] = x[:, :, 0::211][..., :x[:, :, 1::211].shape[-1]]      # and some exact duplicates
+    x = x.contiguous()
+    idx, dist = neighbour_ops.knn_indices(x.to(cuda), k, return_dist=True)
+    eidx, edist = oracle.knn(x.numpy(), k, return_dist=True)
+    assert np.array_equal(idx.cpu().numpy(), eidx)
+    assert np.array_equal(dist.cpu().numpy(), edist)
+
+
 def test_knn_ties_lowest_index(cuda):
     a, _ = synthetic.s3_ties(2, 512, pool=64)  # heavy duplication: many exact ties
     x = a.transpose(1, 2).contiguous()
@@ -137,6 +155,27 @@ def test_errors(cuda):
     assert neighbour_ops.knn(torch.zeros(0, 3, 8, device=cuda), 2).shape == (0, 8, 2)
     idx = neighbour_ops.index_k_neighbours([np.random.default_rng(0).random((64, 3)).astype(np.float32)], 4)
     assert idx.shape == (1, 64, 4) and (idx[0, :, 0] == np.arange(64)).all()
+
+
+def test_dataset_side_index_k_neighbours(cuda):
+    """index_k_neighbours (neighbour_ops.py:16-24; consumer src/data/modelnet.py:150-156 stores it as int16 `index_{k}`):
+    ragged list of clouds, batched by size, against the oracle and -- away from exact ties -- scikit-learn's KDTree,
+    which is what the reference runs."""
+    from sklearn.neighbors import KDTree
+
+    rng = np.random.default_rng(5)
+    pcs = [rng.standard_normal((n, 3)).astype(np.float32) for n in (256, 100, 256, 256, 100)]
+    for chunk in (2, 2048):
+        got = [neighbour_ops.index_k_neighbours([pc], 8)[0] for pc in pcs]  # one by one
+        same = [p for p in pcs if p.shape[0] == 256]
+        batched = neighbour_ops.index_k_neighbours(same, 8, chunk=chunk)
+        assert batched.shape == (3, 256, 8) and batched.dtype == np.int64
+        for row, ref in zip(batched, [g for g, p in zip(got, pcs) if p.shape[0] == 256]):
+            assert np.array_equal(row, ref)
+    for pc, g in zip(pcs, got):
+        assert np.array_equal(g, oracle.knn(pc.T[None].copy(), 8)[0])
+        assert np.array_equal(g, KDTree(pc).query(pc, 8, return_distance=False))
+        assert np.array_equal(g.astype(np.short), g)  # the int16 on-disk format holds them
 
 
 @pytest.mark.parametrize("b,c,n,k", [(2, 3, 300, 4), (2, 64, 1024, 20), (1, 128, 2048, 25), (3, 16, 77, 32), (1, 7, 8192, 3)])
