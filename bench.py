@@ -254,6 +254,16 @@ def run_b200(args) -> None:
                      "frac": 2108416 / (sweep_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "note": "not HBM-bound: 2 MB per launch against 134 M exponentials"},
         "peak_source": pipe.get("source", ""), "launch_ms": sweep_ms,
+        # the sweep's own instruction mix (8 packed FMA-pipe + 2 MUFU.EX2 per partner and thread) on otherwise idle SMs:
+        # what the hardware sustains when both pipes are fed together, with many warps and with the 2 warps per SM
+        # sub-partition that 65 536 points / (32 lanes x 2 points) = 1024 warps leave on 592 sub-partitions
+        "mix_view": None if "emd_mix_gexp_per_s" not in pipe else {
+            "mix_peak_gexp_s": pipe["emd_mix_gexp_per_s_2warps_per_smsp"],
+            "mix_peak_many_warps_gexp_s": pipe["emd_mix_gexp_per_s"],
+            "frac_of_mix_peak": pairs / (sweep_ms * 1e-3) / 1e9 / pipe["emd_mix_gexp_per_s_2warps_per_smsp"],
+            "note": "tools/pipe_peaks k_emd_mix (no shared-memory loads, independent accumulators); with the kernel's "
+                    "broadcast LDS.128 and ordered accumulation tools/emd_mix_probe measures 3101 Gexp/s at 2 warps per "
+                    "sub-partition, x 1.73/2 occupancy quantisation = 2682: the kernel is at 97 % of that"},
         "fp32_tflops": 11 * pairs / (sweep_ms * 1e-3) / 1e12, "fp32_frac": 11 * pairs / (sweep_ms * 1e-3) / 1e12 / fp32_peak,
         "share_of_step": 27 * sweep_ms / (sum(times) / K),
         "algorithmic_unit": "exp-pair evaluations: B*n*m = 134.2 M per sweep launch (DESIGN.md section 4)",

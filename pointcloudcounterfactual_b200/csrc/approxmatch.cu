@@ -61,7 +61,10 @@ __device__ __forceinline__ void am_exp_terms(const float4 q, const f32x2 *npx, c
   }
 }
 
-template <int EPI, int AM_P, int UNROLL = 16>
+#ifndef PCC_AM_UNROLL
+#define PCC_AM_UNROLL 16
+#endif
+template <int EPI, int AM_P, int UNROLL = PCC_AM_UNROLL>
 __global__ void __launch_bounds__(AM_THREADS)
 am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
                 const float *__restrict__ wQ, size_t wQ_stride, float level, float *__restrict__ remainP,
@@ -157,7 +160,10 @@ am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__res
 // (ratioL, :29-62) walk the same (own point k) x (all partners l) loop, so the distance is evaluated once and feeds
 // two exponentials -- 10 instead of 16 FMA-pipe operations per pair for the two sweeps, one partner load instead of two.
 // Each accumulator still sees exactly the reference's operation sequence, so the results stay bit-faithful.
-template <int AM_P, int UNROLL = 8>
+#ifndef PCC_AM31_UNROLL
+#define PCC_AM31_UNROLL 8
+#endif
+template <int AM_P, int UNROLL = PCC_AM31_UNROLL>
 __global__ void __launch_bounds__(AM_THREADS)
 am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
                   const float *__restrict__ ratioR_A, size_t ratioR_stride, const float *__restrict__ remainR,

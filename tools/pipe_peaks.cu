@@ -64,6 +64,36 @@ __global__ void k_ex2(float *out, float a) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// the EMD solver sweep per partner and per thread (two own points packed): 3 FADD2 + FMUL2 + 2 FFMA2 (squared distance),
+// FMUL2 (level), 2 MUFU.EX2, FFMA2 (ordered accumulation) -- 8 packed FMA-pipe instructions and 2 SFU instructions for 2
+// pair evaluations.  ILP independent partners per step, like the 16-partner blocks of am_sweep_kernel.
+__global__ void k_emd_mix(float *out, float qx, float qy, float qz, float lc) {
+  f32x2 px[ILP], py[ILP], pz[ILP], acc[ILP];
+  for (int i = 0; i < ILP; ++i) {
+    px[i] = pack2(threadIdx.x * 1e-3f + i, 0.5f + i);
+    py[i] = pack2(0.1f * i, threadIdx.x * 2e-3f);
+    pz[i] = pack2(0.3f, 0.7f * i);
+    acc[i] = 0ull;
+  }
+  const f32x2 nqx = pack2(-qx, -qx), nqy = pack2(-qy, -qy), nqz = pack2(-qz, -qz), lc2 = pack2(lc, lc), w2 = pack2(0.5f, 0.25f);
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+      f32x2 dx = add2(px[i], nqx), dy = add2(py[i], nqy), dz = add2(pz[i], nqz);
+      f32x2 d = mul2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), lc2);
+      float a, b; unpack2(d, a, b);
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a));
+      asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(b));
+      const f32x2 e = pack2(a, b);
+      acc[i] = fma2(e, w2, acc[i]);
+      px[i] = e, py[i] = dx, pz[i] = dy;  // keep dependencies so nothing is hoisted
+    }
+  }
+  float s = 0;
+  for (int i = 0; i < ILP; ++i) { float lo, hi; unpack2(acc[i], lo, hi); s += lo + hi; }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F> static float time_ms(F launch) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) launch();
@@ -84,12 +114,20 @@ int main() {
   float t2 = time_ms([&] { k_ffma2<<<blocks, threads>>>(out, 1.0001f, 1e-7f); });
   float t3 = time_ms([&] { k_chamfer_mix<<<blocks, threads>>>(out, 0.1f, 0.2f, 0.3f); });
   float t4 = time_ms([&] { k_ex2<<<blocks, threads>>>(out, 0.f); });
+  // EMD mix: plenty of warps (16 per SM sub-partition), then 2 and 1 warps per sub-partition like the sweep kernel itself
+  float t5 = time_ms([&] { k_emd_mix<<<blocks, threads>>>(out, 0.1f, 0.2f, 0.3f, -1.5f); });
+  float t6 = time_ms([&] { k_emd_mix<<<p.multiProcessorCount, 256>>>(out, 0.1f, 0.2f, 0.3f, -1.5f); });
+  float t7 = time_ms([&] { k_emd_mix<<<p.multiProcessorCount, 128>>>(out, 0.1f, 0.2f, 0.3f, -1.5f); });
+  const double emd16 = lanes * ITERS * ILP * 2 / (t5 * 1e-3), emd2 = (double)p.multiProcessorCount * 256 * ITERS * ILP * 2 / (t6 * 1e-3),
+               emd1 = (double)p.multiProcessorCount * 128 * ITERS * ILP * 2 / (t7 * 1e-3);
   const double ffma_tflops = lanes * ITERS * ILP * 2 / (t1 * 1e-3) / 1e12;
   const double ffma2_tflops = lanes * ITERS * ILP * 4 / (t2 * 1e-3) / 1e12;
   const double pairs_per_s = lanes * ITERS * 8 / (t3 * 1e-3);
   const double ex2_per_s = lanes * ITERS * ILP / (t4 * 1e-3);
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"ffma_tflops\": %.2f, \"ffma2_tflops\": %.2f, \"chamfer_mix_gpairs_per_s\": %.2f, "
-         "\"chamfer_mix_flops_equiv_tflops\": %.2f, \"mufu_ex2_gops\": %.2f}\n",
-         p.name, p.multiProcessorCount, ffma_tflops, ffma2_tflops, pairs_per_s / 1e9, pairs_per_s * 8 / 1e12, ex2_per_s / 1e9);
+         "\"chamfer_mix_flops_equiv_tflops\": %.2f, \"mufu_ex2_gops\": %.2f, \"emd_mix_gexp_per_s\": %.2f, "
+         "\"emd_mix_gexp_per_s_2warps_per_smsp\": %.2f, \"emd_mix_gexp_per_s_1warp_per_smsp\": %.2f}\n",
+         p.name, p.multiProcessorCount, ffma_tflops, ffma2_tflops, pairs_per_s / 1e9, pairs_per_s * 8 / 1e12, ex2_per_s / 1e9,
+         emd16 / 1e9, emd2 / 1e9, emd1 / 1e9);
   return cudaDeviceSynchronize() != cudaSuccess;
 }
