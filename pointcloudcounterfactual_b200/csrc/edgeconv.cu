@@ -473,8 +473,13 @@ ec_sort_kernel(int n, int k, int stride, const int *__restrict__ off, const unsi
   const int *offb = off + (size_t)cloud * (n + 1);
   const int beg = offb[j], end = offb[j + 1];
   int rank = 0;
-#pragma unroll 4
-  for (int s2 = beg; s2 < end; ++s2) rank += (src[s2] < mine) ? 1 : 0;
+  int s2 = beg;
+  for (; s2 < end && (s2 & 3); ++s2) rank += (src[s2] < mine) ? 1 : 0;
+  for (; s2 + 4 <= end; s2 += 4) {  // 16-byte loads: the per-cloud stride is a multiple of 32 entries
+    const uint4 v = *reinterpret_cast<const uint4 *>(src + s2);
+    rank += ((v.x < mine) ? 1 : 0) + ((v.y < mine) ? 1 : 0) + ((v.z < mine) ? 1 : 0) + ((v.w < mine) ? 1 : 0);
+  }
+  for (; s2 < end; ++s2) rank += (src[s2] < mine) ? 1 : 0;
   rev[(size_t)cloud * stride + beg + rank] = mine;
 }
 
