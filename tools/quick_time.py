@@ -45,4 +45,8 @@ if "emd" in want:
 if "knn" in want:
     out["knn_feat64_k20_n1024_us"] = graph_time(lambda: neighbour_ops.knn(xf, 20))
     out["knn_xyz_k20_n1024_us"] = graph_time(lambda: neighbour_ops.knn(x3, 20))
+    x25 = synthetic.knn_xyz(32, 2048).to(dev)
+    out["knn_xyz_k4_n2048_us"] = graph_time(lambda: neighbour_ops.knn(x25, 4))
+    out["knn_xyz_k8_n2048_us"] = graph_time(lambda: neighbour_ops.knn(x25, 8))
+    out["knn_xyz_k4_n1024_us"] = graph_time(lambda: neighbour_ops.knn(x3, 4))
 print(json.dumps(out))
