@@ -60,6 +60,31 @@ def global_mean_loss(per_cloud: torch.Tensor) -> torch.Tensor:
     return (acc[0] / acc[1].clamp(min=1.0)).to(per_cloud.dtype)
 
 
+class PendingMean:
+    """Global mean whose all-reduce is in flight (``global_mean_loss_async``).  ``wait()`` makes the current stream wait
+    for the collective and returns the mean; until then the launching stream keeps running -- a reporting collective has
+    no business on the critical path of the step that produced it."""
+
+    def __init__(self, acc: torch.Tensor, work, dtype: torch.dtype):
+        self._acc, self._work, self._dtype = acc, work, dtype
+
+    def wait(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return (self._acc[0] / self._acc[1].clamp(min=1.0)).to(self._dtype)
+
+
+def global_mean_loss_async(per_cloud: torch.Tensor) -> PendingMean:
+    """``global_mean_loss`` with the all-reduce launched asynchronously (NCCL: on the communicator's own stream)."""
+    acc = torch.stack([per_cloud.detach().sum().to(torch.float64),
+                       torch.tensor(float(per_cloud.numel()), dtype=torch.float64, device=per_cloud.device)])
+    work = None
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        work = dist.all_reduce(acc, op=dist.ReduceOp.SUM, async_op=True)
+    return PendingMean(acc, work, per_cloud.dtype)
+
+
 def all_reduce_mean_(grad: torch.Tensor) -> torch.Tensor:
     """In-place data-parallel gradient averaging of a flat buffer (what DDP does per bucket)."""
     if dist.is_initialized() and dist.get_world_size() > 1:

@@ -34,7 +34,12 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
     local, mean = sharding.ShardedLoss(_oracle_chamfer, rank, world)(recon, ref)
     grad = torch.full((4,), float(rank + 1))
     sharding.all_reduce_mean_(grad)
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), local=local.numpy(), mean=mean.numpy(), grad=grad.numpy())
+    # the asynchronous form bench.py uses: two collectives in flight, consumed in order
+    h1 = sharding.global_mean_loss_async(local)
+    h2 = sharding.global_mean_loss_async(local * 2)
+    amean, amean2 = h1.wait(), h2.wait()
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), local=local.numpy(), mean=mean.numpy(), grad=grad.numpy(),
+             amean=amean.numpy(), amean2=amean2.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -51,5 +56,6 @@ def test_sharded_loss_matches_single_process(tmp_path):
     for p in parts:
         assert abs(float(p["mean"]) - full.mean()) < 1e-7
         assert np.allclose(p["grad"], 1.5)
+        assert abs(float(p["amean"]) - full.mean()) < 1e-7 and abs(float(p["amean2"]) - 2 * full.mean()) < 1e-6
     lo, hi = sharding.shard_bounds(5, 2, 0)
     assert (lo, hi) == (0, 3)
