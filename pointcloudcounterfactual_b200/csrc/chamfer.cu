@@ -429,22 +429,26 @@ nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__rest
   const int *__restrict__ iS = (dir ? idx1 : idx2) + cloud * (size_t)nS;  // source -> nearest target
   float *__restrict__ out = (dir ? g2 : g1) + cloud * (size_t)nT * 3;
 
-  int *cursor = sm;             // nT
-  int *start = sm + nT;         // nT
-  int *slots = sm + 2 * nT;     // nS
+  // blockIdx.z splits the TARGETS of this (cloud, direction) into contiguous ranges, one CTA each: every CTA scans all
+  // sources but keeps only those whose nearest target lies in its range (64 CTAs of serial phases are latency-bound)
+  const int per = (nT + gridDim.z - 1) / gridDim.z;
+  const int jb = min((int)blockIdx.z * per, nT), je = min(jb + per, nT), nR = je - jb;
+  int *cursor = sm;             // nR
+  int *start = sm + per;        // nR
+  int *slots = sm + 2 * per;    // up to nS
   int *heavy = slots + nS;      // up to nS / (NG_HEAVY + 1) + 1 entries
 
-  for (int j = threadIdx.x; j < nT; j += NG_THREADS) cursor[j] = 0;
+  for (int j = threadIdx.x; j < nR; j += NG_THREADS) cursor[j] = 0;
   if (threadIdx.x == 0) n_heavy = 0;
   __syncthreads();
   for (int l = threadIdx.x; l < nS; l += NG_THREADS) {
     int t = min(max(iS[l], 0), nT - 1);
-    atomicAdd(&cursor[t], 1);
+    if (t >= jb && t < je) atomicAdd(&cursor[t - jb], 1);
   }
   __syncthreads();
   // exclusive scan of the in-degrees: contiguous chunk per thread
-  const int chunk = (nT + NG_THREADS - 1) / NG_THREADS;
-  const int c0 = min((int)threadIdx.x * chunk, nT), c1 = min(c0 + chunk, nT);
+  const int chunk = (nR + NG_THREADS - 1) / NG_THREADS;
+  const int c0 = min((int)threadIdx.x * chunk, nR), c1 = min(c0 + chunk, nR);
   int local = 0;
   for (int j = c0; j < c1; ++j) local += cursor[j];
   int off = block_exclusive_scan(local, warp_tot, &scan_total);
@@ -457,12 +461,13 @@ nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__rest
   __syncthreads();
   for (int l = threadIdx.x; l < nS; l += NG_THREADS) {
     int t = min(max(iS[l], 0), nT - 1);
-    slots[atomicAdd(&cursor[t], 1)] = l;
+    if (t >= jb && t < je) slots[atomicAdd(&cursor[t - jb], 1)] = l;
   }
   __syncthreads();
 
-  for (int j = threadIdx.x; j < nT; j += NG_THREADS) {
-    const int s = start[j], e = cursor[j], deg = e - s;
+  for (int jr = threadIdx.x; jr < nR; jr += NG_THREADS) {
+    const int j = jb + jr;
+    const int s = start[jr], e = cursor[jr], deg = e - s;
     if (deg > NG_HEAVY) {
       heavy[atomicAdd(&n_heavy, 1)] = j;
       continue;
@@ -531,6 +536,14 @@ nn_grad_kernel(int n, const float *__restrict__ xyz1, int m, const float *__rest
     }
     __syncthreads();
   }
+}
+
+// target ranges per (cloud, direction): about two CTAs per SM in total, at least 256 targets per range
+static int nn_grad_parts(int b, int n_small) {
+  int parts = 300 / (2 * (b > 0 ? b : 1));
+  parts = parts < 1 ? 1 : (parts > 8 ? 8 : parts);
+  while (parts > 1 && n_small / parts < 256) --parts;
+  return parts;
 }
 
 // loss[b] = s1 * sum_j dist1[b][j] + s2 * sum_k dist2[b][k]: fixed summation order (deterministic)
@@ -636,7 +649,6 @@ extern "C" __attribute__((visibility("default"))) int pcc_nndistancegrad(int b, 
   }
   const size_t mx = n > m ? n : m, mn = n > m ? m : n;
   const size_t smem = sizeof(int) * (2 * mx + mx + mx / (NG_HEAVY + 1) + 8);
-  (void)mn;
   if (smem <= 200 * 1024 && b <= 65535) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -644,8 +656,8 @@ extern "C" __attribute__((visibility("default"))) int pcc_nndistancegrad(int b, 
       if (e != cudaSuccess) return (int)e;
       attr_set = true;
     }
-    nn_grad_kernel<<<dim3(b, 2), NG_THREADS, smem, st>>>(n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2,
-                                                          grad_xyz1, grad_xyz2, nullptr, 0.f, 0.f);
+    nn_grad_kernel<<<dim3(b, 2, nn_grad_parts(b, (int)mn)), NG_THREADS, smem, st>>>(
+        n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, nullptr, 0.f, 0.f);
     return finish_launch(1);
   }
   const int threads = 256;
@@ -683,7 +695,7 @@ extern "C" __attribute__((visibility("default"))) int pcc_chamfer_reduce_grad(in
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  nn_grad_kernel<<<dim3(b, 2), NG_THREADS, smem, st>>>(n, xyz1, m, xyz2, nullptr, idx1, nullptr, idx2, grad_xyz1, grad_xyz2,
-                                                        grad_loss, scale1, scale2);
+  nn_grad_kernel<<<dim3(b, 2, nn_grad_parts(b, n < m ? n : m)), NG_THREADS, smem, st>>>(
+      n, xyz1, m, xyz2, nullptr, idx1, nullptr, idx2, grad_xyz1, grad_xyz2, grad_loss, scale1, scale2);
   return finish_launch(1);
 }
