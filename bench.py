@@ -44,6 +44,7 @@ def parse_args():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--eager", action="store_true", help="time the steps with eager launches instead of GraphedLossStep")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--no-sub", action="store_true", help="skip sub-metrics (Chamfer-only, EMD-only, kNN)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -157,23 +158,42 @@ def run_b200(args) -> None:
     # The reported global mean is one all-reduce of (sum, count) per step.  It is launched asynchronously and consumed one
     # step later (the last one inside the last step), so a rank never idles on a reporting collective: with a blocking
     # all-reduce every step ends at the slowest rank and the skew of 8 GPUs adds up (2.00 instead of 1.8 ms per step).
+    e2e_pending = []
+    graphed = graphed_dev = None
+    if not args.eager:
+        try:  # the public fixed-shape step: [H2D copies +] loss forward/backward + D2H of the loss as ONE graph launch
+            graphed = losses.GraphedLossStep(losses.chamfer_emd, recon_h, ref_h, dev)
+            graphed_dev = losses.GraphedLossStep(losses.chamfer_emd, recon_d, ref_d, dev)
+        except Exception as e:  # noqa: BLE001
+            torch.cuda.synchronize()
+            graphed = graphed_dev = None
+            print(f"[bench] graph capture refused ({type(e).__name__}: {e}); eager steps", file=sys.stderr)
+
     def step_device():
-        r = recon_d.detach().requires_grad_(True)
-        loss = losses.chamfer_emd(r, ref_d)
-        (grad,) = torch.autograd.grad(loss.sum(), r)
+        if graphed_dev is not None:
+            _, grad = graphed_dev()
+            loss = graphed_dev.loss_device
+        else:
+            r = recon_d.detach().requires_grad_(True)
+            loss = losses.chamfer_emd(r, ref_d)
+            (grad,) = torch.autograd.grad(loss.sum(), r)
         return loss, grad, sharding.global_mean_loss_async(loss)
 
-    e2e_pending = []
-
     def step_e2e():
-        r = recon_h.to(dev, non_blocking=True).requires_grad_(True)
-        t = ref_h.to(dev, non_blocking=True)
-        loss = losses.chamfer_emd(r, t)
-        (grad,) = torch.autograd.grad(loss.sum(), r)
+        if graphed is not None:
+            local, grad = graphed()          # pinned host clouds -> device -> loss + gradient -> loss on the host
+            loss = graphed.loss_device
+        else:
+            r = recon_h.to(dev, non_blocking=True).requires_grad_(True)
+            t = ref_h.to(dev, non_blocking=True)
+            loss = losses.chamfer_emd(r, t)
+            (grad,) = torch.autograd.grad(loss.sum(), r)
+            local = loss.cpu()
         e2e_pending.append(sharding.global_mean_loss_async(loss))
-        local = loss.cpu()  # the step's result on the host (synchronises this rank's stream)
+        torch.cuda.current_stream(dev).synchronize()  # the step's result is on the host now
+        host_value = float(local[0])
         mean = float(e2e_pending.pop(0).wait().cpu()) if len(e2e_pending) > 1 else None  # previous step's global mean
-        return local, mean, grad
+        return host_value, mean, grad
 
     def timed(fn, steps, warm):
         """per-step CUDA events on the launching stream; L2 flushed between steps outside the events."""
@@ -216,6 +236,8 @@ def run_b200(args) -> None:
     l0 = _lib.launch_count()
     times = timed(step_device, K, W)
     launches = (_lib.launch_count() - l0) * K // (K + W)
+    if graphed_dev is not None:  # replays do not pass through the C entry points: count what the capture recorded
+        launches = graphed_dev.kernels_per_replay * K
     total_ms = reduce_max(sum(times))
     value = world * B_PER_GPU * K / (total_ms * 1e-3)
 
@@ -507,9 +529,13 @@ def run_b200(args) -> None:
             "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "points": N_POINTS,
                        "parallelism": f"batch-sharded x{world}, one all-reduce of the loss per step (asynchronous, consumed one step later)",
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA events); inputs are 1.5 MB",
-                       "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks"},
+                       "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
+                       "launch": "losses.GraphedLossStep (one CUDA-graph launch per step)" if graphed_dev is not None
+                       else "eager"},
             "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "pinned host clouds -> H2D -> chamfer_emd fwd+bwd -> loss D2H each step, host wall clock"},
+                    "note": "pinned host clouds -> H2D -> chamfer_emd fwd+bwd -> loss D2H each step, host wall clock; "
+                            + ("the step is losses.GraphedLossStep (copies + kernels captured as one CUDA graph)"
+                               if graphed is not None else "eager launches")},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

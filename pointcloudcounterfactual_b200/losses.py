@@ -82,3 +82,62 @@ def chamfer_emd(recon: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
     """The reference's ChamferEMD reconstruction loss on GPU (:70-79 -> :59-67 + :50-56):
     ``pykeops_chamfer(recon, ref) + match_cost(recon, ref)``, one value per cloud."""
     return pykeops_chamfer(recon, ref) + match_cost(recon.contiguous(), ref.contiguous())
+
+
+class GraphedLossStep:
+    """One training-loss step for FIXED shapes as a CUDA graph: [host clouds -> device,] ``loss_fn(recon, ref)`` forward,
+    backward w.r.t. ``recon``, per-cloud loss back to the host.  Replaying it costs one launch instead of ~60 Python-side
+    calls, so the GPU does not idle between kernels or between steps while the host issues work (B=32 x 2048, end to
+    end: 16.8 k -> 18.4 k clouds/s).  Usage::
+
+        step = GraphedLossStep(chamfer_emd, recon_host, ref_host, device)   # pinned (B,N,3) / (B,M,3) host tensors
+        recon_host.copy_(new_batch)            # refill the SAME pinned buffers, then
+        loss_host, grad = step()               # loss_host: pinned (B,), valid after step.synchronize(); grad: device (B,N,3)
+
+    With CUDA tensors instead of pinned host tensors the copies are left out and ``step.recon`` / ``step.ref`` are the
+    device buffers to refill.  ``loss_device`` holds the per-cloud loss on the device (e.g. for
+    ``sharding.global_mean_loss_async``)."""
+
+    def __init__(self, loss_fn, recon: torch.Tensor, ref: torch.Tensor, device: torch.device, warmup: int = 2):
+        self.device = torch.device(device)
+        self._from_host = not recon.is_cuda
+        if self._from_host and not (recon.is_pinned() and ref.is_pinned()):
+            raise RuntimeError("GraphedLossStep needs pinned host tensors (the copies are part of the graph)")
+        self._recon_h, self._ref_h = recon, ref
+        with torch.cuda.device(self.device):
+            if self._from_host:
+                self.recon = torch.empty(recon.shape, dtype=recon.dtype, device=self.device).requires_grad_(True)
+                self.ref = torch.empty(ref.shape, dtype=ref.dtype, device=self.device)
+            else:
+                self.recon = recon.detach().clone().requires_grad_(True)
+                self.ref = ref.detach().clone()
+            self.loss_host = torch.empty((recon.size(0),), dtype=torch.float32).pin_memory()
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):  # warm-up outside the capture (lazy initialisation, memory pool)
+                for _ in range(max(warmup, 1)):
+                    self._body(loss_fn)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self._graph = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(self._graph):
+                self._body(loss_fn)
+            self.kernels_per_replay = L.launch_count() - n0  # libpcc_b200 kernels inside one replay
+
+    def _body(self, loss_fn) -> None:
+        if self._from_host:
+            with torch.no_grad():
+                self.recon.copy_(self._recon_h, non_blocking=True)
+                self.ref.copy_(self._ref_h, non_blocking=True)
+        loss = loss_fn(self.recon, self.ref)
+        (self.grad,) = torch.autograd.grad(loss.sum(), self.recon)
+        self.loss_device = loss.detach()
+        self.loss_host.copy_(self.loss_device, non_blocking=True)
+
+    def __call__(self) -> tuple[torch.Tensor, torch.Tensor]:
+        self._graph.replay()
+        return self.loss_host, self.grad
+
+    def synchronize(self) -> None:
+        torch.cuda.current_stream(self.device).synchronize()

@@ -6,7 +6,7 @@ import torch
 
 import oracle
 from conftest import rel_err
-from pointcloudcounterfactual_b200 import synthetic
+from pointcloudcounterfactual_b200 import losses, synthetic
 from pointcloudcounterfactual_b200.emd import emdModule
 from pointcloudcounterfactual_b200.structural_losses import match_cost
 from pointcloudcounterfactual_b200.structural_losses.structural_losses_backend import (
@@ -120,3 +120,39 @@ def test_auction_vs_oracle(cuda, b, n, eps, iters):
     (dist * w.to(cuda)).sum().backward()
     eg = oracle.auction_emd_grad(a.numpy(), c.numpy(), w.numpy(), easg)
     assert rel_err(ta.grad.cpu().numpy(), eg) < TOL
+
+
+def test_graphed_loss_step_equals_eager(cuda):
+    """losses.GraphedLossStep: host -> device copies, chamfer_emd forward/backward and the loss read-back captured as one
+    CUDA graph; refilling the pinned buffers and replaying gives exactly the eager results (same kernels, same order)."""
+    recon, ref = synthetic.s1_near(3, 512)
+    rh, th = recon.clone().pin_memory(), ref.clone().pin_memory()
+    step = losses.GraphedLossStep(losses.chamfer_emd, rh, th, cuda)
+    assert step.kernels_per_replay > 20
+    for seed_shift in (0, 7):
+        a, c = synthetic.s1_near(3, 512, first=seed_shift)
+        rh.copy_(a)
+        th.copy_(c)
+        loss_h, grad = step()
+        step.synchronize()
+        r = a.to(cuda).requires_grad_(True)
+        want = losses.chamfer_emd(r, c.to(cuda))
+        (gw,) = torch.autograd.grad(want.sum(), r)
+        assert torch.equal(loss_h, want.detach().cpu())
+        assert torch.equal(grad.cpu(), gw.cpu())
+    with pytest.raises(RuntimeError):
+        losses.GraphedLossStep(losses.chamfer_emd, recon, ref, cuda)  # not pinned
+
+
+def test_graphed_loss_step_device_resident(cuda):
+    a, c = synthetic.s1_near(2, 384)
+    step = losses.GraphedLossStep(losses.chamfer_emd, a.to(cuda), c.to(cuda), cuda)
+    a2, c2 = synthetic.s1_near(2, 384, first=3)
+    step.recon.data.copy_(a2.to(cuda))
+    step.ref.copy_(c2.to(cuda))
+    loss_h, grad = step()
+    step.synchronize()
+    r = a2.to(cuda).requires_grad_(True)
+    want = losses.chamfer_emd(r, c2.to(cuda))
+    (gw,) = torch.autograd.grad(want.sum(), r)
+    assert torch.equal(loss_h, want.detach().cpu()) and torch.equal(grad.cpu(), gw.cpu())
