@@ -229,6 +229,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // eps_ij = cq * (c1 sqrt(n_j)) + c2 n_j + c2 |x_q|^2: the key-side factors come precomputed (knn_tc2_prep_kernel),
     // the query side is cq = |x_q| and the constant c2 |x_q|^2, which moves into the threshold
     const float cq = sqrtf(nq), c2nq = T2_C2 * nq;
+    const f32x2 m2 = pack2(-2.f, -2.f), cq2 = pack2(cq, cq), ncq2 = pack2(-cq, -cq);
     float thr = INF;
     int cnt = 0;
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 2 * R);
@@ -287,10 +288,12 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const float4 w = *reinterpret_cast<const float4 *>(rns + ch * 32 + 4 * g);
             const float4 sn = *reinterpret_cast<const float4 *>(rns + 2 * R + ch * 32 + 4 * g);
             // upper bound of the true score: s~ + eps_ij (without the per-query constant c2 |x_q|^2)
-            const float z0 = fmaf(cq, sn.x, fmaf(-2.f, __uint_as_float(v[4 * g + 0]), w.x)),
-                        z1 = fmaf(cq, sn.y, fmaf(-2.f, __uint_as_float(v[4 * g + 1]), w.y)),
-                        z2 = fmaf(cq, sn.z, fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z)),
-                        z3 = fmaf(cq, sn.w, fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w));
+            // (two scores per packed instruction: same roundings as the scalar fma)
+            float z0, z1, z2, z3;
+            unpack2(fma2(cq2, pack2(sn.x, sn.y),
+                         fma2(m2, pack2(__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1])), pack2(w.x, w.y))), z0, z1);
+            unpack2(fma2(cq2, pack2(sn.z, sn.w),
+                         fma2(m2, pack2(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])), pack2(w.z, w.w))), z2, z3);
             if (g < 4)
               mlo = fminf(fminf(z0, z1), fminf(fminf(z2, z3), mlo));
             else
@@ -338,6 +341,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // ---- sweep 2: candidate masks (sign bit of score - thr) ----
         unsigned int masks[CHUNKS];
         int c_l = 0;
+        const f32x2 nthr2 = pack2(-thr, -thr);  // z - thr == z + (-thr) bit for bit
 #pragma unroll
         for (int ch = 0; ch < CHUNKS; ++ch) {
           uint32_t v[32];
@@ -349,10 +353,13 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const float4 w = *reinterpret_cast<const float4 *>(rns + R + ch * 32 + 4 * g);
             const float4 sn = *reinterpret_cast<const float4 *>(rns + 2 * R + ch * 32 + 4 * g);
             // lower bound of the true score, minus the threshold
-            const float z3 = fmaf(-cq, sn.w, fmaf(-2.f, __uint_as_float(v[4 * g + 3]), w.w)) - thr,
-                        z2 = fmaf(-cq, sn.z, fmaf(-2.f, __uint_as_float(v[4 * g + 2]), w.z)) - thr,
-                        z1 = fmaf(-cq, sn.y, fmaf(-2.f, __uint_as_float(v[4 * g + 1]), w.y)) - thr,
-                        z0 = fmaf(-cq, sn.x, fmaf(-2.f, __uint_as_float(v[4 * g + 0]), w.x)) - thr;
+            float z0, z1, z2, z3;
+            unpack2(add2(fma2(ncq2, pack2(sn.x, sn.y),
+                              fma2(m2, pack2(__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1])), pack2(w.x, w.y))),
+                         nthr2), z0, z1);
+            unpack2(add2(fma2(ncq2, pack2(sn.z, sn.w),
+                              fma2(m2, pack2(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])), pack2(w.z, w.w))),
+                         nthr2), z2, z3);
             mk = __funnelshift_l(__float_as_uint(z3), mk, 1);
             mk = __funnelshift_l(__float_as_uint(z2), mk, 1);
             mk = __funnelshift_l(__float_as_uint(z1), mk, 1);
