@@ -164,3 +164,45 @@ def test_backward_is_deterministic_and_limits_fall_back(cuda):
     assert out.shape == (2, 64, 512) and int(gelu.bn.num_batches_tracked) == 1
     with pytest.raises(RuntimeError):
         edgeconv.edge_conv_max(x0.cpu(), torch.zeros(2, 512, 20, dtype=torch.int64), layer.dense.weight.cpu())
+
+
+@pytest.mark.parametrize("b,c,n,k,cout,mode", [
+    (1, 4, 37, 1, 4, "train"),        # k = 1, a single quad of channels
+    (2, 8, 2560, 3, 8, "train"),      # exactly at the shared-memory staging limit
+    (1, 8, 2561, 3, 8, "train"),      # one above it: L2-gather kernels
+    (1, 6, 90, 64, 16, "train"),      # k at the kernel limit, k > a few of the in-degrees
+    (3, 5, 64, 7, 24, "eval"),        # eval mode WITH backward (gradients through the running statistics)
+    (2, 5, 64, 7, 24, "affine"),      # no BatchNorm: conv bias gradient
+])
+def test_fused_layer_edge_shapes_and_arbitrary_indices(cuda, b, c, n, k, cout, mode):
+    """Caller-supplied neighbour lists with duplicates inside a list and hubs (every list contains point 0), a
+    non-contiguous (transposed-view) input as DGCNN's first layer passes it, and the shape limits."""
+    gen = torch.Generator().manual_seed(1000 + n + k)
+    xt = torch.randn(b, n, c, generator=gen)                    # (B,N,C) storage; the op sees its transposed view
+    idx = torch.randint(0, n, (b, n, k), generator=gen)
+    idx[:, :, 0] = 0                                            # a hub with in-degree >= n
+    if k > 2:
+        idx[:, :, 2] = idx[:, :, 1]                             # a duplicate inside every list
+    w0 = torch.randn(cout, 2 * c, generator=gen) / (2 * c) ** 0.5
+    g0, b0 = torch.randn(cout, generator=gen), torch.randn(cout, generator=gen) * 0.3
+    rm0, rv0 = torch.randn(cout, generator=gen) * 0.1, torch.rand(cout, generator=gen) + 0.5
+    gout = torch.randn(b, cout, n, generator=gen)
+    bn_mode = {"train": edgeconv.BN_TRAIN, "eval": edgeconv.BN_EVAL, "affine": edgeconv.AFFINE}[mode]
+
+    xd = xt.to(cuda).requires_grad_(True)
+    w, gm, bt = (t.to(cuda).requires_grad_(True) for t in (w0, g0, b0))
+    out = edgeconv.edge_conv_max(xd.transpose(1, 2), idx.to(cuda), w, gm, bt, rm0.to(cuda), rv0.to(cuda), bn_mode, 0.1, 1e-5, 0.2)
+    out.backward(gout.to(cuda))
+
+    xr = xt.double().requires_grad_(True)
+    wr, gr, br = (t.double().requires_grad_(True) for t in (w0, g0, b0))
+    if mode == "affine":
+        ref = edgeconv_ref.edge_conv_max(xr.transpose(1, 2), idx, wr, gr, br, torch.zeros(cout), torch.ones(cout) - 1e-5, False,
+                                         0.1, 1e-5, 0.2)[0]
+    else:
+        ref = edgeconv_ref.edge_conv_max(xr.transpose(1, 2), idx, wr, gr, br, rm0, rv0, mode == "train", 0.1, 1e-5, 0.2)[0]
+    ref.backward(gout.double())
+    assert rel_err(out.detach().cpu(), ref.detach()) < OUT_TOL
+    # ties between duplicated list entries carry the same value: the gradient is the same whichever slot wins
+    for got, want in ((xd.grad, xr.grad), (w.grad, wr.grad), (gm.grad, gr.grad), (bt.grad, br.grad)):
+        assert rel_err(got.cpu(), want) < GRAD_TOL
