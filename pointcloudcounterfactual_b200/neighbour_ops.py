@@ -149,7 +149,17 @@ def get_local_covariance(x: torch.Tensor, indices: torch.Tensor, k: int = 16) ->
 
 
 def graph_max_pooling(x: torch.Tensor, indices: torch.Tensor, k: int = 16) -> torch.Tensor:
-    """(:106-110)"""
+    """(:106-110) max over the k neighbours of every point, (B,C,N) -> (B,C,N) (LDGCNN, src/module/encoders.py:84).
+    On CUDA this is the fused EdgeConv edge pass with the identity as convolution (u_j = x_j, v_i = 0, no
+    normalisation): no (B,C,N,k) tensor, bit-identical values, the gradient goes to the first arg-max slot."""
+    if not indices.numel():
+        indices = knn(x, k)
+    c = x.shape[1]
+    if _fused_gather_ok(x, indices, k) and c % 4 == 0 and 4 <= c <= 1024 and k <= 64:
+        from . import edgeconv  # late import: edgeconv builds on this module
+
+        eye = torch.eye(c, dtype=x.dtype, device=x.device)
+        return edgeconv.edge_conv_max(x, indices, torch.cat([eye, eye], dim=1), bn_mode=edgeconv.AFFINE)
     return get_neighbours(x, indices, k)[1].max(dim=-1)[0]
 
 

@@ -206,3 +206,21 @@ def test_fused_layer_edge_shapes_and_arbitrary_indices(cuda, b, c, n, k, cout, m
     # ties between duplicated list entries carry the same value: the gradient is the same whichever slot wins
     for got, want in ((xd.grad, xr.grad), (w.grad, wr.grad), (gm.grad, gr.grad), (bt.grad, br.grad)):
         assert rel_err(got.cpu(), want) < GRAD_TOL
+
+
+def test_graph_max_pooling_runs_on_the_edge_pass(cuda):
+    """neighbour_ops.graph_max_pooling (reference :106-110, used by LDGCNN) on the fused path: values bit-identical to the
+    gather + max composition, gradient equal (no ties in random data)."""
+    x0 = synthetic.knn_features(2, 64, 700).to(cuda)
+    idx = neighbour_ops.knn(x0[:, :3].contiguous(), 16)
+    xa, xb = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+    out = neighbour_ops.graph_max_pooling(xa, idx, 16)
+    flat = idx.view(2, 1, -1).expand(-1, 64, -1)
+    ref = torch.gather(xb, 2, flat).view(2, 64, 700, 16).max(dim=-1)[0]
+    assert torch.equal(out, ref)
+    g = torch.randn_like(ref)
+    out.backward(g)
+    ref.backward(g)
+    assert rel_err(xa.grad.cpu(), xb.grad.cpu()) < 1e-6
+    odd = synthetic.knn_features(1, 16, 100)[:, :6].contiguous().to(cuda)   # C % 4 != 0: the torch composition
+    assert neighbour_ops.graph_max_pooling(odd, torch.empty(0), 5).shape == (1, 6, 100)
