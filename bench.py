@@ -417,6 +417,17 @@ def run_b200(args) -> None:
         # iteration, per GPU, with the step's real collective ------------------------------------------------------
         grad_buf = torch.zeros(45 * (1 << 20) // 4, device=dev)  # ~45 MB of fp32 autoencoder gradients
 
+        # ---- auction EMD (external/emd): clouds in [0,1]^3, eps = 0.005, 50 rounds -------------------------
+        from pointcloudcounterfactual_b200.emd import emdModule
+
+        ua, uc = (t.to(dev) for t in synthetic.auction_clouds(B_PER_GPU, N_POINTS))
+        auction = emdModule()
+        ms = ev_time(lambda: auction(ua, uc, 0.005, 50), 5, warm=2)
+        sub["auction_emd_fwd_n2048_eps0.005_iters50"] = {
+            "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": False,
+            "note": "one launch: a 4-CTA thread-block cluster per cloud runs all rounds (the reference launches 7 kernels "
+                    "per round; its CUDA kernels recompiled for sm_100a take 6.07 ms on the same GPU, tools/ref_cuda_compare.py)"}
+
         # ---- fused EdgeConv layer (full row) and the DGCNN edge-convolution stack built from it ----------
         class _EdgeConv(torch.nn.Module):
             """Attribute names and forward of the reference's EdgeConvLayer (src/module/layers.py:159-203)."""

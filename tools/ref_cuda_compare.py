@@ -62,6 +62,26 @@ def our_emd_chain():
 out["emd_approxmatch_matchcost_grad"] = {"reference_cuda": ev(ref_emd, reps=3, warm=1),
                                          "b200_same_chain": ev(our_emd_chain, reps=5, warm=1),
                                          "b200_fused_match_cost": ev(lambda: MatchCostFused(a, c, True, True), reps=5, warm=1)}
+# ---- auction EMD (external/emd): B=32, N=2048, eps=0.005, 50 iterations (the reference's documented setting) ----
+if build_ref.available("emd_backend_ref"):
+    from pointcloudcounterfactual_b200.emd import emdModule
+
+    refe = build_ref.load_ref("emd_backend_ref")
+    ua, uc = (t.to(dev) for t in synthetic.auction_clouds(B, N))
+
+    def buf(shape, dtype, fill=0):
+        return torch.full(shape, fill, dtype=dtype, device=dev)
+
+    def ref_auction():  # buffers initialised per call exactly as emd_module.py:34-45 does
+        args = [ua, uc, buf((B, N), torch.float32), buf((B, N), torch.int32, -1), buf((B, N), torch.float32),
+                buf((B, N), torch.int32, -1), buf((B, N), torch.int32), buf((B, N), torch.float32),
+                buf((B, N), torch.float32), buf((B * N,), torch.int32), buf((512,), torch.int32),
+                buf((512,), torch.int32), buf((512,), torch.int32), buf((B * N,), torch.int32), 0.005, 50]
+        refe.forward(*args)
+
+    mod = emdModule()
+    out["auction_emd_fwd_eps0.005_iters50"] = {"reference_cuda": ev(ref_auction, reps=3, warm=1),
+                                               "b200": ev(lambda: mod(ua, uc, 0.005, 50), reps=5, warm=1)}
 for k, v in out.items():
     if isinstance(v, dict) and "reference_cuda" in v:
         base = v["reference_cuda"]
