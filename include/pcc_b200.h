@@ -158,7 +158,8 @@ int pcc_graph_filtering_grad(int b, int n, int k, const float *x, const int64_t 
  * initialises the work buffers exactly as emd/emd_module.py:34-45 does (assignment = assignment_inv = -1, the rest 0;
  * unass_cnt / unass_cnt_sum / cnt_tmp are 512 ints).  Returns 1 on success and -1 on a shape error, like the
  * reference (n must be a multiple of 1024, b <= 512); other values are CUDA errors.
- * One persistent CTA per cloud runs all `iters` rounds (the reference launches 7 kernels per round). */
+ * One persistent thread-block cluster (4 CTAs) per cloud runs all `iters` rounds in one launch (the reference launches 7
+ * kernels per round); unass_cnt carries the per-CTA counts of the cluster (a pool allocation replaces it for b > 128). */
 int pcc_emd_forward(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *assignment,
                     float *price, int *assignment_inv, int *bid, float *bid_increments, float *max_increments,
                     int *unass_idx, int *unass_cnt, int *unass_cnt_sum, int *cnt_tmp, int *max_idx, float eps,
