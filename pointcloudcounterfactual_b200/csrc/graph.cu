@@ -151,7 +151,7 @@ static int launch_gather_grad(int b, int c, int n, int k, const int64_t *idx, co
 // nearest neighbours (column 0 of the kNN list is the point itself),  sigma = max(mean_i d_i1, 0.005) per cloud.
 // The reference runs ~15 elementwise / gather / reduce kernels forward and twice that backward on (B,3,N,3) tensors;
 // here one CTA per cloud keeps the cloud in shared memory and does each direction in one launch.
-constexpr int GF_THREADS = 256;
+constexpr int GF_THREADS = 1024;
 constexpr int GF_MAXK = 8;
 
 __device__ __forceinline__ float gf_block_sum(float v, float *red) {  // fixed order: deterministic

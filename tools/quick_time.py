@@ -50,3 +50,11 @@ if "knn" in want:
     out["knn_xyz_k8_n2048_us"] = graph_time(lambda: neighbour_ops.knn(x25, 8))
     out["knn_xyz_k4_n1024_us"] = graph_time(lambda: neighbour_ops.knn(x3, 4))
 print(json.dumps(out))
+if "gfilt" in want:
+    xg = synthetic.knn_xyz(32, 2048).to(dev).requires_grad_(True)
+
+    def gf():
+        o = neighbour_ops.graph_filtering(xg, 4)
+        torch.autograd.grad(o, xg, o)
+
+    print(json.dumps({"graph_filtering_fwd_bwd_us": graph_time(gf)}))
