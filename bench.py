@@ -587,7 +587,16 @@ def cpu_reference_value(sample_clouds: int, reps: int) -> dict:
         oracle.matchcost(recon.numpy(), ref.numpy(), match)
         oracle.matchcostgrad(recon.numpy(), ref.numpy(), match)
     dt = (time.perf_counter() - t0) / reps
-    return {"value": sample_clouds / dt, "unit": "clouds/s", "cores": cores, "kind": "port",
+    # the kNN half of the metric: the reference's torch CPU path (torch_knn, neighbour_ops.py:71-74), full batch
+    knn = {}
+    for name, x in (("knn_xyz_k20_n1024_graphs_per_s", synthetic.knn_xyz(B_PER_GPU, KNN_N)),
+                    ("knn_feat64_k20_n1024_graphs_per_s", synthetic.knn_features(B_PER_GPU, KNN_C, KNN_N))):
+        torch_ref.torch_knn(x, KNN_K)
+        t1 = time.perf_counter()
+        for _ in range(3):
+            torch_ref.torch_knn(x, KNN_K)
+        knn[name] = B_PER_GPU / ((time.perf_counter() - t1) / 3)
+    return {"value": sample_clouds / dt, "unit": "clouds/s", "cores": cores, "kind": "port", **knn,
             "sample": f"{sample_clouds} clouds x {N_POINTS} points, {reps} repetitions: torch CPU torch_chamfer fwd+bwd "
                       f"(reference path) + C oracle approxmatch/matchcost/matchcostgrad (no CPU EMD exists in the reference)"}
 
