@@ -41,6 +41,7 @@ class _EdgeConvMax(Function):
     GEMM with K = B*N and two output tiles, and so that no transposed copy of x or of the gradient is made."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)  # the kernels are fp32: no autocast inside
     def forward(ctx: Any, x: torch.Tensor, weight: torch.Tensor, idx: torch.Tensor, gamma: torch.Tensor | None,
                 beta: torch.Tensor | None, running_mean: torch.Tensor | None, running_var: torch.Tensor | None,
                 bn_mode: int, momentum: float, eps: float, act: int, slope: float) -> torch.Tensor:
@@ -68,6 +69,7 @@ class _EdgeConvMax(Function):
         return out
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx: Any, grad_out: torch.Tensor):
         x, ws, uv, idx, gamma, beta, mean, invstd, exty, sy, slot = ctx.saved_tensors
         bn_mode, act, slope = ctx.cfg

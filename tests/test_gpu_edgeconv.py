@@ -224,3 +224,14 @@ def test_graph_max_pooling_runs_on_the_edge_pass(cuda):
     assert rel_err(xa.grad.cpu(), xb.grad.cpu()) < 1e-6
     odd = synthetic.knn_features(1, 16, 100)[:, :6].contiguous().to(cuda)   # C % 4 != 0: the torch composition
     assert neighbour_ops.graph_max_pooling(odd, torch.empty(0), 5).shape == (1, 6, 100)
+
+
+def test_fused_layer_under_autocast_stays_fp32(cuda):
+    """Inside torch.autocast the point GEMM must not drop to half precision (the edge kernels read fp32)."""
+    x0 = synthetic.knn_features(1, 16, 200).to(cuda)
+    idx = neighbour_ops.knn(x0, 6)
+    w = torch.randn(8, 32, device=cuda) * 0.2
+    ref = edgeconv.edge_conv_max(x0, idx, w, bn_mode=edgeconv.AFFINE)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = edgeconv.edge_conv_max(x0, idx, w, bn_mode=edgeconv.AFFINE)
+    assert out.dtype == torch.float32 and torch.equal(out, ref)
