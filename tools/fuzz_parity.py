@@ -1,0 +1,86 @@
+"""One-off randomized parity sweep on the GPU (not part of the test suite): feature / xyz kNN against the exact oracle on
+random shapes and input styles, fused EdgeConv against the float64 oracle.  Prints one line per failure and a summary."""
+import sys
+from pathlib import Path
+import numpy as np
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import oracle
+from oracle import edgeconv_ref
+from pointcloudcounterfactual_b200 import edgeconv, neighbour_ops, synthetic
+
+dev = torch.device("cuda", 0)
+rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+fails = 0
+cases = 0
+for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 40):
+    c = int(rng.choice([3, 3, 32, 64, 96, 128, 17, 160]))
+    n = int(rng.integers(40, 2300))
+    k = int(rng.integers(1, min(33, n)))
+    b = int(rng.integers(1, 4))
+    style = int(rng.integers(0, 4))
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    if c == 3:
+        x = torch.randn(b, 3, n, generator=g) * torch.tensor([1.0, 0.6, 0.3]).view(1, 3, 1)
+        if style == 1:
+            x = (x * 16).round() / 16          # many exact ties
+    else:
+        x = torch.randn(b, c, n, generator=g)
+        if style == 1:
+            x = torch.nn.functional.leaky_relu(x, 0.2) + 3.0        # far from the origin
+        elif style == 2:
+            z = torch.randn(b, 4, n, generator=g)
+            x = torch.randn(1, c, 4, generator=g) @ z               # low-rank manifold
+            x[:, :, ::53] *= 25.0                                   # outliers
+        elif style == 3:
+            x = (x * 4).round() / 4                                 # exact ties in feature space
+    x = x.contiguous()
+    idx, dist = neighbour_ops.knn_indices(x.to(dev), k, return_dist=True)
+    eidx, edist = oracle.knn(x.numpy(), k, return_dist=True)
+    cases += 1
+    if not (np.array_equal(idx.cpu().numpy(), eidx) and np.array_equal(dist.cpu().numpy(), edist)):
+        fails += 1
+        print("KNN MISMATCH", dict(c=c, n=n, k=k, b=b, style=style), flush=True)
+for it in range(12):
+    c = int(rng.choice([3, 8, 16, 64]))
+    cout = int(rng.choice([4, 8, 12, 32, 64, 128]))
+    n = int(rng.integers(30, 900))
+    k = int(rng.integers(1, min(26, n)))
+    b = int(rng.integers(1, 3))
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    x0 = torch.randn(b, c, n, generator=g)
+    idx = torch.randint(0, n, (b, n, k), generator=g)
+    w0 = torch.randn(cout, 2 * c, generator=g) / (2 * c) ** 0.5
+    g0, b0 = torch.randn(cout, generator=g), torch.randn(cout, generator=g) * 0.3
+    gout = torch.randn(b, cout, n, generator=g)
+    slope = [None, 0.0, 0.2][int(rng.integers(0, 3))]
+    xd = x0.to(dev).requires_grad_(True)
+    w, gm, bt = (t.to(dev).requires_grad_(True) for t in (w0, g0, b0))
+    out = edgeconv.edge_conv_max(xd, idx.to(dev), w, gm, bt, None, None, edgeconv.BN_TRAIN, 0.1, 1e-5, slope)
+    out.backward(gout.to(dev))
+    xr = x0.double().requires_grad_(True)
+    wr, gr, br = (t.double().requires_grad_(True) for t in (w0, g0, b0))
+    ref = edgeconv_ref.edge_conv_max(xr, idx, wr, gr, br, None, None, True, 0.1, 1e-5, slope)[0]
+    ref.backward(gout.double())
+    def rel(a, bb):
+        a, bb = a.detach().cpu().double(), bb.detach().double()
+        return float((a - bb).abs().max() / max(float(bb.abs().max()), 1e-30))
+    errs = [rel(out, ref), rel(xd.grad, xr.grad), rel(w.grad, wr.grad), rel(gm.grad, gr.grad), rel(bt.grad, br.grad)]
+    cases += 1
+    if errs[0] > 2e-5 or max(errs[1:]) > 2e-4:
+        fails += 1
+        # diagnostic: the smallest gap between the two best DISTINCT neighbours of any (point, channel) in float64 -- a gap
+        # below fp32 resolution means the arg-max itself is ambiguous in fp32 (the gradient then goes to another neighbour)
+        with torch.no_grad():
+            xx = x0.double()
+            ws = w0.double()
+            u = torch.einsum("oc,bcn->bno", ws[:, :c], xx)
+            v = torch.einsum("oc,bcn->bno", ws[:, c:] - ws[:, :c], xx)
+            y = torch.gather(u, 1, idx.reshape(b, n * k, 1).expand(-1, -1, cout)).view(b, n, k, cout) + v.unsqueeze(2)
+            sgn = torch.where(g0 >= 0, 1.0, -1.0).double()
+            ys = (y * sgn).sort(dim=2, descending=True)[0]
+            gaps = (ys[:, :, :1] - ys)                       # gap to the best, per slot
+            gaps = torch.where(gaps > 0, gaps, torch.full_like(gaps, 1e9)).min(dim=2)[0]
+            print("   smallest positive top-2 gap:", float(gaps.min()), "scale", float(y.abs().max()))
+        print("EDGECONV MISMATCH", dict(c=c, cout=cout, n=n, k=k, b=b, slope=slope), errs, flush=True)
+print(f"fuzz: {cases} cases, {fails} failures")
