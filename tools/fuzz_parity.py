@@ -83,4 +83,26 @@ for it in range(12):
             gaps = torch.where(gaps > 0, gaps, torch.full_like(gaps, 1e9)).min(dim=2)[0]
             print("   smallest positive top-2 gap:", float(gaps.min()), "scale", float(y.abs().max()))
         print("EDGECONV MISMATCH", dict(c=c, cout=cout, n=n, k=k, b=b, slope=slope), errs, flush=True)
+from pointcloudcounterfactual_b200.structural_losses.structural_losses_backend import NNDistance, NNDistanceGrad  # noqa: E402
+
+for it in range(20):
+    b = int(rng.integers(1, 5))
+    n, m = int(rng.integers(1, 3000)), int(rng.integers(1, 3000))
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    a, c2 = torch.randn(b, n, 3, generator=g), torch.randn(b, m, 3, generator=g)
+    if it % 3 == 1:
+        a, c2 = (a * 8).round() / 8, (c2 * 8).round() / 8      # exact ties: lowest index must win
+    d1, i1, d2, i2 = NNDistance(a.to(dev), c2.to(dev))
+    e1, j1, e2, j2 = oracle.nn_distance(a.numpy(), c2.numpy())
+    g1, g2 = torch.randn(b, n, generator=g), torch.randn(b, m, generator=g)
+    ga, gc = NNDistanceGrad(a.to(dev), c2.to(dev), i1, i2, g1.to(dev), g2.to(dev))
+    ea, ec = oracle.nn_distance_grad(a.numpy(), c2.numpy(), j1, j2, g1.numpy(), g2.numpy())
+    cases += 1
+    ok = (np.array_equal(d1.cpu().numpy(), e1) and np.array_equal(i1.cpu().numpy(), j1) and np.array_equal(d2.cpu().numpy(), e2)
+          and np.array_equal(i2.cpu().numpy(), j2))
+    scale = max(np.abs(ea).max(), np.abs(ec).max(), 1e-30)
+    ok = ok and np.abs(ga.cpu().numpy() - ea).max() / scale < 1e-5 and np.abs(gc.cpu().numpy() - ec).max() / scale < 1e-5
+    if not ok:
+        fails += 1
+        print("CHAMFER MISMATCH", dict(b=b, n=n, m=m, it=it), flush=True)
 print(f"fuzz: {cases} cases, {fails} failures")
