@@ -399,26 +399,38 @@ ec_bwd_stats_kernel(int cout, int nparts, double edges, int bn_mode, const doubl
 }
 
 // Edges sorted by TARGET, per cloud: off (n+1) run starts, rev (n*k, per-cloud stride padded to whole chunks) packed
-// (target << 19 | source << 6 | slot) -- 13 + 13 + 6 bits, n <= 8192, k <= 64 -- ascending inside each run.  Four small full-grid launches (histogram by integer atomics, per-cloud scan, fill, per-run rank sort); the
-// integer atomics make the order inside a run arbitrary, the rank sort fixes it again.
-__global__ void __launch_bounds__(256)
-ec_hist_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ cnt) {
-  const int cloud = blockIdx.y, total = n * k;
-  const int e = blockIdx.x * 256 + threadIdx.x;
-  if (e < total) atomicAdd(&cnt[(size_t)cloud * n + ec_clamp(idx[(size_t)cloud * total + e], n)], 1);
+// (target << 19 | source << 6 | slot) -- 13 + 13 + 6 bits, n <= 8192, k <= 64 -- ascending inside each run.
+constexpr int EC_PARTS = 8;  // the edges of a cloud are histogrammed / filled in EC_PARTS contiguous ranges, one CTA each
+
+// hist2[cloud][part][j] = edges of the part's range that point at j: shared-memory atomics only
+__global__ void __launch_bounds__(512)
+ec_hist_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ hist2) {
+  extern __shared__ int sc[];  // [n]
+  const int cloud = blockIdx.y, part = blockIdx.x, total = n * k;
+  const int per = (total + EC_PARTS - 1) / EC_PARTS;
+  const int e0 = min(part * per, total), e1 = min(e0 + per, total);
+  for (int j = threadIdx.x; j < n; j += 512) sc[j] = 0;
+  __syncthreads();
+  for (int e = e0 + threadIdx.x; e < e1; e += 512) atomicAdd(&sc[ec_clamp(idx[(size_t)cloud * total + e], n)], 1);
+  __syncthreads();
+  int *h = hist2 + ((size_t)cloud * EC_PARTS + part) * n;
+  for (int j = threadIdx.x; j < n; j += 512) h[j] = sc[j];
 }
 
+// off[j] = start of target j's run; base2[cloud][part][j] = where the part's entries for j begin inside that run
 __global__ void __launch_bounds__(1024)
-ec_scan_kernel(int n, int total, const int *__restrict__ cnt, int *__restrict__ off, int *__restrict__ cursor) {
+ec_scan_kernel(int n, int total, const int *__restrict__ hist2, int *__restrict__ off, int *__restrict__ base2) {
   __shared__ int wsum[32];
   const int cloud = blockIdx.x;
-  const int *c = cnt + (size_t)cloud * n;
-  int *offb = off + (size_t)cloud * (n + 1), *cur = cursor + (size_t)cloud * n;
+  const int *h = hist2 + (size_t)cloud * EC_PARTS * n;
+  int *offb = off + (size_t)cloud * (n + 1), *bs = base2 + (size_t)cloud * EC_PARTS * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunk = (n + 1023) / 1024;  // each thread owns a contiguous chunk
   const int j0 = threadIdx.x * chunk, j1 = min(n, j0 + chunk);
   int local = 0;
-  for (int j = j0; j < j1; ++j) local += c[j];
+  for (int j = j0; j < j1; ++j)
+#pragma unroll
+    for (int p = 0; p < EC_PARTS; ++p) local += h[(size_t)p * n + j];
   int incl = local;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -439,23 +451,32 @@ ec_scan_kernel(int n, int total, const int *__restrict__ cnt, int *__restrict__ 
   __syncthreads();
   int run = incl - local + (warp ? wsum[warp - 1] : 0);
   for (int j = j0; j < j1; ++j) {
-    cur[j] = run;
     offb[j] = run;
-    run += c[j];
+#pragma unroll
+    for (int p = 0; p < EC_PARTS; ++p) {
+      bs[(size_t)p * n + j] = run;
+      run += h[(size_t)p * n + j];
+    }
   }
   if (threadIdx.x == 0) offb[n] = total;
 }
 
-__global__ void __launch_bounds__(256)
-ec_fill_kernel(int n, int k, int stride, const int64_t *__restrict__ idx, int *__restrict__ cursor,
+// every part places its edges with shared-memory cursors that start at base2: no global atomics
+__global__ void __launch_bounds__(512)
+ec_fill_kernel(int n, int k, int stride, const int64_t *__restrict__ idx, const int *__restrict__ base2,
                unsigned int *__restrict__ rev_tmp) {
-  const int cloud = blockIdx.y, total = n * k;
-  const int e = blockIdx.x * 256 + threadIdx.x;
-  if (e >= total) return;
-  const int j = ec_clamp(idx[(size_t)cloud * total + e], n);
-  const int i = e / k, t = e - i * k;
-  rev_tmp[(size_t)cloud * stride + atomicAdd(&cursor[(size_t)cloud * n + j], 1)] =
-      ((unsigned int)j << 19) | ((unsigned int)i << 6) | (unsigned int)t;
+  extern __shared__ int sc[];  // [n] cursors
+  const int cloud = blockIdx.y, part = blockIdx.x, total = n * k;
+  const int per = (total + EC_PARTS - 1) / EC_PARTS;
+  const int e0 = min(part * per, total), e1 = min(e0 + per, total);
+  const int *bs = base2 + ((size_t)cloud * EC_PARTS + part) * n;
+  for (int j = threadIdx.x; j < n; j += 512) sc[j] = bs[j];
+  __syncthreads();
+  for (int e = e0 + threadIdx.x; e < e1; e += 512) {
+    const int j = ec_clamp(idx[(size_t)cloud * total + e], n);
+    const int i = e / k, t = e - i * k;
+    rev_tmp[(size_t)cloud * stride + atomicAdd(&sc[j], 1)] = ((unsigned int)j << 19) | ((unsigned int)i << 6) | (unsigned int)t;
+  }
 }
 
 // one thread per entry: its rank inside its target's run by counting (entries are distinct).  Entries of one run are
@@ -789,7 +810,7 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t part_bytes = up(sizeof(double) * 2 * cout * nparts), dz_bytes = up(sizeof(float) * (size_t)b * ec_nslice(cout) * n * 8),
                coef_bytes = up(sizeof(float) * 4 * cout), off_bytes = up(sizeof(int) * (size_t)b * (n + 1)),
-               cnt_bytes = up(sizeof(int) * (size_t)b * n), rev_bytes = up(sizeof(int) * (size_t)b * nchunks * EC_CHUNK),
+               cnt_bytes = up(sizeof(int) * (size_t)b * EC_PARTS * n), rev_bytes = up(sizeof(int) * (size_t)b * nchunks * EC_CHUNK),
                raw_bytes = up(sizeof(float) * (size_t)b * n * 2 * cout),
                pbuf_bytes = up(sizeof(float) * (size_t)b * nchunks * 2 * cout);
   char *ws = nullptr;
@@ -806,8 +827,8 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   float *dz = reinterpret_cast<float *>(take(dz_bytes));
   float *coef = reinterpret_cast<float *>(take(coef_bytes));
   int *off = reinterpret_cast<int *>(take(off_bytes));
-  int *cnt = reinterpret_cast<int *>(take(cnt_bytes));
-  int *cursor = reinterpret_cast<int *>(take(cnt_bytes));
+  int *hist2 = reinterpret_cast<int *>(take(cnt_bytes));
+  int *base2 = reinterpret_cast<int *>(take(cnt_bytes));
   unsigned int *rev_tmp = reinterpret_cast<unsigned int *>(take(rev_bytes));
   unsigned int *rev = reinterpret_cast<unsigned int *>(take(rev_bytes));
   const int estride = nchunks * EC_CHUNK;  // per-cloud stride of the edge lists
@@ -817,11 +838,10 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
                                              partials, nparts);
   ec_bwd_stats_kernel<<<cout, 128, 0, st>>>(cout, nparts, (double)b * n * k, bn_mode, partials, gamma, invstd,
                                             grad_gamma, grad_beta, coef);
-  const dim3 egrid((per_cloud + 255) / 256, b);
-  cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)b * n, st);
-  ec_hist_kernel<<<egrid, 256, 0, st>>>(n, k, idx, cnt);
-  ec_scan_kernel<<<b, 1024, 0, st>>>(n, per_cloud, cnt, off, cursor);
-  ec_fill_kernel<<<egrid, 256, 0, st>>>(n, k, estride, idx, cursor, rev_tmp);
+  const dim3 egrid((per_cloud + 255) / 256, b), pgrid(EC_PARTS, b);
+  ec_hist_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, idx, hist2);
+  ec_scan_kernel<<<b, 1024, 0, st>>>(n, per_cloud, hist2, off, base2);
+  ec_fill_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, estride, idx, base2, rev_tmp);
   ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, estride, off, rev_tmp, rev);
   const int groups = EC_THREADS / (cout >> 2);
   const dim3 cgrid((nchunks + groups - 1) / groups, b), grid((n + EC_PTS - 1) / EC_PTS, b);
