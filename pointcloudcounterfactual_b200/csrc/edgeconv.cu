@@ -479,20 +479,26 @@ ec_fill_kernel(int n, int k, int stride, const int64_t *__restrict__ idx, const 
   }
 }
 
-// one thread per entry: its rank inside its target's run by counting (entries are distinct).  Entries of one run are
-// neighbours in rev_tmp, so a warp walks one or two runs together (broadcast loads); hub targets (in-degree of several
-// hundred in feature space) are spread over many warps instead of serialising one.
+// one thread per entry: its final position by rank counting (entries are distinct).  The fill leaves every run as
+// EC_PARTS consecutive segments -- the parts are ranges of ascending edge ids -- so only the entry's own segment
+// [base2[part][j], base2[part+1][j]) has to be counted.  Entries of one segment are neighbours in rev_tmp, so a warp walks
+// one or two segments together (broadcast loads); hub targets (in-degree of several hundred in feature space) are
+// spread over many threads instead of serialising one.
 __global__ void __launch_bounds__(256)
-ec_sort_kernel(int n, int k, int stride, const int *__restrict__ off, const unsigned int *__restrict__ rev_tmp,
-               unsigned int *__restrict__ rev) {
+ec_sort_kernel(int n, int k, int stride, const int *__restrict__ off, const int *__restrict__ base2,
+               const unsigned int *__restrict__ rev_tmp, unsigned int *__restrict__ rev) {
   const int cloud = blockIdx.y, total = n * k;
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= total) return;
   const unsigned int *src = rev_tmp + (size_t)cloud * stride;
   const unsigned int mine = src[p];
   const int j = (int)(mine >> 19);
-  const int *offb = off + (size_t)cloud * (n + 1);
-  const int beg = offb[j], end = offb[j + 1];
+  const int e = (int)((mine >> 6) & 8191u) * k + (int)(mine & 63u);  // edge id = source * k + slot
+  const int per = (total + EC_PARTS - 1) / EC_PARTS;
+  const int part = e / per;
+  const int *bs = base2 + ((size_t)cloud * EC_PARTS + part) * n;
+  const int beg = bs[j];
+  const int end = part + 1 < EC_PARTS ? bs[n + j] : off[(size_t)cloud * (n + 1) + j + 1];
   int rank = 0;
   int s2 = beg;
   for (; s2 < end && (s2 & 3); ++s2) rank += (src[s2] < mine) ? 1 : 0;
@@ -842,7 +848,7 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   ec_hist_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, idx, hist2);
   ec_scan_kernel<<<b, 1024, 0, st>>>(n, per_cloud, hist2, off, base2);
   ec_fill_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, estride, idx, base2, rev_tmp);
-  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, estride, off, rev_tmp, rev);
+  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, estride, off, base2, rev_tmp, rev);
   const int groups = EC_THREADS / (cout >> 2);
   const dim3 cgrid((nchunks + groups - 1) / groups, b), grid((n + EC_PTS - 1) / EC_PTS, b);
   const bool staged = n <= EC_STAGE_MAX_N;
