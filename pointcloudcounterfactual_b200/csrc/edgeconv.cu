@@ -187,27 +187,27 @@ ec_reduce_staged_kernel(int n, int k, int cout, const float *__restrict__ uv, co
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, ext[4] = {NINF, NINF, NINF, NINF};
     int slot[4] = {0, 0, 0, 0};
     const unsigned short *nb = sidx + ps * k;
-    for (int t0 = 0; t0 < k; t0 += 4) {
+    auto edge = [&](const float4 u4, int t) {
+      const float y[4] = {u4.x + v[0], u4.y + v[1], u4.z + v[2], u4.w + v[3]};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (STATS) {
+          s1[c] += y[c];
+          s2[c] = fmaf(y[c], y[c], s2[c]);
+        }
+        slot[c] = y[c] > ext[c] ? t : slot[c];  // strict: the first slot wins a tie
+        ext[c] = fmaxf(ext[c], y[c]);
+      }
+    };
+    int t0 = 0;
+    for (; t0 + 4 <= k; t0 += 4) {  // four rows in flight, no bounds checks inside
       float4 u8[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) u8[u] = rows[2 * (int)nb[min(t0 + u, k - 1)] + qq];  // 4 rows in flight
+      for (int u = 0; u < 4; ++u) u8[u] = rows[2 * (int)nb[t0 + u] + qq];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int t = t0 + u;
-        if (t < k) {
-          const float y[4] = {u8[u].x + v[0], u8[u].y + v[1], u8[u].z + v[2], u8[u].w + v[3]};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (STATS) {
-              s1[c] += y[c];
-              s2[c] = fmaf(y[c], y[c], s2[c]);
-            }
-            slot[c] = y[c] > ext[c] ? t : slot[c];  // strict: the first slot wins a tie
-            ext[c] = fmaxf(ext[c], y[c]);
-          }
-        }
-      }
+      for (int u = 0; u < 4; ++u) edge(u8[u], t0 + u);
     }
+    for (; t0 < k; ++t0) edge(rows[2 * (int)nb[t0] + qq], t0);
     const size_t o = ((size_t)cloud * n + i) * cout + 4 * quad;
     *reinterpret_cast<float4 *>(exty + o) = make_float4(ext[0] * sg[0], ext[1] * sg[1], ext[2] * sg[2], ext[3] * sg[3]);
     *reinterpret_cast<uchar4 *>(slot_out + ec_sl(cloud, n, cout, i, 4 * quad)) =
