@@ -587,8 +587,10 @@ ec_bwd_chunk_kernel(int n, int k, int cout, int nchunks, const float *__restrict
 // The same segmented sum with the per-edge operands served from SHARED memory: a CTA owns one slice of 8 channels of one
 // cloud, stages that slice of v (32 B per point) and of slot (8 B per point) and walks all chunks of the cloud's edge
 // list.  thread = (chunk slot, quad of the slice).
+constexpr int EC_CTHREADS = 1024;  // the chunk kernel's slice buffers allow one CTA per SM: make it a large one
+
 template <bool TRAIN>
-__global__ void __launch_bounds__(EC_STHREADS)
+__global__ void __launch_bounds__(EC_CTHREADS)
 ec_bwd_chunk_staged_kernel(int n, int k, int cout, int nchunks, const float *__restrict__ uv,
                            const unsigned int *__restrict__ rev, const float *__restrict__ dz,
                            const unsigned char *__restrict__ slot, float *__restrict__ raw, float *__restrict__ pbuf) {
@@ -601,7 +603,7 @@ ec_bwd_chunk_staged_kernel(int n, int k, int cout, int nchunks, const float *__r
   const float *uvb = uv + (size_t)cloud * n * 2 * cout;
   const uchar4 *gslot = reinterpret_cast<const uchar4 *>(slot + ec_sl(cloud, n, cout, 0, 8 * slice));
   const float4 *gdz = reinterpret_cast<const float4 *>(dz + ec_sl(cloud, n, cout, 0, 8 * slice));
-  for (int e = threadIdx.x; e < 2 * n; e += EC_STHREADS) {
+  for (int e = threadIdx.x; e < 2 * n; e += EC_CTHREADS) {
     const bool ok = 2 * slice + (e & 1) < nquad;
     rows[e] = ok ? gdz[e] : make_float4(0.f, 0.f, 0.f, 0.f);
     if (TRAIN)
@@ -616,7 +618,7 @@ ec_bwd_chunk_staged_kernel(int n, int k, int cout, int nchunks, const float *__r
   if (quad >= nquad) return;
   const int total = n * k;
   const size_t pbase = (size_t)cloud * n;
-  for (int q = cs; q < nchunks; q += EC_SPTS) {
+  for (int q = cs; q < nchunks; q += EC_CTHREADS / 2) {
     const int pos0 = q * EC_CHUNK, cnt = min(EC_CHUNK, total - pos0);
     const unsigned int *revb = rev + (size_t)cloud * nchunks * EC_CHUNK + pos0;  // 128-byte aligned chunk
     // the chunk's 32 entries: eight 16-byte loads issued together (the padding past the list is allocated)
@@ -868,12 +870,12 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
     }
   }
   if (staged && bn_mode == EC_BN_TRAIN) {
-    ec_bwd_chunk_staged_kernel<true><<<sgrid, EC_STHREADS, (size_t)n * 72, st>>>(n, k, cout, nchunks, uv, rev, dz, slot,
+    ec_bwd_chunk_staged_kernel<true><<<sgrid, EC_CTHREADS, (size_t)n * 72, st>>>(n, k, cout, nchunks, uv, rev, dz, slot,
                                                                                 raw, pbuf);
     ec_bwd_finish_kernel<true><<<grid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, off, raw, pbuf, dz, sy, mean, coef,
                                                             grad_uv);
   } else if (staged) {
-    ec_bwd_chunk_staged_kernel<false><<<sgrid, EC_STHREADS, (size_t)n * 40, st>>>(n, k, cout, nchunks, uv, rev, dz, slot,
+    ec_bwd_chunk_staged_kernel<false><<<sgrid, EC_CTHREADS, (size_t)n * 40, st>>>(n, k, cout, nchunks, uv, rev, dz, slot,
                                                                                 raw, pbuf);
     ec_bwd_finish_kernel<false><<<grid, EC_THREADS, 0, st>>>(n, k, cout, nchunks, uv, off, raw, pbuf, dz, sy, mean,
                                                              coef, grad_uv);
