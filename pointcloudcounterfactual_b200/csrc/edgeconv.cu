@@ -649,13 +649,14 @@ ec_bwd_chunk_staged_kernel(int n, int k, int cout, int nchunks, const float *__r
         }
         const int i = (int)((w[u] >> 6) & 8191u);
         const unsigned int t = w[u] & 63u;
-        const uchar4 s4 = sslot[2 * i + qq];
-        if (s4.x == t || s4.y == t || s4.z == t || s4.w == t) {  // ~4 in k quads: dz is read where it lands
+        const unsigned int s4 = reinterpret_cast<const unsigned int *>(sslot)[2 * i + qq];
+        const unsigned int hit = __vcmpeq4(s4, t * 0x01010101u);  // 0xff in the bytes whose slot is t
+        if (hit) {  // ~4 in k quads: dz is read where it lands
           const float4 d4 = sdz[2 * i + qq];
-          gd[0] += (s4.x == t) ? d4.x : 0.f;
-          gd[1] += (s4.y == t) ? d4.y : 0.f;
-          gd[2] += (s4.z == t) ? d4.z : 0.f;
-          gd[3] += (s4.w == t) ? d4.w : 0.f;
+          gd[0] += (hit & 0x000000ffu) ? d4.x : 0.f;
+          gd[1] += (hit & 0x0000ff00u) ? d4.y : 0.f;
+          gd[2] += (hit & 0x00ff0000u) ? d4.z : 0.f;
+          gd[3] += (hit & 0xff000000u) ? d4.w : 0.f;
         }
         if (TRAIN) {
           const float4 v4 = sv[2 * i + qq];
