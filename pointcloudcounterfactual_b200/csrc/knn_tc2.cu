@@ -38,8 +38,10 @@ struct T2 {
   static constexpr int THREADS = 64 + 32 * NEPI;       // warp 0 = TMA, warp 1 = MMA
   static constexpr int A_BYTES = KB * QUERIES * 128;   // query tile: KB blocks of [QUERIES][32 floats]
   static constexpr int B_BYTES = KB * R * 128;         // one key stage
-  static constexpr int CAP = 56;                       // candidate slots per query
-  static constexpr int W = 85;                         // words per query record: CAP distances + CAP/2 packed indices,
+  // candidate slots per query: 56 where two M-tiles share the CTA (the records of 256 queries must fit next to the
+  // operand tiles), 112 where one does -- fewer lists reach the prune path (a serial insertion sort) on the way
+  static constexpr int CAP = HALVES == 1 ? 112 : 56;
+  static constexpr int W = HALVES == 1 ? 169 : 85;     // words per query record: CAP distances + CAP/2 packed indices,
                                                        // >= 64 (sweep 1 keeps the group minima there), odd (banks)
   static constexpr int PCAP = 192;                     // (query, key) pairs per warp and tile
   static constexpr int CHUNKS = R / 32;                // 32-column TMEM loads per tile
@@ -266,6 +268,29 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       reinterpret_cast<unsigned short *>(r + CAP)[slot] = (unsigned short)j;
     };
 
+    // keeps the k best (distance, index) entries of this query's list, in order, and tightens the threshold with the
+    // k-th best exact distance so far: a key of the final top-k has a true score <= rd[k-1] - |x_q|^2, so its lower bound
+    // (which dropped c2 |x_q|^2) is <= rd[k-1] - |x_q|^2 + c2 |x_q|^2
+    auto prune_to_k = [&]() {
+      float *rd = reinterpret_cast<float *>(rec);
+      unsigned short *rix = reinterpret_cast<unsigned short *>(rec + CAP);
+      for (int s1 = 1; s1 < cnt; ++s1) {
+        const float vd = rd[s1];
+        const unsigned short vi = rix[s1];
+        int p = s1;
+        while (p > 0 && (rd[p - 1] > vd || (rd[p - 1] == vd && rix[p - 1] > vi))) {
+          rd[p] = rd[p - 1];
+          rix[p] = rix[p - 1];
+          --p;
+        }
+        rd[p] = vd;
+        rix[p] = vi;
+      }
+      cnt = k;
+      const float tk = rd[k - 1] - nq + c2nq;
+      thr = fminf(thr, tk * (tk > 0.f ? 1.000001f : 0.999999f) + 1e-30f);
+    };
+
     for (int i = 0; i < niter; ++i) {
       const int s = i & 1, par = (i >> 1) & 1;
       const bool second = i >= ntile;
@@ -370,27 +395,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         // a list that would overflow is first pruned to its k best entries (exact distances, so nothing is lost);
         // only a tile with more than CAP - k candidates of one query (massive ties) defeats this
-        if (cnt <= CAP && cnt + c_l > CAP && cnt > k) {
-          float *rd = reinterpret_cast<float *>(rec);
-          unsigned short *rix = reinterpret_cast<unsigned short *>(rec + CAP);
-          for (int s1 = 1; s1 < cnt; ++s1) {
-            const float vd = rd[s1];
-            const unsigned short vi = rix[s1];
-            int p = s1;
-            while (p > 0 && (rd[p - 1] > vd || (rd[p - 1] == vd && rix[p - 1] > vi))) {
-              rd[p] = rd[p - 1];
-              rix[p] = rix[p - 1];
-              --p;
-            }
-            rd[p] = vd;
-            rix[p] = vi;
-          }
-          cnt = k;
-          // the k-th best exact distance so far bounds the final one: a key of the final top-k has a true score
-          // <= rd[k-1] - |x_q|^2, so its lower bound (which dropped c2 |x_q|^2) is <= rd[k-1] - |x_q|^2 + c2 |x_q|^2
-          const float tk = rd[k - 1] - nq + c2nq;
-          thr = fminf(thr, tk * (tk > 0.f ? 1.000001f : 0.999999f) + 1e-30f);
-        }
+        if (cnt <= CAP && cnt + c_l > CAP && cnt > k) prune_to_k();
         __syncwarp();
         // ---- (query, key) pairs of the whole warp, compacted so that the exact re-rank is spread evenly over the
         //      lanes (the candidates of one query differ a lot from tile to tile) ----
@@ -442,6 +447,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
     }
 
+    if (CAP > 64 && cnt > 64 && cnt <= CAP) prune_to_k();  // the ranking below holds two candidates per lane
     // ---- ranking, one query of the warp at a time, one candidate per lane.  d >= 0, so the bit patterns order like the
     //      values.  Without exact ties the strict ranks are a permutation (their sum is c(c-1)/2). ----
     __syncwarp();

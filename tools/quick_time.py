@@ -58,3 +58,9 @@ if "gfilt" in want:
         torch.autograd.grad(o, xg, o)
 
     print(json.dumps({"graph_filtering_fwd_bwd_us": graph_time(gf)}))
+if "knn2048" in want:
+    o = {}
+    for c in (64, 128):
+        xx = synthetic.knn_features(32, c, 2048).to(dev)
+        o[f"knn_feat{c}_k25_n2048_us"] = graph_time(lambda: neighbour_ops.knn(xx, 25), 10)
+    print(json.dumps(o))
