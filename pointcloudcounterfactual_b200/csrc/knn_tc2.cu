@@ -160,7 +160,8 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const int q0 = blockIdx.x * Q;
   const int ntile = npad / R;
   const int niter = 2 * ntile;
-  const bool fine = ntile * CHUNKS <= 32;  // group minima over 16 instead of 32 keys while at most 64 groups result
+  // group minima over 16 instead of 32 keys while the query record holds them (64 values, 128 with the long records)
+  const bool fine = ntile * CHUNKS * 2 <= (W >= 128 ? 128 : 64);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -324,7 +325,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             else
               mhi = fminf(fminf(z0, z1), fminf(fminf(z2, z3), mhi));
           }
-          if (fine) {  // n <= 1024: 64 groups of 16 (tighter tau, fewer candidates to re-rank)
+          if (fine) {  // groups of 16 keys (tighter tau, fewer candidates to re-rank)
             rec[(t * CHUNKS + ch) * 2] = __float_as_uint(mlo);
             rec[(t * CHUNKS + ch) * 2 + 1] = __float_as_uint(mhi);
           } else {
@@ -338,16 +339,16 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           mbar_arrive(&ctl->empty[s]);
         }
         if (i == ntile - 1) {
-          // ---- tau = k-th smallest of the ng <= 64 group minima (at least k groups hold a key with score <= tau) ----
+          // ---- tau = k-th smallest of the ng <= 128 group minima (at least k groups hold a key with score <= tau) ----
           const int ng = ntile * CHUNKS * (fine ? 2 : 1);
           float a[32];
 #pragma unroll
           for (int u = 0; u < 32; ++u) a[u] = (u < ng) ? __uint_as_float(rec[u]) : INF;
           bitonic_sort_regs<32>(a);
-          if (ng > 32) {
+          for (int blk = 32; blk < ng; blk += 32) {  // fold in the next 32 minima: keep the 32 smallest of both
             float b2[32];
 #pragma unroll
-            for (int u = 0; u < 32; ++u) b2[u] = (32 + u < ng) ? __uint_as_float(rec[32 + u]) : INF;
+            for (int u = 0; u < 32; ++u) b2[u] = (blk + u < ng) ? __uint_as_float(rec[blk + u]) : INF;
             bitonic_sort_regs<32>(b2);
 #pragma unroll
             for (int u = 0; u < 32; ++u) a[u] = fminf(a[u], b2[31 - u]);  // the 32 smallest of both, a bitonic sequence
