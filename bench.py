@@ -45,6 +45,7 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--eager", action="store_true", help="time the steps with eager launches instead of GraphedLossStep")
+    p.add_argument("--no-pipeline", action="store_true", help="end-to-end leg without the copy-stream pipelining")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--no-sub", action="store_true", help="skip sub-metrics (Chamfer-only, EMD-only, kNN)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -242,14 +243,39 @@ def run_b200(args) -> None:
     value = world * B_PER_GPU * K / (total_ms * 1e-3)
 
     # ---- e2e: pinned host inputs -> device -> loss back on the host, every step ------------------------------
-    for _ in range(W):
-        step_e2e()
+    e2e_pipe = None
+    if graphed is not None and not args.no_pipeline:
+        try:  # the same graphed step fed through a copy stream: step i+1's clouds travel while step i computes
+            e2e_pipe = losses.PipelinedLossStep(losses.chamfer_emd, recon_h, ref_h, dev)
+        except Exception as e:  # noqa: BLE001
+            torch.cuda.synchronize()
+            print(f"[bench] pipelined e2e refused ({type(e).__name__}: {e}); unpipelined graph", file=sys.stderr)
+
+    def run_e2e(nsteps):
+        if e2e_pipe is None:
+            for _ in range(nsteps):
+                step_e2e()
+            while e2e_pending:
+                float(e2e_pending.pop(0).wait().cpu())  # the last global mean arrives inside the timed region
+            return
+        e2e_pipe.prefetch()  # H2D of the first step's clouds
+        host_values = []
+        for _ in range(nsteps):
+            prev = e2e_pipe.step()  # launches this step (graph), starts the next step's H2D, returns the previous loss
+            e2e_pending.append(sharding.global_mean_loss_async(e2e_pipe.loss_device))
+            if prev is not None:
+                host_values.append(float(prev[0]))  # the previous step's per-cloud loss, read on the host
+            if len(e2e_pending) > 1:
+                float(e2e_pending.pop(0).wait().cpu())
+        host_values.append(float(e2e_pipe.drain()[0]))
+        while e2e_pending:
+            float(e2e_pending.pop(0).wait().cpu())
+        assert len(host_values) == nsteps
+
+    run_e2e(W)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        step_e2e()
-    while e2e_pending:
-        float(e2e_pending.pop(0).wait().cpu())  # the last global mean arrives inside the timed region
+    run_e2e(K)
     barrier()
     e2e_s = reduce_max(time.perf_counter() - t0)
     e2e_value = world * B_PER_GPU * K / e2e_s
@@ -548,7 +574,10 @@ def run_b200(args) -> None:
                        else "eager"},
             "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pinned host clouds -> H2D -> chamfer_emd fwd+bwd -> loss D2H each step, host wall clock; "
-                            + ("the step is losses.GraphedLossStep (copies + kernels captured as one CUDA graph)"
+                            + ("the step is losses.PipelinedLossStep: one CUDA-graph launch per step, step i+1's H2D on a "
+                               "copy stream while step i computes, step i's loss read on the host during step i+1"
+                               if e2e_pipe is not None else
+                               "the step is losses.GraphedLossStep (copies + kernels captured as one CUDA graph)"
                                if graphed is not None else "eager launches")},
             "gpu_launches": int(launches),
             "roofline": roofline,

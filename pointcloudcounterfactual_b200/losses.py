@@ -98,8 +98,10 @@ class GraphedLossStep:
     device buffers to refill.  ``loss_device`` holds the per-cloud loss on the device (e.g. for
     ``sharding.global_mean_loss_async``)."""
 
-    def __init__(self, loss_fn, recon: torch.Tensor, ref: torch.Tensor, device: torch.device, warmup: int = 2):
+    def __init__(self, loss_fn, recon: torch.Tensor, ref: torch.Tensor, device: torch.device, warmup: int = 2,
+                 staged: bool = False):
         self.device = torch.device(device)
+        self._staged = staged  # device inputs are staging buffers: the graph starts by copying them (PipelinedLossStep)
         self._from_host = not recon.is_cuda
         if self._from_host and not (recon.is_pinned() and ref.is_pinned()):
             raise RuntimeError("GraphedLossStep needs pinned host tensors (the copies are part of the graph)")
@@ -126,7 +128,7 @@ class GraphedLossStep:
             self.kernels_per_replay = L.launch_count() - n0  # libpcc_b200 kernels inside one replay
 
     def _body(self, loss_fn) -> None:
-        if self._from_host:
+        if self._from_host or self._staged:
             with torch.no_grad():
                 self.recon.copy_(self._recon_h, non_blocking=True)
                 self.ref.copy_(self._ref_h, non_blocking=True)
@@ -141,3 +143,68 @@ class GraphedLossStep:
 
     def synchronize(self) -> None:
         torch.cuda.current_stream(self.device).synchronize()
+
+
+class PipelinedLossStep:
+    """``GraphedLossStep`` with the host-to-device copies taken off the critical path: two device staging buffers and two
+    captured graphs alternate, and while the graph of step i runs, the pinned host clouds of step i+1 travel to the
+    other staging buffer on a copy stream.  Every step still moves its inputs host -> device and its per-cloud loss
+    device -> host; only the waiting is overlapped.  Usage::
+
+        pipe = PipelinedLossStep(chamfer_emd, recon_host, ref_host, device)   # pinned host tensors
+        pipe.prefetch()                    # copies for the first step
+        for batch in loader:
+            loss_prev = pipe.step()        # runs the step whose inputs were prefetched, prefetches the next one from the
+            ...                            # pinned buffers (refill them after step() returns), returns the PREVIOUS
+        last = pipe.drain()                # step's per-cloud loss on the host (None on the first call)
+    """
+
+    def __init__(self, loss_fn, recon_host: torch.Tensor, ref_host: torch.Tensor, device: torch.device):
+        if not (recon_host.is_pinned() and ref_host.is_pinned()):
+            raise RuntimeError("PipelinedLossStep needs pinned host tensors")
+        self.device = torch.device(device)
+        self._recon_h, self._ref_h = recon_host, ref_host
+        with torch.cuda.device(self.device):
+            self._copy = torch.cuda.Stream(self.device)
+            self._stage = [(torch.empty(recon_host.shape, dtype=recon_host.dtype, device=self.device),
+                            torch.empty(ref_host.shape, dtype=ref_host.dtype, device=self.device)) for _ in range(2)]
+            self._steps = [GraphedLossStep(loss_fn, a, b, self.device, staged=True) for a, b in self._stage]
+            self._ready = [torch.cuda.Event() for _ in range(2)]   # staging buffer filled
+            self._done = [torch.cuda.Event() for _ in range(2)]    # graph finished (staging free, loss on the host)
+        self._next = 0        # staging buffer the next prefetch fills
+        self._pending = None  # index of the step whose loss has not been returned yet
+        self.kernels_per_replay = self._steps[0].kernels_per_replay
+        self.grad = None
+        self.loss_device = None
+
+    def prefetch(self) -> None:
+        i = self._next
+        self._copy.wait_event(self._done[i])  # the graph that read this staging buffer last has finished
+        with torch.cuda.stream(self._copy):
+            self._stage[i][0].copy_(self._recon_h, non_blocking=True)
+            self._stage[i][1].copy_(self._ref_h, non_blocking=True)
+            self._ready[i].record(self._copy)
+
+    def step(self):
+        i = self._next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._ready[i])
+        _, self.grad = self._steps[i]()
+        self.loss_device = self._steps[i].loss_device
+        self._done[i].record(cur)
+        self._next = 1 - i
+        self.prefetch()  # the next step's inputs travel while this step computes
+        prev = self._collect()
+        self._pending = i
+        return prev
+
+    def _collect(self):
+        if self._pending is None:
+            return None
+        self._done[self._pending].synchronize()
+        return self._steps[self._pending].loss_host
+
+    def drain(self):
+        out = self._collect()
+        self._pending = None
+        return out

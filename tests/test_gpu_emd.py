@@ -156,3 +156,30 @@ def test_graphed_loss_step_device_resident(cuda):
     want = losses.chamfer_emd(r, c2.to(cuda))
     (gw,) = torch.autograd.grad(want.sum(), r)
     assert torch.equal(loss_h, want.detach().cpu()) and torch.equal(grad.cpu(), gw.cpu())
+
+
+def test_pipelined_loss_step_equals_eager(cuda):
+    """losses.PipelinedLossStep: two staging buffers / two graphs alternate, the next step's H2D overlaps the current
+    step; every step's loss and gradient equal the eager ones, and the losses come back one step late, in order."""
+    b, n = 2, 384
+    rh = torch.empty(b, n, 3).pin_memory()
+    th = torch.empty(b, n, 3).pin_memory()
+    batches = [synthetic.s1_near(b, n, first=3 * i) for i in range(5)]
+    rh.copy_(batches[0][0]), th.copy_(batches[0][1])
+    pipe = losses.PipelinedLossStep(losses.chamfer_emd, rh, th, cuda)
+    pipe.prefetch()
+    got_losses, got_grads = [], []
+    for i in range(5):
+        torch.cuda.synchronize()  # the prefetch of batch i has read the pinned buffers: refill them for batch i+1
+        if i + 1 < 5:
+            rh.copy_(batches[i + 1][0]), th.copy_(batches[i + 1][1])
+        prev = pipe.step()
+        got_grads.append(pipe.grad.clone())
+        if prev is not None:
+            got_losses.append(prev.clone())
+    got_losses.append(pipe.drain().clone())
+    for (a, c), lo, gr in zip(batches, got_losses, got_grads):
+        r = a.to(cuda).requires_grad_(True)
+        want = losses.chamfer_emd(r, c.to(cuda))
+        (gw,) = torch.autograd.grad(want.sum(), r)
+        assert torch.equal(lo, want.detach().cpu()) and torch.equal(gr.cpu(), gw.cpu())
