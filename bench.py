@@ -132,7 +132,7 @@ def run_b200(args) -> None:
     import torch.distributed as dist
 
     from pointcloudcounterfactual_b200 import _lib, edgeconv, losses, neighbour_ops, sharding, synthetic
-    from pointcloudcounterfactual_b200.structural_losses import match_cost, nn_distance
+    from pointcloudcounterfactual_b200.structural_losses import match_cost
     from pointcloudcounterfactual_b200.structural_losses.structural_losses_backend import NNDistance
 
     if not torch.cuda.is_available():
