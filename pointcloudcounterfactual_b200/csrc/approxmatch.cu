@@ -27,6 +27,7 @@ constexpr float AM_LOG2E = 1.4426950408889634f;  // 0f3FB8AA3B, the constant __e
 enum { EPI_RATIO_L = 0, EPI_RATIO_R = 1, EPI_REMAIN_L = 2 };
 
 __global__ void am_init_kernel(int n, int m, float *__restrict__ temp, float multiL, float multiR) {
+  pdl_enter();
   // temp per cloud: [remainL(n) | remainR(m) | ratioL(n) | ratioR(m)]   (approxmatch.cu:4,19-21)
   float *t = temp + (size_t)blockIdx.y * (size_t)(n + m) * 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n + m; i += gridDim.x * blockDim.x)
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(AM_THREADS)
 am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
                 const float *__restrict__ wQ, size_t wQ_stride, float level, float *__restrict__ remainP,
                 size_t remain_stride, float *__restrict__ ratioP, size_t ratio_stride) {
+  pdl_wait();
   constexpr int H = AM_P / 2, U = UNROLL;
   __shared__ float4 tile[AM_QTILE];  // (x, y, z, w) per partner
   const size_t cloud = blockIdx.y;
@@ -133,6 +135,7 @@ am_sweep_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__res
       }
     }
   }
+  pdl_trigger();
 #pragma unroll
   for (int h = 0; h < H; ++h) {
     float s[2];
@@ -170,6 +173,7 @@ am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__r
                   size_t remainR_stride, float levelA, float levelB, float *__restrict__ remainL,
                   size_t remainL_stride, const float *__restrict__ ratioL_A, float *__restrict__ ratioL_B,
                   size_t ratioL_stride) {
+  pdl_wait();
   __shared__ float4 tile[AM_QTILE];  // (x, y, z, ratioR_A) per partner
   __shared__ float wB[AM_QTILE];     // remainR per partner
   const size_t cloud = blockIdx.y;
@@ -224,6 +228,7 @@ am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__r
       }
     }
   }
+  pdl_trigger();
 #pragma unroll
   for (int h = 0; h < AM_P / 2; ++h) {
     float s3[2], s1[2];
@@ -349,6 +354,7 @@ __global__ void __launch_bounds__(AM_THREADS)
 am_costgrad_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
                    const float *__restrict__ fP, const float *__restrict__ fQ, size_t fP_level_stride,
                    size_t fQ_level_stride, AmLevels sc, float *__restrict__ cost_part, float *__restrict__ gradP) {
+  pdl_wait();
   __shared__ float4 tile[AMF_QTILE / 2 * AMF_F4_PER_PAIR];
   __shared__ float red[AM_THREADS / 32];
   const size_t cloud = blockIdx.y;
@@ -392,6 +398,7 @@ am_costgrad_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__
       gz = fma2(u, dz, gz);
     }
   }
+  pdl_trigger();
   float c0, c1, x0, x1, y0, y1, z0, z1;
   unpack2(cst, c0, c1);
   unpack2(gx, x0, x1);
@@ -418,6 +425,7 @@ am_costgrad_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__
 }
 
 __global__ void am_cost_reduce_kernel(int b, int parts, const float *__restrict__ cost_part, float *__restrict__ cost) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b) return;
   float s = 0.f;
@@ -427,6 +435,7 @@ __global__ void am_cost_reduce_kernel(int b, int parts, const float *__restrict_
 
 __global__ void am_export_temp_kernel(int n, int m, const float *__restrict__ fL_last, const float *__restrict__ fR_last,
                                       float *__restrict__ temp) {
+  pdl_enter();
   // temp's ratioL / ratioR slots receive the last level's vectors, as the reference leaves them (approxmatch.cu:4)
   float *t = temp + (size_t)blockIdx.y * (size_t)(n + m) * 2 + (n + m);
   const float *l = fL_last + (size_t)blockIdx.y * n, *r = fR_last + (size_t)blockIdx.y * m;
@@ -613,7 +622,7 @@ static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, f
   }
   const size_t tstride = (size_t)(n + m) * 2;
   float *remainL = temp, *remainR = temp + n;
-  am_init_kernel<<<dim3((n + m + 255) / 256, b), 256, 0, st>>>(n, m, temp, multiL, multiR);
+  PCC_LAUNCH(PDL_EMD_SMALL, am_init_kernel, dim3((n + m + 255) / 256, b), 256, 0, st, n, m, temp, multiL, multiR);
   constexpr int P = AM_P_DEFAULT;
   const int per_cta = AM_THREADS * P;
   const dim3 gk((n + per_cta - 1) / per_cta, b), gl((m + per_cta - 1) / per_cta, b);
@@ -623,22 +632,20 @@ static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, f
   auto fR = [&](int t) { return ws.fR + (size_t)t * ws.fR_level_stride; };
   for (int t = 0; t < AM_LEVELS; ++t) {
     if (t == 0) {
-      am_sweep_kernel<EPI_RATIO_L, P><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, remainR, tstride, lv.lv[0], remainL,
-                                                                 tstride, fL(0), (size_t)n);
+      PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_RATIO_L, P>), gk, AM_THREADS, 0, st, n, m, xyz1, xyz2, remainR,
+                 tstride, lv.lv[0], remainL, tstride, fL(0), (size_t)n);
     } else {
-      am_sweep31_kernel<P><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, fR(t - 1), (size_t)m, remainR, tstride,
-                                                      lv.lv[t - 1], lv.lv[t], remainL, tstride, fL(t - 1), fL(t),
-                                                      (size_t)n);
+      PCC_LAUNCH(PDL_EMD_SWEEP, am_sweep31_kernel<P>, gk, AM_THREADS, 0, st, n, m, xyz1, xyz2, fR(t - 1), (size_t)m,
+                 remainR, tstride, lv.lv[t - 1], lv.lv[t], remainL, tstride, fL(t - 1), fL(t), (size_t)n);
     }
-    am_sweep_kernel<EPI_RATIO_R, P><<<gl, AM_THREADS, 0, st>>>(m, n, xyz2, xyz1, fL(t), (size_t)n, lv.lv[t], remainR,
-                                                               tstride, fR(t), (size_t)m);
+    PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_RATIO_R, P>), gl, AM_THREADS, 0, st, m, n, xyz2, xyz1, fL(t),
+               (size_t)n, lv.lv[t], remainR, tstride, fR(t), (size_t)m);
   }
-  am_sweep_kernel<EPI_REMAIN_L, P><<<gk, AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, fR(AM_LEVELS - 1), (size_t)m,
-                                                              lv.lv[AM_LEVELS - 1], remainL, tstride, fL(AM_LEVELS - 1),
-                                                              (size_t)n);
-  am_export_temp_kernel<<<dim3((n + m + 255) / 256, b), 256, 0, st>>>(
-      n, m, ws.fL + (size_t)(AM_LEVELS - 1) * ws.fL_level_stride, ws.fR + (size_t)(AM_LEVELS - 1) * ws.fR_level_stride,
-      temp);
+  PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_REMAIN_L, P>), gk, AM_THREADS, 0, st, n, m, xyz1, xyz2,
+             fR(AM_LEVELS - 1), (size_t)m, lv.lv[AM_LEVELS - 1], remainL, tstride, fL(AM_LEVELS - 1), (size_t)n);
+  PCC_LAUNCH(PDL_EMD_SMALL, am_export_temp_kernel, dim3((n + m + 255) / 256, b), 256, 0, st, n, m,
+             ws.fL + (size_t)(AM_LEVELS - 1) * ws.fL_level_stride, ws.fR + (size_t)(AM_LEVELS - 1) * ws.fR_level_stride,
+             temp);
   *launches += 2 + 2 * AM_LEVELS + 1;
   return (int)cudaGetLastError();
 }
@@ -690,17 +697,16 @@ extern "C" __attribute__((visibility("default"))) int pcc_matchcost_fused(int b,
   const int parts = (n + AM_THREADS - 1) / AM_THREADS;
   int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, (size_t)b * parts, sc, st, &launches);
   if (rc == 0) {
-    am_costgrad_kernel<<<dim3(parts, b), AM_THREADS, 0, st>>>(n, m, xyz1, xyz2, ws.fL, ws.fR, ws.fL_level_stride,
-                                                              ws.fR_level_stride, sc, cost ? ws.cost_part : nullptr,
-                                                              grad1);
+    PCC_LAUNCH(PDL_EMD_SWEEP, am_costgrad_kernel, dim3(parts, b), AM_THREADS, 0, st, n, m, xyz1, xyz2, ws.fL, ws.fR,
+               ws.fL_level_stride, ws.fR_level_stride, sc, cost ? ws.cost_part : nullptr, grad1);
     ++launches;
     if (cost) {
-      am_cost_reduce_kernel<<<(b + 127) / 128, 128, 0, st>>>(b, parts, ws.cost_part, cost);
+      PCC_LAUNCH(PDL_EMD_SMALL, am_cost_reduce_kernel, (b + 127) / 128, 128, 0, st, b, parts, ws.cost_part, cost);
       ++launches;
     }
     if (grad2) {
-      am_costgrad_kernel<<<dim3((m + AM_THREADS - 1) / AM_THREADS, b), AM_THREADS, 0, st>>>(
-          m, n, xyz2, xyz1, ws.fR, ws.fL, ws.fR_level_stride, ws.fL_level_stride, sc, nullptr, grad2);
+      PCC_LAUNCH(PDL_EMD_SWEEP, am_costgrad_kernel, dim3((m + AM_THREADS - 1) / AM_THREADS, b), AM_THREADS, 0, st, m, n,
+                 xyz2, xyz1, ws.fR, ws.fL, ws.fR_level_stride, ws.fL_level_stride, sc, (float *)nullptr, grad2);
       ++launches;
     }
     rc = (int)cudaGetLastError();

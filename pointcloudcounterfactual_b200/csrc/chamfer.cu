@@ -186,6 +186,7 @@ struct NnPart {
 __global__ void __launch_bounds__(NS_THREADS, 4)
 nn_sym_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2, int nrb, int ncc,
               NnPart *__restrict__ rowpart, NnPart *__restrict__ colpart) {
+  pdl_enter();
   __shared__ float4 tile[NS_CCOLS / 4 * 3];  // groups of 4 columns: X, Y, Z
   __shared__ __align__(16) float cval[NS_CCOLS];  // per column: minimum over this CTA's rows
   __shared__ __align__(16) int cloc[NS_CCOLS];    //             lowest lane attaining it
@@ -311,6 +312,7 @@ nn_sym_finalize_kernel(int n, const float *__restrict__ xyz1, int m, const float
                        const NnPart *__restrict__ rowpart, const NnPart *__restrict__ colpart,
                        float *__restrict__ dist1, int *__restrict__ idx1, float *__restrict__ dist2,
                        int *__restrict__ idx2) {
+  pdl_enter();
   const size_t cloud = blockIdx.y;
   const bool cols = blockIdx.z != 0;
   const int sub = threadIdx.x & 7;
@@ -550,6 +552,7 @@ static int nn_grad_parts(int b, int n_small) {
 __global__ void __launch_bounds__(256)
 nn_reduce_kernel(int n, int m, const float *__restrict__ dist1, const float *__restrict__ dist2, float s1, float s2,
                  float *__restrict__ loss) {
+  pdl_enter();
   __shared__ float red[2][8];
   const size_t cloud = blockIdx.x;
   float a = 0.f, c = 0.f;
@@ -608,8 +611,11 @@ __global__ void nn_grad_scatter_kernel(int b, int n, const float *__restrict__ x
 
 using namespace pcc;
 
-extern "C" __attribute__((visibility("default"))) int pcc_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *result,
-                              int *result_i, float *result2, int *result2_i, pcc_stream_t stream) {
+// `keep`: the caller launches a dependent kernel right behind the finalize kernel (programmatic dependent launch
+// needs kernel -> kernel edges) and releases the scratch buffer itself.
+static int nn_forward(int b, int n, const float *xyz, int m, const float *xyz2, float *result, int *result_i,
+                      float *result2, int *result2_i, pcc_stream_t stream, NnPart **keep) {
+  if (keep) *keep = nullptr;
   if (b < 0 || n < 0 || m < 0) return PCC_EINVAL;
   if (b == 0 || n == 0 || m == 0) return PCC_OK;  // nothing to compare against: outputs are left untouched
   if (b > 65535) return PCC_ENOTSUP;
@@ -630,10 +636,18 @@ extern "C" __attribute__((visibility("default"))) int pcc_nndistance(int b, int 
   NnPart *rowpart = scratch, *colpart = scratch + nrow;
   nn_sym_kernel<<<dim3(nrb * ncc, b), NS_THREADS, 0, st>>>(n, xyz, m, xyz2, nrb, ncc, rowpart, colpart);
   const int mx = n > m ? n : m;
-  nn_sym_finalize_kernel<<<dim3((mx + 31) / 32, b, 2), 256, 0, st>>>(n, xyz, m, xyz2, nrb, ncc, rowpart, colpart, result,
-                                                                      result_i, result2, result2_i);
-  cudaFreeAsync(scratch, st);
+  PCC_LAUNCH(PDL_CHAMFER, nn_sym_finalize_kernel, dim3((mx + 31) / 32, b, 2), 256, 0, st, n, xyz, m, xyz2, nrb, ncc,
+             (const NnPart *)rowpart, (const NnPart *)colpart, result, result_i, result2, result2_i);
+  if (keep)
+    *keep = scratch;
+  else
+    cudaFreeAsync(scratch, st);
   return finish_launch(2);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *result,
+                              int *result_i, float *result2, int *result2_i, pcc_stream_t stream) {
+  return nn_forward(b, n, xyz, m, xyz2, result, result_i, result2, result2_i, stream, nullptr);
 }
 
 extern "C" __attribute__((visibility("default"))) int pcc_nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2,
@@ -674,10 +688,15 @@ extern "C" __attribute__((visibility("default"))) int pcc_chamfer_reduce(int b, 
                                   pcc_stream_t stream) {
   if (b < 0 || n <= 0 || m <= 0) return PCC_EINVAL;
   if (b == 0) return PCC_OK;
-  int rc = pcc_nndistance(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, stream);
-  if (rc != 0) return rc;
-  nn_reduce_kernel<<<b, 256, 0, (cudaStream_t)stream>>>(n, m, dist1, dist2, scale1, scale2, loss);
-  return finish_launch(1);
+  NnPart *scratch = nullptr;
+  int rc = nn_forward(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, stream, &scratch);
+  if (rc == 0) {
+    PCC_LAUNCH(PDL_CHAMFER, nn_reduce_kernel, b, 256, 0, (cudaStream_t)stream, n, m, (const float *)dist1,
+               (const float *)dist2, scale1, scale2, loss);
+    rc = finish_launch(1);
+  }
+  if (scratch) cudaFreeAsync(scratch, (cudaStream_t)stream);
+  return rc;
 }
 
 extern "C" __attribute__((visibility("default"))) int pcc_chamfer_reduce_grad(int b, int n, const float *xyz1, int m, const float *xyz2,

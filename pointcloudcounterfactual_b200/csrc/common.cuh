@@ -17,6 +17,51 @@ inline int finish_launch(int nkernels) {
   return (int)cudaGetLastError();
 }
 
+// ---- programmatic dependent launch (experimental build variant: nvcc -DPCC_PDL, tools/build_variant.sh) -------
+// A kernel launched with the programmatic-stream-serialization attribute may become resident while its predecessor
+// in the stream still runs; pdl_wait() -- the FIRST statement of every kernel launched through PCC_LAUNCH -- blocks
+// until the predecessor has completed and its writes are visible (griddepcontrol.wait); pdl_trigger() lets the
+// successor become resident.  Short kernels trigger at once (pdl_enter); the solver sweeps trigger after their main
+// loop, when the SMs are draining: a successor placed while every CTA of the sweep is still resident lands on the
+// SMs the sweep loaded least and ends up three deep on some of them.  Only launch latency and CTA scheduling
+// overlap: no kernel touches memory before the wait.
+// The PCC_PDL_MASK environment variable selects which kernel classes get the attribute (default PCC_PDL_DEFAULT_MASK).
+// Without -DPCC_PDL the macro expands to the plain <<<>>> launch and pdl_enter() to nothing.
+constexpr unsigned PDL_CHAMFER = 1u, PDL_EMD_SMALL = 2u, PDL_EMD_SWEEP = 4u;
+#define PCC_K(...) __VA_ARGS__  // protects the commas of a template-id inside PCC_LAUNCH
+#ifdef PCC_PDL
+#ifndef PCC_PDL_DEFAULT_MASK
+#define PCC_PDL_DEFAULT_MASK 0
+#endif
+unsigned pdl_mask();  // lib.cu
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(unsigned cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_mask() & cls) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define PCC_LAUNCH(cls, k, g, b, s, st, ...) pcc::launch_pdl(cls, k, dim3(g), dim3(b), s, st, __VA_ARGS__)
+#else
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#define PCC_LAUNCH(cls, k, g, b, s, st, ...) k<<<g, b, s, st>>>(__VA_ARGS__)
+#endif
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+
 // ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2) ------------------------------------------
 // A f32x2 value lives in a 64-bit register pair; .x is the low half.  Each op rounds both lanes exactly like
 // the scalar .rn instruction, so results are bit-identical to scalar FADD/FMUL/FFMA.
