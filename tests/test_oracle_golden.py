@@ -161,3 +161,84 @@ def test_torch_ref_matches_reference(golden):
     k = golden["knn"]
     x = torch.from_numpy(k["feat64_k20_x"])
     assert (torch_ref.torch_knn(x, 20).numpy() == k["feat64_k20_torch_idx"]).mean() > 0.9999
+
+
+def _approxmatch_numpy(x1, x2):
+    """Independent restatement of SURVEY.md Appendix A.3 (approxmatch.cu:3-182) in float64, vectorised per sweep."""
+    n, m = len(x1), len(x2)
+    multi_l, multi_r = (1, n // m) if n >= m else (m // n, 1)
+    d2 = ((x1[:, None, :].astype(np.float64) - x2[None, :, :]) ** 2).sum(-1)  # (n, m): k indexes cloud 1, l cloud 2
+    remain_l, remain_r = np.full(n, float(multi_l)), np.full(m, float(multi_r))
+    match = np.zeros((m, n))
+    for j in range(7, -2, -1):
+        e = np.exp(-(4.0 ** j) * d2)
+        ratio_l = remain_l / (1e-9 + e @ remain_r)
+        sumr = (ratio_l @ e) * remain_r
+        ratio_r = np.minimum(remain_r / (sumr + 1e-9), 1.0) * remain_r
+        remain_r = np.maximum(0.0, remain_r - sumr)
+        w = e * ratio_l[:, None] * ratio_r[None, :]
+        match += w.T
+        remain_l = np.maximum(0.0, remain_l - w.sum(1))
+    return match, remain_l, remain_r
+
+
+@pytest.mark.parametrize("n,m", [(96, 96), (128, 64), (48, 144), (100, 37)])
+def test_approxmatch_matches_independent_numpy_restatement(n, m):
+    """The C oracle against a float64 numpy restatement written from the pseudo-code alone: same plan (B,m,n layout,
+    integer multipliers incl. the non-divisible case, level schedule, guards), same cost and gradients.  The iteration
+    amplifies fp32-vs-fp64 rounding ~1000x, hence 1e-3 on the plan and 1e-5 only on the cost."""
+    a, c = (t.numpy() for t in synthetic.s2_far(1, n, m))
+    match, temp = oracle.approxmatch(a, c)
+    want, rl, rr = _approxmatch_numpy(a[0], c[0])
+    assert match.shape == (1, m, n)
+    assert np.abs(match[0] - want).max() < 1e-3 * max(want.max(), 1e-3)
+    assert np.abs(temp[0, :n] - rl).max() < 1e-3 and np.abs(temp[0, n:n + m] - rr).max() < 1e-3
+    diff = a[0][:, None, :].astype(np.float64) - c[0][None, :, :]  # (n, m, 3)
+    dist = np.sqrt((diff ** 2).sum(-1))
+    cost = (match[0].astype(np.float64).T * dist).sum()
+    assert rel_err(oracle.matchcost(a, c, match), np.array([cost])) < TOL
+    g1, g2 = oracle.matchcostgrad(a, c, match)
+    unit = diff / np.sqrt(np.maximum((diff ** 2).sum(-1), 1e-20))[..., None]
+    w = match[0].astype(np.float64).T[..., None] * unit
+    assert rel_err(g1[0], w.sum(1)) < TOL and rel_err(g2[0], -w.sum(0)) < TOL
+
+
+def test_auction_matches_independent_python_restatement():
+    """oracle.auction_emd against a plain-Python restatement of Appendix A.5 (emd_cuda.cu:94-225) with the oracle's
+    deterministic tie rule (highest source index among bids within 1e-6 wins), on a small cloud pair."""
+    n = 1024
+    a, c = (t.numpy() for t in synthetic.auction_clouds(1, n))
+    eps, iters = np.float32(0.01), 6
+    x1, x2 = a[0], c[0]
+    asg, inv, price = np.full(n, -1), np.full(n, -1), np.zeros(n, np.float32)
+    dx = x2[None, :, :] - x1[:, None, :]
+    d2 = (dx[..., 2] * dx[..., 2] + (dx[..., 0] * dx[..., 0] + dx[..., 1] * dx[..., 1])).astype(np.float32)
+    root = np.sqrt(d2).astype(np.float32)
+    for it in range(iters):
+        last = it == iters - 1
+        un = np.flatnonzero(asg == -1)
+        if len(un) == 0:
+            break
+        v = (np.float32(3.0) - root[un]) - price[None, :]
+        best_k = v.argmax(1)
+        best = v[np.arange(len(un)), best_k]
+        v2 = v.copy()
+        v2[np.arange(len(un)), best_k] = -np.inf
+        inc = (best - v2.max(1)) + eps
+        top = np.full(n, -1e9, np.float32)
+        np.maximum.at(top, best_k, inc)
+        winner = np.full(n, -1)
+        for i, k, g in zip(un, best_k, inc):  # ascending i: the highest index within 1e-6 of the top bid wins
+            if abs(g - top[k]) <= 1e-6:
+                winner[k] = i
+        for i, k, g in zip(un, best_k, inc):
+            if last or winner[k] == i:
+                if not last and inv[k] != -1:
+                    asg[inv[k]] = -1
+                inv[k], asg[i] = i, k
+                price[k] += g
+    dist, got, _ = oracle.auction_emd(a, c, float(eps), iters)
+    agree = (got[0] == asg).mean()
+    assert agree > 0.99, agree  # second-best ties / fp32 association may flip isolated bids
+    same = got[0] == asg
+    assert rel_err(dist[0][same], d2[np.arange(n), asg][same]) < TOL
