@@ -31,3 +31,13 @@ def test_gpu_arm_refuses_to_run_without_cuda():
                        text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and not r.stdout.strip()
     assert "needs CUDA" in r.stderr or "CUDA" in r.stderr
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun (N > 1) rank 0 alone runs and prints the reference arm; the other ranks exit 0 without work."""
+    import os
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29571")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert not r.stdout.strip()
