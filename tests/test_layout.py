@@ -71,3 +71,23 @@ def test_kernels_use_blackwell_packed_fp32():
     sass = subprocess.run(["cuobjdump", "-sass", str(build.build())], capture_output=True, text=True).stdout
     for op in ("FFMA2", "FADD2", "FMNMX3", "MUFU.EX2"):
         assert op in sass, op
+
+
+def test_dependent_launch_is_compiled_into_the_chamfer_forward_chain_only():
+    """Programmatic dependent launch was measured per kernel chain: a gain on the Chamfer forward
+    chain, a loss on the EMD solver sweeps, nothing on the feature kNN.  Guard that build configuration: the wait /
+    trigger instructions (SASS ACQBULK / PREEXIT) appear in the three Chamfer forward kernels and nowhere else."""
+    import shutil
+    import subprocess
+
+    from pointcloudcounterfactual_b200 import build
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", str(build.build())], capture_output=True, text=True).stdout
+    with_pdl = set()
+    for chunk in sass.split("Function : ")[1:]:
+        name = chunk.split("\n", 1)[0].strip()
+        if "ACQBULK" in chunk or "PREEXIT" in chunk:
+            with_pdl.add(re.sub(r"^_ZN3pcc\d+", "", name).split("E", 1)[0])
+    assert with_pdl == {"nn_sym_kernel", "nn_sym_finalize_kernel", "nn_reduce_kernel"}, with_pdl
