@@ -24,6 +24,8 @@ _SIGNATURES = {
     "pcc_version": (ctypes.c_char_p, []),
     "pcc_status_string": (ctypes.c_char_p, [_i]),
     "pcc_launch_count": (ctypes.c_uint64, []),
+    "pcc_route_names": (ctypes.c_char_p, []),
+    "pcc_route_count": (ctypes.c_int64, [ctypes.c_char_p]),
     "pcc_nndistance": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_nndistancegrad": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_chamfer_reduce": (_i, [_i, _i, _vp, _i, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -68,6 +70,12 @@ def load() -> ctypes.CDLL:
 
 def launch_count() -> int:
     return int(load().pcc_launch_count())
+
+
+def route_counts() -> dict[str, int]:
+    """Per kernel family, how often the library dispatched to it (pcc_route_count): evidence of WHICH kernel ran."""
+    lib = load()
+    return {n: int(lib.pcc_route_count(n.encode())) for n in lib.pcc_route_names().decode().split(",")}
 
 
 def check(status: int, what: str, ok: int = 0) -> None:

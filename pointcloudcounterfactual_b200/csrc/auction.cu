@@ -134,6 +134,12 @@ auction_kernel(int n, const float *__restrict__ xyz1, const float *__restrict__ 
         r = bid_merge(r, q);
       }
       if (u < U && sub == 0) {
+        // a source whose every value is NaN (diverged decoder output) never beats the -1e9 start: r.idx stays -1.  Bid on
+        // target 0 with the minimum increment instead of indexing mig[-1] (memory safety; the loss is NaN either way)
+        if (r.idx < 0) {
+          r.idx = 0;
+          r.best = r.better = 0.f;
+        }
         const float inc = r.best - r.better + eps;
         bd[i] = r.idx;
         binc[i] = inc;
@@ -315,6 +321,12 @@ auction_cluster_kernel(int n, const float *__restrict__ xyz1, const float *__res
         r = bid_merge(r, q);
       }
       if (u < U && sub == 0) {
+        // a source whose every value is NaN (diverged decoder output) never beats the -1e9 start: r.idx stays -1.  Bid on
+        // target 0 with the minimum increment instead of indexing mig[-1] (memory safety; the loss is NaN either way)
+        if (r.idx < 0) {
+          r.idx = 0;
+          r.best = r.better = 0.f;
+        }
         const float inc = r.best - r.better + eps;
         bd[i] = r.idx;
         binc[i] = inc;
@@ -401,23 +413,15 @@ extern "C" __attribute__((visibility("default"))) int pcc_emd_forward(int b, int
   if (b <= 0 || n == 0) return 1;
   const size_t smem = sizeof(float) * 5 * (size_t)n;
   if (smem > 220 * 1024) return PCC_ENOTSUP;  // n <= 11264
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = smem;
-  }
+  static size_t attr[64];
+  if (cudaError_t e = smem_optin(auction_kernel, smem, attr); e != cudaSuccess) return (int)e;
   static const bool single_cta = getenv("PCC_AUCTION_SINGLE_CTA") != nullptr;  // test hook: one CTA per cloud
   if (!single_cta && b <= 65535) {
     // clusters of AUC_CTAS CTAs per cloud; unass_cnt (512 ints, caller-zeroed) carries the per-CTA counts for up to
     // 512 / AUC_CTAS clouds, more clouds take a pool allocation
     const size_t csmem = sizeof(float) * 4 * (size_t)n;
-    static size_t cattr = 0;
-    if (csmem > 48 * 1024 && csmem > cattr) {
-      cudaError_t e = cudaFuncSetAttribute(auction_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);
-      if (e != cudaSuccess) return (int)e;
-      cattr = csmem;
-    }
+    static size_t cattr[64];
+    if (cudaError_t e = smem_optin(auction_cluster_kernel, csmem, cattr); e != cudaSuccess) return (int)e;
     int *cnt = unass_cnt;
     int *pool = nullptr;
     if (cnt == nullptr || b * AUC_CTAS > 512) {

@@ -625,6 +625,7 @@ static int nn_forward(int b, int n, const float *xyz, int m, const float *xyz2, 
     const int mx = n > m ? n : m;
     dim3 grid((mx + NN_QT - 1) / NN_QT, b, 2);
     nn_fwd_kernel<<<grid, NN_THREADS, 0, st>>>(n, xyz, m, xyz2, result, result_i, result2, result2_i);
+    note_route(R_NN_ASYM);
     return finish_launch(1);
   }
   const int nrb = (n + NS_ROWS - 1) / NS_ROWS, ncc = (m + NS_CCOLS - 1) / NS_CCOLS;
@@ -634,6 +635,7 @@ static int nn_forward(int b, int n, const float *xyz, int m, const float *xyz2, 
   cudaError_t e = cudaMallocAsync((void **)&scratch, sizeof(NnPart) * (nrow + ncol), st);
   if (e != cudaSuccess) return (int)e;
   NnPart *rowpart = scratch, *colpart = scratch + nrow;
+  note_route(R_NN_SYM);
   nn_sym_kernel<<<dim3(nrb * ncc, b), NS_THREADS, 0, st>>>(n, xyz, m, xyz2, nrb, ncc, rowpart, colpart);
   const int mx = n > m ? n : m;
   PCC_LAUNCH(PDL_CHAMFER, nn_sym_finalize_kernel, dim3((mx + 31) / 32, b, 2), 256, 0, st, n, xyz, m, xyz2, nrb, ncc,
@@ -664,12 +666,8 @@ extern "C" __attribute__((visibility("default"))) int pcc_nndistancegrad(int b, 
   const size_t mx = n > m ? n : m, mn = n > m ? m : n;
   const size_t smem = sizeof(int) * (2 * mx + mx + mx / (NG_HEAVY + 1) + 8);
   if (smem <= 200 * 1024 && b <= 65535) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(nn_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return (int)e;
-      attr_set = true;
-    }
+    static size_t attr[64];
+    if (cudaError_t e = smem_optin(nn_grad_kernel, 200 * 1024, attr); e != cudaSuccess) return (int)e;
     nn_grad_kernel<<<dim3(b, 2, nn_grad_parts(b, (int)mn)), NG_THREADS, smem, st>>>(
         n, xyz1, m, xyz2, grad_dist1, idx1, grad_dist2, idx2, grad_xyz1, grad_xyz2, nullptr, 0.f, 0.f);
     return finish_launch(1);
@@ -708,12 +706,8 @@ extern "C" __attribute__((visibility("default"))) int pcc_chamfer_reduce_grad(in
   const size_t mx = n > m ? n : m;
   const size_t smem = sizeof(int) * (2 * mx + mx + mx / (NG_HEAVY + 1) + 8);
   if (smem > 200 * 1024 || b > 65535) return PCC_ENOTSUP;  // caller falls back to per-point upstream gradients
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(nn_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static size_t attr[64];
+  if (cudaError_t e = smem_optin(nn_grad_kernel, 200 * 1024, attr); e != cudaSuccess) return (int)e;
   nn_grad_kernel<<<dim3(b, 2, nn_grad_parts(b, n < m ? n : m)), NG_THREADS, smem, st>>>(
       n, xyz1, m, xyz2, nullptr, idx1, nullptr, idx2, grad_xyz1, grad_xyz2, grad_loss, scale1, scale2);
   return finish_launch(1);

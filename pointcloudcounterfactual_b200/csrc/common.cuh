@@ -17,6 +17,41 @@ inline int finish_launch(int nkernels) {
   return (int)cudaGetLastError();
 }
 
+// Which kernel family an entry point dispatched to (pcc_route_count): the tests and bench.py use it to PROVE that a call
+// made through the reference's unchanged call sites reached the fast kernels and not the generic SIMT path.
+enum Route {
+  R_KNN3W = 0,      // warp-cooperative xyz kNN (knn3w_kernel)
+  R_KNN3_THREAD,    // one-thread-per-query xyz kNN (knn3_kernel) as the primary kernel
+  R_KNN_TC2,        // tcgen05 feature kNN, second generation
+  R_KNN_TC1,        // tcgen05 feature kNN, first generation
+  R_KNN_SIMT,       // generic exact SIMT kernel (knn_kernel)
+  R_ARGMIN_SMALL,   // one-thread-per-query argmin (vector quantisation)
+  R_NN_SYM,         // symmetric brute-force Chamfer forward (nn_sym_kernel)
+  R_NN_ASYM,        // one-direction Chamfer forward (nn_fwd_kernel)
+  R_NN_GRID,        // grid-pruned exact Chamfer forward
+  R_KNN3_GRID,      // grid-pruned exact xyz kNN
+  R_PM_SELF,        // pcc_argkmin recognised q == r (point-major self kNN)
+  R_COUNT
+};
+extern std::atomic<uint64_t> g_routes[R_COUNT];
+inline void note_route(Route r) { g_routes[r].fetch_add(1, std::memory_order_relaxed); }
+
+// Opt-in to more than 48 KiB of dynamic shared memory.  The attribute is PER DEVICE: one process may drive several GPUs
+// (the Python wrappers take tensors on any device), so the high-water mark is kept per device ordinal.
+template <typename Kernel>
+inline cudaError_t smem_optin(Kernel kernel, size_t bytes, size_t (&done)[64], size_t threshold = 48 * 1024) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  size_t &d = done[dev & 63];
+  if (bytes > threshold && bytes > d) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    d = bytes;
+  }
+  return cudaSuccess;
+}
+
 // ---- programmatic dependent launch (experimental build variant: nvcc -DPCC_PDL, tools/build_variant.sh) -------
 // A kernel launched with the programmatic-stream-serialization attribute may become resident while its predecessor
 // in the stream still runs; pdl_wait() -- the FIRST statement of every kernel launched through PCC_LAUNCH -- blocks
@@ -116,7 +151,7 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 }
 
 // knn_tc.cu: tcgen05 candidate generator + exact re-rank; PCC_ENOTSUP when the shape is outside that path
-int knn_tc_launch(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st);
+int knn_tc_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

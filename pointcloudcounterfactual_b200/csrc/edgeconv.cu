@@ -769,15 +769,10 @@ pcc_edgeconv_forward(int b, int n, int k, int cout, const float *uv, const int64
   const int nparts = staged ? b : (int)(grid.x * grid.y);
   const size_t stage_smem = (size_t)max(n * 32, 2 * EC_STHREADS * 4 * 8) + (size_t)EC_SPTS * k * 2;
   if (staged) {
-    static bool attr = false;
-    if (!attr) {
-      cudaError_t e1 = cudaFuncSetAttribute(ec_reduce_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            EC_STAGE_MAX_N * 32 + EC_SPTS * EC_MAX_K * 2);
-      cudaError_t e2 = cudaFuncSetAttribute(ec_reduce_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            EC_STAGE_MAX_N * 32 + EC_SPTS * EC_MAX_K * 2);
-      if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
-      attr = true;
-    }
+    static size_t attr1[64], attr2[64];
+    cudaError_t e1 = smem_optin(ec_reduce_staged_kernel<true>, EC_STAGE_MAX_N * 32 + EC_SPTS * EC_MAX_K * 2, attr1);
+    cudaError_t e2 = smem_optin(ec_reduce_staged_kernel<false>, EC_STAGE_MAX_N * 32 + EC_SPTS * EC_MAX_K * 2, attr2);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
   }
   char *ws = nullptr;
   const size_t part_bytes = sizeof(double) * 2 * cout * nparts, aff_bytes = sizeof(float) * 2 * cout;
@@ -857,17 +852,12 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   const bool staged = n <= EC_STAGE_MAX_N;
   const dim3 sgrid(ec_nslice(cout), b);
   if (staged) {
-    static bool attr = false;
-    if (!attr) {
-      cudaError_t e1 = cudaFuncSetAttribute(ec_bwd_chunk_staged_kernel<true>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, EC_STAGE_MAX_N * 72);
-      cudaError_t e2 = cudaFuncSetAttribute(ec_bwd_chunk_staged_kernel<false>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, EC_STAGE_MAX_N * 40);
-      if (e1 != cudaSuccess || e2 != cudaSuccess) {
-        cudaFreeAsync(ws, st);
-        return (int)(e1 != cudaSuccess ? e1 : e2);
-      }
-      attr = true;
+    static size_t attr1[64], attr2[64];
+    cudaError_t e1 = smem_optin(ec_bwd_chunk_staged_kernel<true>, EC_STAGE_MAX_N * 72, attr1);
+    cudaError_t e2 = smem_optin(ec_bwd_chunk_staged_kernel<false>, EC_STAGE_MAX_N * 40, attr2);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      cudaFreeAsync(ws, st);
+      return (int)(e1 != cudaSuccess ? e1 : e2);
     }
   }
   if (staged && bn_mode == EC_BN_TRAIN) {

@@ -128,12 +128,8 @@ graph_gather_grad_kernel(int c, int n, int k, const int64_t *__restrict__ idx, c
 template <int MODE>
 static int launch_gather(int b, int c, int n, int k, const float *x, const int64_t *idx, float *out, cudaStream_t st) {
   const size_t smem = sizeof(float) * GG_CH * n;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(graph_gather_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = smem;
-  }
+  static size_t attr[64];
+  if (cudaError_t e = smem_optin(graph_gather_kernel<MODE>, smem, attr); e != cudaSuccess) return (int)e;
   graph_gather_kernel<MODE><<<dim3((n + GG_PT - 1) / GG_PT, b), GG_THREADS, smem, st>>>(c, n, k, x, idx, out);
   return finish_launch(1);
 }
@@ -298,12 +294,8 @@ extern "C" __attribute__((visibility("default"))) int pcc_graph_filtering(int b,
   if (b == 0) return PCC_OK;
   if (k > GF_MAXK || n > 6144) return PCC_ENOTSUP;
   const size_t smem = sizeof(float) * 3 * n;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(graph_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = smem;
-  }
+  static size_t attr[64];
+  if (cudaError_t e = smem_optin(graph_filter_kernel, smem, attr); e != cudaSuccess) return (int)e;
   graph_filter_kernel<<<b, GF_THREADS, smem, (cudaStream_t)stream>>>(n, k, x, idx, out, mean_dist);
   return finish_launch(1);
 }
@@ -315,12 +307,8 @@ extern "C" __attribute__((visibility("default"))) int pcc_graph_filtering_grad(i
   if (b == 0) return PCC_OK;
   if (k > GF_MAXK || n > 6144) return PCC_ENOTSUP;
   const size_t smem = sizeof(float) * 9 * n;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(graph_filter_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = smem;
-  }
+  static size_t attr[64];
+  if (cudaError_t e = smem_optin(graph_filter_grad_kernel, smem, attr); e != cudaSuccess) return (int)e;
   graph_filter_grad_kernel<<<b, GF_THREADS, smem, (cudaStream_t)stream>>>(n, k, x, idx, mean_dist, grad_out, grad_x);
   return finish_launch(1);
 }

@@ -176,7 +176,7 @@ __device__ __forceinline__ f32x2 knn_sqdist2(f32x2 rx, f32x2 ry, f32x2 rz, f32x2
 
 template <int K>
 __global__ void __launch_bounds__(K3_THREADS)
-knn3_kernel(int n, int k, int groups8, const float *__restrict__ x, int64_t *__restrict__ idx_out,
+knn3_kernel(int n, int k, int groups8, int ps, int cs, const float *__restrict__ x, int64_t *__restrict__ idx_out,
             float *__restrict__ dist_out, const int *__restrict__ only_hard) {
   if (only_hard && !only_hard[blockIdx.y]) return;  // repair pass behind knn3w_kernel: only the flagged clouds
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -186,11 +186,13 @@ knn3_kernel(int n, int k, int groups8, const float *__restrict__ x, int64_t *__r
 
   const int tid = threadIdx.x;
   const size_t cloud = blockIdx.y;
-  const float *__restrict__ xr = x + cloud * (size_t)3 * n;  // rows: x[0][:], x[1][:], x[2][:]
+  // coordinate c of point i sits at xr[i * ps + c * cs]: channels-first (b,3,n) has ps = 1, cs = n; point-major
+  // (b,n,3) -- the layout the reference hands to KeOps, neighbour_ops.py:79 -- has ps = 3, cs = 1
+  const float *__restrict__ xr = x + cloud * (size_t)3 * n;
   const int q0 = blockIdx.x * K3_THREADS;
   const int q = min(q0 + tid, n - 1);
   const float INF = __int_as_float(0x7f800000);
-  const float qx = xr[q], qy = xr[(size_t)n + q], qz = xr[(size_t)2 * n + q];
+  const float qx = xr[(size_t)q * ps], qy = xr[(size_t)q * ps + cs], qz = xr[(size_t)q * ps + 2 * (size_t)cs];
   const f32x2 nqx = pack2(-qx, -qx), nqy = pack2(-qy, -qy), nqz = pack2(-qz, -qz);
   float *tf = reinterpret_cast<float *>(tile);
 
@@ -211,9 +213,9 @@ knn3_kernel(int n, int k, int groups8, const float *__restrict__ x, int64_t *__r
         for (int i = tid; i < tcnt8; i += K3_THREADS) {
           float vx = INF, vy = INF, vz = INF;  // padding: distance +inf
           if (i < tcnt) {
-            vx = xr[base + i];
-            vy = xr[(size_t)n + base + i];
-            vz = xr[(size_t)2 * n + base + i];
+            vx = xr[(size_t)(base + i) * ps];
+            vy = xr[(size_t)(base + i) * ps + cs];
+            vz = xr[(size_t)(base + i) * ps + 2 * (size_t)cs];
           }
           const int o = (i >> 2) * 12 + (i & 3);
           tf[o] = vx;
@@ -348,7 +350,7 @@ __device__ __forceinline__ void team_sync(int id, int threads) {
 
 template <int S>
 __global__ void __launch_bounds__(KW_THREADS, 3)
-knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__restrict__ idx_out,
+knn3w_kernel(int n, int k, int qper, int ps, int cs, const float *__restrict__ x, int64_t *__restrict__ idx_out,
              float *__restrict__ dist_out, int *__restrict__ hard) {
   constexpr int T = KW_THREADS / 32 / S;  // teams per CTA
   constexpr int NP = 1024 * S;
@@ -366,9 +368,9 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
   const float *__restrict__ xr = x + cloud * (size_t)3 * n;
   const float INF = __int_as_float(0x7f800000);
   for (int i = tid; i < NP; i += KW_THREADS) {  // padding: +inf coordinates => +inf distance
-    xs[i] = i < n ? xr[i] : INF;
-    ys[i] = i < n ? xr[(size_t)n + i] : INF;
-    zs[i] = i < n ? xr[(size_t)2 * n + i] : INF;
+    xs[i] = i < n ? xr[(size_t)i * ps] : INF;  // (ps, cs) = (1, n) channels-first, (3, 1) point-major
+    ys[i] = i < n ? xr[(size_t)i * ps + cs] : INF;
+    zs[i] = i < n ? xr[(size_t)i * ps + 2 * (size_t)cs] : INF;
   }
   if (tid < T) tsum[tid] = 0;
   __syncthreads();
@@ -553,46 +555,38 @@ knn3w_kernel(int n, int k, int qper, const float *__restrict__ x, int64_t *__res
 }
 
 template <int S>
-static int launch_knn3w_s(int b, int n, int k, int parts, const float *x, int64_t *idx, float *dist, int *hard,
+static int launch_knn3w_s(int b, int n, int k, int parts, bool pm, const float *x, int64_t *idx, float *dist, int *hard,
                           cudaStream_t st) {
   const size_t smem = sizeof(float) * 3 * 1024 * S;
-  static bool attr = false;
-  if (!attr) {  // static + dynamic shared memory exceeds the 48 KiB default at S = 4
-    cudaError_t e = cudaFuncSetAttribute(knn3w_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  static size_t attr[64];  // static + dynamic shared memory exceeds the 48 KiB default at S = 4: opt in at any size
+  if (cudaError_t e = smem_optin(knn3w_kernel<S>, smem, attr, 0); e != cudaSuccess) return (int)e;
   const int qper = (n + parts - 1) / parts;
-  knn3w_kernel<S><<<dim3((n + qper - 1) / qper, b), KW_THREADS, smem, st>>>(n, k, qper, x, idx, dist, hard);
+  knn3w_kernel<S><<<dim3((n + qper - 1) / qper, b), KW_THREADS, smem, st>>>(n, k, qper, pm ? 3 : 1, pm ? 1 : n, x, idx, dist, hard);
   return (int)cudaGetLastError();
 }
 
 template <int K>
-static int launch_knn3_k(int b, int n, int k, const float *x, int64_t *idx, float *dist, const int *only_hard,
+static int launch_knn3_k(int b, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, const int *only_hard,
                          cudaStream_t st) {
   const size_t smem = sizeof(float4) * (K3_TILE / 4 * 3) + (size_t)K3_CAP * K3_THREADS * (sizeof(float) + sizeof(int));
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(knn3_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  static size_t attr[64];
+  if (cudaError_t e = smem_optin(knn3_kernel<K>, smem, attr); e != cudaSuccess) return (int)e;
   // group size G = 8 * groups8: as large as possible while leaving at least ~3k groups (tight tau, few candidates)
   int groups8 = 4;
   while (groups8 > 1 && (n / (8 * groups8)) < 3 * k) groups8 >>= 1;
   dim3 grid((n + K3_THREADS - 1) / K3_THREADS, b);
-  knn3_kernel<K><<<grid, K3_THREADS, smem, st>>>(n, k, groups8, x, idx, dist, only_hard);
+  knn3_kernel<K><<<grid, K3_THREADS, smem, st>>>(n, k, groups8, pm ? 3 : 1, pm ? 1 : n, x, idx, dist, only_hard);
   return finish_launch(1);
 }
 
-static int launch_knn3_thread(int b, int n, int k, const float *x, int64_t *idx, float *dist, const int *only_hard,
+static int launch_knn3_thread(int b, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, const int *only_hard,
                               cudaStream_t st) {
-  if (k <= 4) return launch_knn3_k<4>(b, n, k, x, idx, dist, only_hard, st);
-  if (k <= 8) return launch_knn3_k<8>(b, n, k, x, idx, dist, only_hard, st);
-  if (k <= 16) return launch_knn3_k<16>(b, n, k, x, idx, dist, only_hard, st);
-  if (k <= 20) return launch_knn3_k<20>(b, n, k, x, idx, dist, only_hard, st);
-  if (k <= 24) return launch_knn3_k<24>(b, n, k, x, idx, dist, only_hard, st);
-  return launch_knn3_k<32>(b, n, k, x, idx, dist, only_hard, st);
+  if (k <= 4) return launch_knn3_k<4>(b, n, k, pm, x, idx, dist, only_hard, st);
+  if (k <= 8) return launch_knn3_k<8>(b, n, k, pm, x, idx, dist, only_hard, st);
+  if (k <= 16) return launch_knn3_k<16>(b, n, k, pm, x, idx, dist, only_hard, st);
+  if (k <= 20) return launch_knn3_k<20>(b, n, k, pm, x, idx, dist, only_hard, st);
+  if (k <= 24) return launch_knn3_k<24>(b, n, k, pm, x, idx, dist, only_hard, st);
+  return launch_knn3_k<32>(b, n, k, pm, x, idx, dist, only_hard, st);
 }
 
 // Number of query ranges per cloud: fill the 148 SMs x 3 resident CTAs evenly, at least 8 queries per team
@@ -624,20 +618,24 @@ static int knn3w_parts(int b, int n, int teams) {
   return best;
 }
 
-static int launch_knn3(int b, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
+static int launch_knn3(int b, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
   static const bool thread_only = getenv("PCC_KNN3_THREAD") != nullptr;  // test hook: one-thread-per-query kernel only
-  if (thread_only || n > 4096) return launch_knn3_thread(b, n, k, x, idx, dist, nullptr, st);
+  if (thread_only || n > 4096) {
+    note_route(R_KNN3_THREAD);
+    return launch_knn3_thread(b, n, k, pm, x, idx, dist, nullptr, st);
+  }
+  note_route(R_KNN3W);
   int *hard = nullptr;
   cudaError_t e = cudaMallocAsync((void **)&hard, sizeof(int) * b, st);
   if (e != cudaSuccess) return (int)e;
   cudaMemsetAsync(hard, 0, sizeof(int) * b, st);
   int rc;
-  if (n <= 1024) rc = launch_knn3w_s<1>(b, n, k, knn3w_parts(b, n, 4), x, idx, dist, hard, st);
-  else if (n <= 2048) rc = launch_knn3w_s<2>(b, n, k, knn3w_parts(b, n, 2), x, idx, dist, hard, st);
-  else rc = launch_knn3w_s<4>(b, n, k, knn3w_parts(b, n, 1), x, idx, dist, hard, st);
+  if (n <= 1024) rc = launch_knn3w_s<1>(b, n, k, knn3w_parts(b, n, 4), pm, x, idx, dist, hard, st);
+  else if (n <= 2048) rc = launch_knn3w_s<2>(b, n, k, knn3w_parts(b, n, 2), pm, x, idx, dist, hard, st);
+  else rc = launch_knn3w_s<4>(b, n, k, knn3w_parts(b, n, 1), pm, x, idx, dist, hard, st);
   if (rc == 0) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    rc = launch_knn3_thread(b, n, k, x, idx, dist, hard, st);  // exits at once unless a cloud overflowed KW_CAP
+    rc = launch_knn3_thread(b, n, k, pm, x, idx, dist, hard, st);  // exits at once unless a cloud overflowed KW_CAP
   }
   cudaFreeAsync(hard, st);
   return rc;
@@ -683,26 +681,36 @@ static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const
   if (PM && k == 1 && nr <= 64 && c <= 16 && nq <= 8 && b > 0 && nq > 0 && getenv("PCC_KNN_SIMT") == nullptr) {
     const size_t total = (size_t)b * nq;  // no 65535-cloud grid limit on this path (B * n_codes problems)
     argmin_small_kernel<<<(unsigned int)((total + 255) / 256), 256, 0, st>>>(b, nq, nr, c, q, r, idx, dist);
+    note_route(R_ARGMIN_SMALL);
     return finish_launch(1);
   }
   if (k > PCC_KNN_MAX_K || b > 65535) return PCC_ENOTSUP;
   if (b == 0 || nq == 0) return PCC_OK;
   static const bool force_simt = getenv("PCC_KNN_SIMT") != nullptr;  // test hook: exact SIMT kernels only
 
-  if (!PM && c == 3 && q == r && nq == nr && k <= 32) return launch_knn3(b, nq, k, q, idx, dist, st);
-  if (!PM && !force_simt && q == r && nq == nr && c % 32 == 0) {
+  // Self kNN (q == r): channels-first through pcc_knn, point-major through pcc_argkmin -- the latter is what the
+  // reference's UNCHANGED pykeops_knn produces (neighbour_ops.py:77-82: x.transpose(2, 1).contiguous(), then one
+  // LazyTensor expression on (x, x)), so both layouts reach the same fast kernels.
+  const bool self = q == r && nq == nr;
+  if (PM && self) note_route(R_PM_SELF);
+  if (self && c == 3 && k <= 32) return launch_knn3(b, nq, k, PM, q, idx, dist, st);
+  if (self && !force_simt && c % 32 == 0) {
     static const bool tc_v1 = getenv("PCC_KNN_TC1") != nullptr;  // test hook: first-generation tcgen05 kernel only
-    int rc = tc_v1 ? PCC_ENOTSUP : knn_tc2_launch(b, c, nq, k, q, idx, dist, st);
-    if (rc == PCC_ENOTSUP) rc = knn_tc_launch(b, c, nq, k, q, idx, dist, st);
-    if (rc != PCC_ENOTSUP) return rc;
+    int rc = tc_v1 ? PCC_ENOTSUP : knn_tc2_launch(b, c, nq, k, PM, q, idx, dist, st);
+    if (rc != PCC_ENOTSUP) {
+      note_route(R_KNN_TC2);
+      return rc;
+    }
+    rc = knn_tc_launch(b, c, nq, k, PM, q, idx, dist, st);
+    if (rc != PCC_ENOTSUP) {
+      note_route(R_KNN_TC1);
+      return rc;
+    }
   }
+  note_route(R_KNN_SIMT);
   const size_t smem = sizeof(KnnSmem) + (size_t)k * KN_TQ * (sizeof(float) + sizeof(int));
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(knn_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = smem;
-  }
+  static size_t attr[64];
+  if (cudaError_t e = smem_optin(knn_kernel<PM>, smem, attr); e != cudaSuccess) return (int)e;
   dim3 grid((nq + KN_TQ - 1) / KN_TQ, b);
   knn_kernel<PM><<<grid, KN_THREADS, smem, st>>>(c, nq, nr, k, q, r, idx, dist);
   return finish_launch(1);

@@ -33,7 +33,7 @@ constexpr uint32_t TC_IDESC = umma_idesc_tf32(TC_M, TC_N);
 
 // ---- prep: transpose + norms ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-knn_tc_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict__ xT, float *__restrict__ norms,
+knn_tc_prep_kernel(int c, int n, bool pm, const float *__restrict__ x, float *__restrict__ xT, float *__restrict__ norms,
                    int norm_stride, unsigned int *__restrict__ nmax_bits) {
   __shared__ float t[64][33];
   const size_t cloud = blockIdx.y;
@@ -42,7 +42,21 @@ knn_tc_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict_
   const float *xb = x + cloud * (size_t)c * n;
   float *xo = xT + cloud * (size_t)n * c;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // thread (tx = channel lane, ty) accumulates points ty, ty+8, ty+16, ty+24
-  for (int c0 = 0; c0 < c; c0 += 64) {
+  // point-major input (b,n,c) -- what the reference hands to KeOps after x.transpose(2, 1).contiguous(),
+  // neighbour_ops.py:79 -- is already the operand layout: only the norms are needed (same summation order)
+  for (int c0 = 0; pm && c0 < c; c0 += 64) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int p = n0 + ty + 8 * r;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ch = c0 + tx + 32 * h;
+        const float v = (p < n && ch < c) ? xb[(size_t)p * c + ch] : 0.f;
+        acc[r] = fmaf(v, v, acc[r]);
+      }
+    }
+  }
+  for (int c0 = 0; !pm && c0 < c; c0 += 64) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {  // rows = channels c0 + ty + 8r, columns = points n0 + tx: 8 loads in flight
       const int ch = c0 + ty + 8 * r;
@@ -415,19 +429,16 @@ template <int K>
 static int launch_tc_k(const CUtensorMap &mq, const CUtensorMap &mr, int b, int c, int n, int k, const float *xT,
                        const float *norms, const unsigned int *nmax, int64_t *idx, float *dist, cudaStream_t st) {
   const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_CAP * TC_M * 6 + 4 * TC_N * 4 + sizeof(TcSmemCtl) + 64;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  static size_t attr[64];
+  if (cudaError_t e = smem_optin(knn_tc_kernel<K>, smem, attr); e != cudaSuccess) return (int)e;
   dim3 grid((n + TC_M - 1) / TC_M, b);
   knn_tc_kernel<K><<<grid, TC_THREADS, smem, st>>>(mq, mr, c, n, k, xT, norms, nmax, idx, dist);
   return (int)cudaGetLastError();
 }
 
-// x (b,c,n) channels-first.  Returns PCC_ENOTSUP when the shape is outside this path (caller falls back to SIMT).
-int knn_tc_launch(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
+// x (b,c,n) channels-first, or (b,n,c) point-major with pm.  Returns PCC_ENOTSUP when the shape is outside this path
+// (caller falls back to SIMT).
+int knn_tc_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
   if (c % TC_KB != 0 || c < TC_KB || c > 1024 || k > 32 || k > TC_CAP / 2 || n < 16 * k || n > 65535 || b > 65535)
     return PCC_ENOTSUP;
   if (!tc_get_encode()) return PCC_ENOTSUP;
@@ -435,10 +446,11 @@ int knn_tc_launch(int b, int c, int n, int k, const float *x, int64_t *idx, floa
   const size_t nxt = (size_t)b * n * c, nn = (size_t)b * n;
   cudaError_t e = cudaMallocAsync((void **)&ws, sizeof(float) * (nxt + nn) + sizeof(unsigned int) * b, st);
   if (e != cudaSuccess) return (int)e;
-  float *xT = ws, *norms = ws + nxt;
+  const float *xT = pm ? x : ws;
+  float *norms = ws + nxt;
   unsigned int *nmax = reinterpret_cast<unsigned int *>(norms + nn);
   cudaMemsetAsync(nmax, 0, sizeof(unsigned int) * b, st);
-  knn_tc_prep_kernel<<<dim3((n + 31) / 32, b), 256, 0, st>>>(c, n, x, xT, norms, n, nmax);
+  knn_tc_prep_kernel<<<dim3((n + 31) / 32, b), 256, 0, st>>>(c, n, pm, x, ws, norms, n, nmax);
   CUtensorMap mq, mr;
   int rc = tc_make_map(&mq, xT, b, n, c, TC_M);
   if (rc == 0) rc = tc_make_map(&mr, xT, b, n, c, TC_N);

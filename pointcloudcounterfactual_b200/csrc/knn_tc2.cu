@@ -57,7 +57,7 @@ constexpr float T2_C2 = 4e-5f;
 // bounds[(cloud*npad + j)/R tile][3][R] = { n_j (1+c2), n_j (1-c2), c1 sqrt(n_j) }, padding keys {inf, inf, 0}
 template <int R>
 __global__ void __launch_bounds__(256)
-knn_tc2_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict__ xT, float *__restrict__ norms,
+knn_tc2_prep_kernel(int c, int n, bool pm, const float *__restrict__ x, float *__restrict__ xT, float *__restrict__ norms,
                     float *__restrict__ bounds, int npad) {
   __shared__ float t[64][33];
   const size_t cloud = blockIdx.y;
@@ -66,7 +66,21 @@ knn_tc2_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict
   const float *xb = x + cloud * (size_t)c * n;
   float *xo = xT + cloud * (size_t)n * c;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // thread (tx = channel lane, ty) accumulates points ty, ty+8, ty+16, ty+24
-  for (int c0 = 0; c0 < c; c0 += 64) {
+  // point-major input (b,n,c) -- what the reference hands to KeOps after x.transpose(2, 1).contiguous(),
+  // neighbour_ops.py:79 -- is already the operand layout: only the norms are needed (same summation order)
+  for (int c0 = 0; pm && c0 < c; c0 += 64) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int p = n0 + ty + 8 * r;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ch = c0 + tx + 32 * h;
+        const float v = (p < n && ch < c) ? xb[(size_t)p * c + ch] : 0.f;
+        acc[r] = fmaf(v, v, acc[r]);
+      }
+    }
+  }
+  for (int c0 = 0; !pm && c0 < c; c0 += 64) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {  // rows = channels c0 + ty + 8r, columns = points n0 + tx: 8 loads in flight
       const int ch = c0 + ty + 8 * r;
@@ -550,17 +564,13 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
 // ---- host ----------------------------------------------------------------------------------------------------
 template <int KB, int HALVES, int R>
-static int launch_tc2(int b, int c, int n, int k, int npad, const float *x, float *xT, float *norms, float *bounds,
+static int launch_tc2(int b, int c, int n, int k, int npad, bool pm, const float *x, float *xT_ws, float *norms, float *bounds,
                       int64_t *idx, float *dist, cudaStream_t st) {
   using Cfg = T2<KB, HALVES, R>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(knn_tc2_kernel<KB, HALVES, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::SMEM);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
-  knn_tc2_prep_kernel<R><<<dim3((npad + 31) / 32, b), 256, 0, st>>>(c, n, x, xT, norms, bounds, npad);
+  static size_t attr[64];
+  if (cudaError_t e = smem_optin(knn_tc2_kernel<KB, HALVES, R>, Cfg::SMEM, attr); e != cudaSuccess) return (int)e;
+  knn_tc2_prep_kernel<R><<<dim3((npad + 31) / 32, b), 256, 0, st>>>(c, n, pm, x, xT_ws, norms, bounds, npad);
+  const float *xT = pm ? x : xT_ws;
   CUtensorMap mq, mr;
   int rc = tc_make_map(&mq, xT, b, n, Cfg::C, Cfg::QUERIES);
   if (rc == 0) rc = tc_make_map(&mr, xT, b, n, Cfg::C, R);
@@ -570,8 +580,8 @@ static int launch_tc2(int b, int c, int n, int k, int npad, const float *x, floa
   return (int)cudaGetLastError();
 }
 
-// x (b,c,n) channels-first.  Returns PCC_ENOTSUP when the shape is outside this path.
-int knn_tc2_launch(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
+// x (b,c,n) channels-first, or (b,n,c) point-major with pm.  Returns PCC_ENOTSUP when the shape is outside this path.
+int knn_tc2_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
   if (c % 32 != 0 || c < 32 || c > 128 || k > 32 || n < 32 * k || n > 2048 || b > 65535) return PCC_ENOTSUP;
   if (!tc_get_encode()) return PCC_ENOTSUP;
   const int r = (c <= 64) ? 128 : 64;
@@ -583,10 +593,10 @@ int knn_tc2_launch(int b, int c, int n, int k, const float *x, int64_t *idx, flo
   float *xT = ws, *norms = ws + nxt, *bounds = norms + nn;
   int rc;
   switch (c / 32) {
-    case 1: rc = launch_tc2<1, 2, 128>(b, c, n, k, npad, x, xT, norms, bounds, idx, dist, st); break;
-    case 2: rc = launch_tc2<2, 2, 128>(b, c, n, k, npad, x, xT, norms, bounds, idx, dist, st); break;
-    case 3: rc = launch_tc2<3, 1, 64>(b, c, n, k, npad, x, xT, norms, bounds, idx, dist, st); break;
-    default: rc = launch_tc2<4, 1, 64>(b, c, n, k, npad, x, xT, norms, bounds, idx, dist, st); break;
+    case 1: rc = launch_tc2<1, 2, 128>(b, c, n, k, npad, pm, x, xT, norms, bounds, idx, dist, st); break;
+    case 2: rc = launch_tc2<2, 2, 128>(b, c, n, k, npad, pm, x, xT, norms, bounds, idx, dist, st); break;
+    case 3: rc = launch_tc2<3, 1, 64>(b, c, n, k, npad, pm, x, xT, norms, bounds, idx, dist, st); break;
+    default: rc = launch_tc2<4, 1, 64>(b, c, n, k, npad, pm, x, xT, norms, bounds, idx, dist, st); break;
   }
   cudaFreeAsync(ws, st);
   if (rc == 0) g_launches.fetch_add(2, std::memory_order_relaxed);

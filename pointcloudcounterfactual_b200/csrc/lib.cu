@@ -1,12 +1,17 @@
 // Library-level entry points of libpcc_b200.so.
 #include "common.cuh"
 
+#include <string.h>
+
 #ifdef PCC_PDL
 #include <stdlib.h>
 #endif
 
 namespace pcc {
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_routes[R_COUNT];
+static const char *const kRouteNames[R_COUNT] = {"knn3w", "knn3_thread", "knn_tc2", "knn_tc1", "knn_simt", "argmin_small",
+                                                 "nn_sym", "nn_asym", "nn_grid", "knn3_grid", "pm_self"};
 #ifdef PCC_PDL
 unsigned pdl_mask() {  // read at every launch (captured graphs keep what was set at capture time): A/B runs in one process
   const char *e = getenv("PCC_PDL_MASK");
@@ -18,6 +23,17 @@ unsigned pdl_mask() {  // read at every launch (captured graphs keep what was se
 extern "C" __attribute__((visibility("default"))) const char *pcc_version(void) { return "pcc_b200 0.1 (sm_100a)"; }
 
 extern "C" __attribute__((visibility("default"))) uint64_t pcc_launch_count(void) { return pcc::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" __attribute__((visibility("default"))) const char *pcc_route_names(void) {
+  return "knn3w,knn3_thread,knn_tc2,knn_tc1,knn_simt,argmin_small,nn_sym,nn_asym,nn_grid,knn3_grid,pm_self";
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t pcc_route_count(const char *name) {
+  if (!name) return -1;
+  for (int i = 0; i < pcc::R_COUNT; ++i)
+    if (strcmp(name, pcc::kRouteNames[i]) == 0) return (int64_t)pcc::g_routes[i].load(std::memory_order_relaxed);
+  return -1;
+}
 
 extern "C" __attribute__((visibility("default"))) const char *pcc_status_string(int status) {
   switch (status) {

@@ -123,6 +123,6 @@ int tc_make_map(CUtensorMap *m, const float *xT, int b, int n, int c, int box_ro
 __global__ void knn_tc_prep_kernel(int c, int n, const float *__restrict__ x, float *__restrict__ xT,
                                    float *__restrict__ norms, int norm_stride, unsigned int *__restrict__ nmax_bits);
 // knn_tc2.cu: 256-query CTAs, keys resident in shared memory for the exact re-rank; PCC_ENOTSUP outside its shapes
-int knn_tc2_launch(int b, int c, int n, int k, const float *x, int64_t *idx, float *dist, cudaStream_t st);
+int knn_tc2_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st);
 
 }  // namespace pcc

@@ -96,6 +96,52 @@ class _EdgeConvMax(Function):
                 None, None, None, None, None, None, None)
 
 
+class _GraphMaxPool(Function):
+    """x (B,C,N), idx (B,N,k) -> max over the k neighbours (B,C,N): the edge pass with u = x, v = 0 and no
+    normalisation.  uv = [x^T | 0] is built by a copy -- no GEMM, so the values are bit-identical to gather + max whatever
+    ``torch.backends.cuda.matmul.allow_tf32`` says; the gradient goes to the first arg-max slot."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx: Any, x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        b, c, n = x.shape
+        k = idx.shape[2]
+        dev = x.device
+        with torch.cuda.device(dev):
+            uv = torch.zeros((b, n, 2 * c), dtype=torch.float32, device=dev)
+            uv[:, :, :c].copy_(x.transpose(1, 2))
+            out = torch.empty((b, c, n), dtype=torch.float32, device=dev)
+            exty = torch.empty((b, n, c), dtype=torch.float32, device=dev)
+            slot = torch.empty((b, (c + 7) // 8, n, 8), dtype=torch.uint8, device=dev)
+            mean = torch.empty((c,), dtype=torch.float32, device=dev)
+            invstd = torch.empty((c,), dtype=torch.float32, device=dev)
+            L.check(L.load().pcc_edgeconv_forward(
+                b, n, k, c, L.ptr(uv), L.ptr(idx), None, None, None, None, AFFINE, 0.0, 0.0, ACT_NONE, 0.0, L.ptr(out),
+                L.ptr(exty), None, L.ptr(slot), L.ptr(mean), L.ptr(invstd), L.stream_of(uv)), "graph_max_pooling")
+        ctx.save_for_backward(uv, idx, mean, invstd, exty, slot)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx: Any, grad_out: torch.Tensor):
+        uv, idx, mean, invstd, exty, slot = ctx.saved_tensors
+        b, n, c2 = uv.shape
+        c = c2 // 2
+        g = grad_out.contiguous()
+        with torch.cuda.device(uv.device):
+            guv = torch.empty_like(uv)
+            L.check(L.load().pcc_edgeconv_backward(
+                b, n, idx.shape[2], c, L.ptr(uv), L.ptr(idx), None, None, L.ptr(mean), L.ptr(invstd), AFFINE, ACT_NONE,
+                0.0, L.ptr(exty), None, L.ptr(slot), L.ptr(g), L.ptr(guv), None, None, L.stream_of(uv)),
+                "graph_max_pooling backward")
+        return guv[:, :, :c].transpose(1, 2).contiguous(), None
+
+
+def graph_max_pool(x: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(x, contiguous=False)
+    return _GraphMaxPool.apply(x, indices.contiguous())
+
+
 def _act_code(act: nn.Module | None) -> tuple[int, float] | None:
     if act is None or isinstance(act, nn.Identity):
         return ACT_NONE, 0.0

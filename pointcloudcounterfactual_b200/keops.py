@@ -19,10 +19,20 @@ import torch
 from . import _lib as L
 
 
+def _same_view(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride() and a.dtype == b.dtype
+            and a.device == b.device)
+
+
 def argkmin(q: torch.Tensor, r: torch.Tensor, k: int, return_dist: bool = False):
-    """q (B,Nq,C), r (B,Nr,C) CUDA fp32 -> idx (B,Nq,k) int64, ascending by (squared distance, index)."""
+    """q (B,Nq,C), r (B,Nr,C) CUDA fp32 -> idx (B,Nq,k) int64, ascending by (squared distance, index).
+
+    When both operands are the same storage -- the reference's ``pykeops_knn`` builds its expression on (x, x),
+    neighbour_ops.py:79-81 -- the C entry point sees q == r and runs the point-major SELF kNN route: the
+    warp-cooperative xyz kernel for C == 3, the tcgen05 kernels for C % 32 == 0 (``pcc_argkmin``, csrc/knn.cu)."""
+    same = _same_view(q, r)
     q = q.contiguous()
-    r = r.contiguous()
+    r = q if same else r.contiguous()
     L.require_cuda(q, r)
     if q.dim() != 3 or r.dim() != 3 or q.size(0) != r.size(0) or q.size(2) != r.size(2):
         raise RuntimeError("argkmin expects (B,Nq,C) and (B,Nr,C)")
@@ -85,6 +95,25 @@ class SquareDistance:
 
     def __init__(self, ti: torch.Tensor, tj: torch.Tensor):
         self.ti, self.tj = ti, tj
+        self._nn = None  # (versions, dist1, idx1, dist2, idx2) of one fused Chamfer launch
+
+    def _nn_pair(self):
+        """xyz clouds, k = 1 (``pykeops_chamfer``, metrics_and_losses.py:32-36: argmin over axis 1, then over axis 2, of ONE
+        expression): both directions come from ONE ``pcc_nndistance`` launch, kept for the second reduction.  Distances
+        and the lowest-index tie rule are those of the reference's own Chamfer kernel (nndistance.cu:2-124)."""
+        ti, tj = self.ti, self.tj
+        ok = (ti.is_cuda and tj.is_cuda and ti.dtype == torch.float32 and tj.dtype == torch.float32 and ti.dim() == 3
+              and tj.dim() == 3 and ti.size(2) == 3 and tj.size(2) == 3 and ti.size(0) == tj.size(0) and ti.size(0) > 0
+              and ti.size(1) > 64 and tj.size(1) > 64)  # tiny problems (vector quantisation) keep the argKmin route
+        if not ok:
+            return None
+        ver = (ti._version, tj._version)
+        if self._nn is None or self._nn[0] != ver:
+            from .structural_losses.structural_losses_backend import NNDistance
+
+            d1, i1, d2, i2 = NNDistance(ti.detach().contiguous(), tj.detach().contiguous())
+            self._nn = (ver, d1, i1, d2, i2)
+        return self._nn[1:]
 
     def argKmin(self, K: int, dim: int = 2, axis: int | None = None) -> torch.Tensor:
         dim = dim if axis is None else axis
@@ -95,7 +124,11 @@ class SquareDistance:
         raise NotImplementedError("argKmin over dim 1 or 2 only")
 
     def argmin(self, axis: int | None = None, dim: int | None = None) -> torch.Tensor:
-        return self.argKmin(1, dim=axis if axis is not None else dim)
+        d = axis if axis is not None else dim
+        nn = self._nn_pair() if d in (1, 2) else None
+        if nn is not None:  # axis 2: nearest tj for every ti (idx1); axis 1: nearest ti for every tj (idx2)
+            return (nn[1] if d == 2 else nn[3]).to(torch.int64).unsqueeze(-1)
+        return self.argKmin(1, dim=d)
 
     def _dense(self) -> torch.Tensor:
         # only quantize.py's tiny (B*n_codes, 1, 16) case reaches this; dense torch keeps it differentiable (the
@@ -112,6 +145,9 @@ class SquareDistance:
 
     def min(self, axis: int | None = None, dim: int | None = None) -> torch.Tensor:
         d = axis if axis is not None else dim
+        nn = self._nn_pair() if d in (1, 2) else None
+        if nn is not None:
+            return (nn[0] if d == 2 else nn[2]).unsqueeze(-1)
         q, r = (self.ti, self.tj) if d == 2 else (self.tj, self.ti)
         return argkmin(q, r, 1, return_dist=True)[1]
 

@@ -151,12 +151,14 @@ class PipelinedLossStep:
     other staging buffer on a copy stream.  Every step still moves its inputs host -> device and its per-cloud loss
     device -> host; only the waiting is overlapped.  Usage::
 
-        pipe = PipelinedLossStep(chamfer_emd, recon_host, ref_host, device)   # pinned host tensors
-        pipe.prefetch()                    # copies for the first step
-        for batch in loader:
-            loss_prev = pipe.step()        # runs the step whose inputs were prefetched, prefetches the next one from the
-            ...                            # pinned buffers (refill them after step() returns), returns the PREVIOUS
-        last = pipe.drain()                # step's per-cloud loss on the host (None on the first call)
+        pipe = PipelinedLossStep(chamfer_emd, recon_host, ref_host, device)   # pinned host tensors holding batch 0
+        pipe.prefetch()                    # batch 0 starts travelling to the device
+        for i in range(steps):
+            pipe.wait_prefetch()           # the DMA that reads the pinned buffers has finished: only now may they be
+            fill(recon_host, ref_host)     # rewritten, with batch i+1 (rewriting earlier races with the copy in flight)
+            loss_prev = pipe.step()        # runs batch i, starts the copy of batch i+1, returns the per-cloud loss of
+            ...                            # batch i-1 on the host (None on the first call)
+        last = pipe.drain()
     """
 
     def __init__(self, loss_fn, recon_host: torch.Tensor, ref_host: torch.Tensor, device: torch.device):
@@ -184,6 +186,11 @@ class PipelinedLossStep:
             self._stage[i][0].copy_(self._recon_h, non_blocking=True)
             self._stage[i][1].copy_(self._ref_h, non_blocking=True)
             self._ready[i].record(self._copy)
+
+    def wait_prefetch(self) -> None:
+        """Block the host until the most recent ``prefetch()`` (the one ``step()`` issues included) has read the pinned
+        host buffers -- the only moment from which they may be refilled.  Waits for that copy alone, not for the device."""
+        self._ready[self._next].synchronize()
 
     def step(self):
         i = self._next

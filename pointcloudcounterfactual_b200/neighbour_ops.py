@@ -8,6 +8,7 @@ for callers that ask for them by name.
 """
 from __future__ import annotations
 
+import warnings
 from typing import Any
 
 import numpy as np
@@ -121,11 +122,36 @@ class _GraphGather(Function):
         return gx, None, None
 
 
-def _fused_gather_ok(x: torch.Tensor, indices: torch.Tensor, k: int) -> bool:
+_WARNED: set[str] = set()
+
+
+def _composed(what: str, why: str) -> None:
+    """The fused kernels have shape limits; outside them the op is COMPOSED from this package's kNN kernel and torch
+    indexing (the reference's own op sequence) -- never silently: one warning per operator and reason."""
+    key = what + why
+    if key not in _WARNED:
+        _WARNED.add(key)
+        warnings.warn(f"pointcloudcounterfactual_b200.{what}: {why}; composing the op from knn + torch indexing "
+                      "(slower than the fused sm_100a kernel)", RuntimeWarning, stacklevel=3)
+
+
+def _fused_gather_ok(x: torch.Tensor, indices: torch.Tensor, k: int, what: str = "get_neighbours") -> bool:
     """The fused kernels cover CUDA fp32 features, int64 (B,N,k) indices, k <= 32, N <= 8192; anything else (and
-    empty batches) takes the reference's torch composition."""
-    return (x.is_cuda and x.dtype == torch.float32 and indices.dtype == torch.int64 and indices.dim() == 3
-            and x.shape[0] > 0 and k <= 32 and x.shape[2] <= 8192 and tuple(indices.shape) == (x.shape[0], x.shape[2], k))
+    empty batches) takes the reference's torch composition, with a warning."""
+    if not x.is_cuda:
+        raise RuntimeError(f"{what}: CUDA tensors only (no CPU fallback in pointcloudcounterfactual_b200)")
+    if x.shape[0] == 0:
+        return False
+    if x.dtype != torch.float32 or indices.dtype != torch.int64:
+        _composed(what, f"dtypes {x.dtype} / {indices.dtype} (fused kernel: float32 features, int64 indices)")
+        return False
+    if indices.dim() != 3 or tuple(indices.shape) != (x.shape[0], x.shape[2], k):
+        _composed(what, f"indices of shape {tuple(indices.shape)} (fused kernel: (B,N,k))")
+        return False
+    if k > 32 or x.shape[2] > 8192:
+        _composed(what, f"k={k}, N={x.shape[2]} (fused kernel: k <= 32, N <= 8192)")
+        return False
+    return True
 
 
 def get_neighbours(x: torch.Tensor, indices: torch.Tensor, k: int):
@@ -150,16 +176,18 @@ def get_local_covariance(x: torch.Tensor, indices: torch.Tensor, k: int = 16) ->
 
 def graph_max_pooling(x: torch.Tensor, indices: torch.Tensor, k: int = 16) -> torch.Tensor:
     """(:106-110) max over the k neighbours of every point, (B,C,N) -> (B,C,N) (LDGCNN, src/module/encoders.py:84).
-    On CUDA this is the fused EdgeConv edge pass with the identity as convolution (u_j = x_j, v_i = 0, no
-    normalisation): no (B,C,N,k) tensor, bit-identical values, the gradient goes to the first arg-max slot."""
+    On CUDA this is the fused EdgeConv edge pass with u_j = x_j, v_i = 0 and no normalisation (the operands are copied,
+    not multiplied by an identity: no GEMM, so TF32 settings cannot touch the values): no (B,C,N,k) tensor,
+    bit-identical values, the gradient goes to the first arg-max slot."""
     if not indices.numel():
         indices = knn(x, k)
     c = x.shape[1]
-    if _fused_gather_ok(x, indices, k) and c % 4 == 0 and 4 <= c <= 1024 and k <= 64:
-        from . import edgeconv  # late import: edgeconv builds on this module
+    if _fused_gather_ok(x, indices, k, "graph_max_pooling"):
+        if c % 4 == 0 and 4 <= c <= 1024:
+            from . import edgeconv  # late import: edgeconv builds on this module
 
-        eye = torch.eye(c, dtype=x.dtype, device=x.device)
-        return edgeconv.edge_conv_max(x, indices, torch.cat([eye, eye], dim=1), bn_mode=edgeconv.AFFINE)
+            return edgeconv.graph_max_pool(x, indices)
+        _composed("graph_max_pooling", f"C={c} (fused kernel: C % 4 == 0, 4 <= C <= 1024)")
     return get_neighbours(x, indices, k)[1].max(dim=-1)[0]
 
 
@@ -167,7 +195,7 @@ def get_graph_features(x: torch.Tensor, indices: torch.Tensor, k: int = 20) -> t
     """(:113-119) EdgeConv input: cat(neighbour - centre, centre) -> (B, 2C, N, k)."""
     if not indices.numel():
         indices = knn(x, k)
-    if _fused_gather_ok(x, indices, k):
+    if _fused_gather_ok(x, indices, k, "get_graph_features"):
         return indices, _GraphGather.apply(x.contiguous(), indices.contiguous(), 1)
     indices_out, neighbours = get_neighbours(x, indices, k)
     centre = x.unsqueeze(3).expand(-1, -1, -1, k)
@@ -207,6 +235,11 @@ def graph_filtering(x: torch.Tensor, k: int = 4) -> torch.Tensor:
             and 2 <= k <= 8 and k <= x.shape[2] <= 6144):
         xc = x.contiguous()
         return _GraphFiltering.apply(xc, knn(xc.detach(), k))
+    if not x.is_cuda:
+        raise RuntimeError("graph_filtering: CUDA tensors only (no CPU fallback in pointcloudcounterfactual_b200)")
+    if x.shape[0] > 0:
+        _composed("graph_filtering", f"input {tuple(x.shape)} {x.dtype}, k={k} (fused kernel: float32 (B,3,N), 2 <= k <= 8, "
+                                     "k <= N <= 6144)")
     neighbours = get_neighbours(x, indices=torch.empty(0), k=k)[1][..., 1:]
     diff = x.unsqueeze(-1) - neighbours
     dist = torch.sqrt((diff * diff).sum(1).abs())

@@ -170,7 +170,7 @@ def test_pipelined_loss_step_equals_eager(cuda):
     pipe.prefetch()
     got_losses, got_grads = [], []
     for i in range(5):
-        torch.cuda.synchronize()  # the prefetch of batch i has read the pinned buffers: refill them for batch i+1
+        pipe.wait_prefetch()  # the prefetch of batch i has read the pinned buffers (no device-wide sync): refill for i+1
         if i + 1 < 5:
             rh.copy_(batches[i + 1][0]), th.copy_(batches[i + 1][1])
         prev = pipe.step()
