@@ -585,27 +585,11 @@ static int am_levels(cudaStream_t st, AmLevels *out) {
   return 0;
 }
 
-// keep freed workspace memory cached in the stream-ordered pool (default threshold 0 returns it to the OS at every
-// synchronisation, which makes the next cudaMallocAsync cost milliseconds)
-static void am_pool_setup() {
-  static bool done[64] = {false};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
-  cudaGetLastError();
-  done[dev] = true;
-}
-
 // Phase A: runs the 27 sweeps; leaves remainL/remainR in temp and the per-level factors in ws.
 static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, float *temp, AmWorkspace &ws,
                     size_t extra_floats, const AmLevels &lv, cudaStream_t st, int *launches) {
-  am_pool_setup();
   const size_t nfl = (size_t)AM_LEVELS * b * n, nfr = (size_t)AM_LEVELS * b * m;
-  cudaError_t e = cudaMallocAsync((void **)&ws.base, sizeof(float) * (nfl + nfr + extra_floats), st);
+  cudaError_t e = ws_alloc((void **)&ws.base, sizeof(float) * (nfl + nfr + extra_floats), st);
   if (e != cudaSuccess) return (int)e;
   ws.fL = ws.base;
   ws.fR = ws.base + nfl;
@@ -728,7 +712,7 @@ extern "C" __attribute__((visibility("default"))) int pcc_matchcost(int b, int n
   if (b > 65535) return PCC_ENOTSUP;
   const int parts = (m + MC_ROWS - 1) / MC_ROWS;
   float *partial = nullptr;
-  cudaError_t e = cudaMallocAsync((void **)&partial, sizeof(float) * (size_t)b * parts, st);
+  cudaError_t e = ws_alloc((void **)&partial, sizeof(float) * (size_t)b * parts, st);
   if (e != cudaSuccess) return (int)e;
   matchcost_kernel<<<dim3(parts, b), MC_THREADS, 0, st>>>(n, m, xyz1, xyz2, match, partial);
   am_cost_reduce_kernel<<<(b + 127) / 128, 128, 0, st>>>(b, parts, partial, out);

@@ -425,7 +425,7 @@ extern "C" __attribute__((visibility("default"))) int pcc_emd_forward(int b, int
     int *cnt = unass_cnt;
     int *pool = nullptr;
     if (cnt == nullptr || b * AUC_CTAS > 512) {
-      cudaError_t e = cudaMallocAsync((void **)&pool, sizeof(int) * (size_t)b * AUC_CTAS, (cudaStream_t)stream);
+      cudaError_t e = ws_alloc((void **)&pool, sizeof(int) * (size_t)b * AUC_CTAS, (cudaStream_t)stream);
       if (e != cudaSuccess) return (int)e;
       cnt = pool;
     }

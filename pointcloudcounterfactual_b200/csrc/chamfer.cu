@@ -632,7 +632,7 @@ static int nn_forward(int b, int n, const float *xyz, int m, const float *xyz2, 
   if ((long long)nrb * ncc > 2147483647LL) return PCC_ENOTSUP;
   NnPart *scratch = nullptr;
   const size_t nrow = (size_t)b * ncc * n, ncol = (size_t)b * nrb * m;
-  cudaError_t e = cudaMallocAsync((void **)&scratch, sizeof(NnPart) * (nrow + ncol), st);
+  cudaError_t e = ws_alloc((void **)&scratch, sizeof(NnPart) * (nrow + ncol), st);
   if (e != cudaSuccess) return (int)e;
   NnPart *rowpart = scratch, *colpart = scratch + nrow;
   note_route(R_NN_SYM);

@@ -36,6 +36,12 @@ enum Route {
 extern std::atomic<uint64_t> g_routes[R_COUNT];
 inline void note_route(Route r) { g_routes[r].fetch_add(1, std::memory_order_relaxed); }
 
+// Stream-ordered workspace allocation from a pool PRIVATE to this library (one per device, created on first use; lib.cu).
+// Freed workspaces stay cached in it (release threshold = max: a default-threshold pool returns the memory to the OS at
+// every synchronisation and the next allocation costs milliseconds) -- but only this library's own scratch, never the
+// device's default pool that other libraries and captured graphs allocate from.  Release with cudaFreeAsync.
+cudaError_t ws_alloc(void **ptr, size_t bytes, cudaStream_t st);
+
 // Opt-in to more than 48 KiB of dynamic shared memory.  The attribute is PER DEVICE: one process may drive several GPUs
 // (the Python wrappers take tensors on any device), so the high-water mark is kept per device ordinal.
 template <typename Kernel>

@@ -776,7 +776,7 @@ pcc_edgeconv_forward(int b, int n, int k, int cout, const float *uv, const int64
   }
   char *ws = nullptr;
   const size_t part_bytes = sizeof(double) * 2 * cout * nparts, aff_bytes = sizeof(float) * 2 * cout;
-  cudaError_t e = cudaMallocAsync((void **)&ws, part_bytes + aff_bytes, st);
+  cudaError_t e = ws_alloc((void **)&ws, part_bytes + aff_bytes, st);
   if (e != cudaSuccess) return (int)e;
   double *partials = reinterpret_cast<double *>(ws);
   float *scale = reinterpret_cast<float *>(ws + part_bytes), *shift = scale + cout;
@@ -818,7 +818,7 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
                raw_bytes = up(sizeof(float) * (size_t)b * n * 2 * cout),
                pbuf_bytes = up(sizeof(float) * (size_t)b * nchunks * 2 * cout);
   char *ws = nullptr;
-  cudaError_t e = cudaMallocAsync((void **)&ws, part_bytes + dz_bytes + coef_bytes + off_bytes + 2 * cnt_bytes +
+  cudaError_t e = ws_alloc((void **)&ws, part_bytes + dz_bytes + coef_bytes + off_bytes + 2 * cnt_bytes +
                                                     2 * rev_bytes + raw_bytes + pbuf_bytes, st);
   if (e != cudaSuccess) return (int)e;
   char *w = ws;

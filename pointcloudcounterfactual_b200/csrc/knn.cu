@@ -626,7 +626,7 @@ static int launch_knn3(int b, int n, int k, bool pm, const float *x, int64_t *id
   }
   note_route(R_KNN3W);
   int *hard = nullptr;
-  cudaError_t e = cudaMallocAsync((void **)&hard, sizeof(int) * b, st);
+  cudaError_t e = ws_alloc((void **)&hard, sizeof(int) * b, st);
   if (e != cudaSuccess) return (int)e;
   cudaMemsetAsync(hard, 0, sizeof(int) * b, st);
   int rc;

@@ -444,7 +444,7 @@ int knn_tc_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t *
   if (!tc_get_encode()) return PCC_ENOTSUP;
   float *ws = nullptr;
   const size_t nxt = (size_t)b * n * c, nn = (size_t)b * n;
-  cudaError_t e = cudaMallocAsync((void **)&ws, sizeof(float) * (nxt + nn) + sizeof(unsigned int) * b, st);
+  cudaError_t e = ws_alloc((void **)&ws, sizeof(float) * (nxt + nn) + sizeof(unsigned int) * b, st);
   if (e != cudaSuccess) return (int)e;
   const float *xT = pm ? x : ws;
   float *norms = ws + nxt;

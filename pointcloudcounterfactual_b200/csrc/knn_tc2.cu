@@ -588,7 +588,7 @@ int knn_tc2_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t 
   const int npad = (n + r - 1) / r * r;
   float *ws = nullptr;
   const size_t nxt = (size_t)b * n * c, nn = (size_t)b * npad;
-  cudaError_t e = cudaMallocAsync((void **)&ws, sizeof(float) * (nxt + 4 * nn), st);
+  cudaError_t e = ws_alloc((void **)&ws, sizeof(float) * (nxt + 4 * nn), st);
   if (e != cudaSuccess) return (int)e;
   float *xT = ws, *norms = ws + nxt, *bounds = norms + nn;
   int rc;

@@ -3,6 +3,8 @@
 
 #include <string.h>
 
+#include <mutex>
+
 #ifdef PCC_PDL
 #include <stdlib.h>
 #endif
@@ -12,6 +14,35 @@ std::atomic<uint64_t> g_launches{0};
 std::atomic<uint64_t> g_routes[R_COUNT];
 static const char *const kRouteNames[R_COUNT] = {"knn3w", "knn3_thread", "knn_tc2", "knn_tc1", "knn_simt", "argmin_small",
                                                  "nn_sym", "nn_asym", "nn_grid", "knn3_grid", "pm_self"};
+cudaError_t ws_alloc(void **ptr, size_t bytes, cudaStream_t st) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, st);
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      e = cudaMemPoolCreate(&pools[dev], &props);
+      if (e != cudaSuccess) {
+        pools[dev] = nullptr;
+        return e;
+      }
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    pool = pools[dev];
+  }
+  return cudaMallocFromPoolAsync(ptr, bytes, pool, st);
+}
+
 #ifdef PCC_PDL
 unsigned pdl_mask() {  // read at every launch (captured graphs keep what was set at capture time): A/B runs in one process
   const char *e = getenv("PCC_PDL_MASK");
