@@ -15,50 +15,59 @@
 //                                the fp32 accumulation of the tensor core.  Rows are stored in the UMMA canonical
 //                                K-major no-swizzle order (8-row groups of 4 core matrices), i.e. a tile of rows is one
 //                                contiguous block that a plain cp.async.bulk brings into shared memory.
-//   main   nn_tc_kernel          CTA = 128 queries of one cloud and direction against all keys.  warp 0 streams key tiles
-//                                (cp.async.bulk + mbarrier), warp 1 issues tcgen05.mma kind::f16 (bf16, M=128, N=128,
-//                                K=16 x 2) into a double-buffered TMEM accumulator, four epilogue warps own one query per
-//                                thread: tcgen05.ld of 32 scores, their minimum (the only per-score work: one 3-input
-//                                FMNMX per two scores), and a short list of the 32-key chunks whose minimum is within
-//                                the error band of the running row minimum.  After the last tile every listed chunk that
-//                                is still within the band of the FINAL minimum is evaluated exactly
-//                                (d = fma(dz,dz,fma(dx,dx,dy*dy)), ascending key index, strict '<').
+//   main   nn_tc_kernel          persistent CTA = one cloud, one direction, a contiguous range of 128-query tiles.  ALL keys
+//                                of the cloud are brought into shared memory once (cp.async.bulk + one mbarrier per key
+//                                tile) and stay there: operand traffic from L2 is one pass per CTA instead of one pass
+//                                per query tile (a streaming version of this kernel was L2-bound at 4.8 TB/s, 82 us).
+//                                warp 0 loads, warp 1 issues tcgen05.mma kind::f16 (bf16, M=128, N=256) into a
+//                                double-buffered TMEM accumulator (512 columns), sixteen epilogue warps in four sets own
+//                                one query per thread and two 32-key chunks of every key tile: tcgen05.ld, the minimum
+//                                of the 32 scores (the only per-score work: one 3-input FMNMX per two scores) and a short
+//                                list of the chunks whose minimum is within the error band of the running row minimum.
+//                                At the end of a query tile the sets exchange their row minima and keep, per query, the
+//                                chunks still within the band of the FINAL minimum (two slots per set); after the last
+//                                tile every recorded chunk is evaluated exactly
+//                                (d = fma(dz,dz,fma(dx,dx,dy*dy)), lexicographic minimum of (distance, key index)).
 //   The candidate set provably contains the exact nearest neighbour and every key tied with it: the score of pair
 //   (i,j) differs from the exact distance by at most eps_ij = NT_CEPS (|a_i|^2 + |b_j|^2) (measured: tools/nn_tc_probe),
-//   and a chunk is kept when its minimum is <= row minimum + 2 max_j eps_ij.  Queries whose list overflows (massive ties),
+//   and a chunk is kept when its minimum is <= row minimum + 2 max_j eps_ij.  Queries whose record overflows (massive ties),
 //   whose scores are not finite (NaN / inf coordinates) or whose first key is NaN (the reference lets a NaN at k = 0
 //   stick, nndistance.cu:26) are redone by an exact warp-cooperative scan with the reference's NaN semantics.
 #include "tc_ptx.cuh"
 
 namespace pcc {
 
-constexpr int NT_M = 128;          // queries per CTA = TMEM lanes
-constexpr int NT_N = 128;          // keys per tile = accumulator columns per TMEM stage
+constexpr int NT_M = 128;          // queries per tile = TMEM lanes
+constexpr int NT_N = 256;          // keys per tile = accumulator columns per TMEM stage
 constexpr int NT_ROWB = 64;        // bytes per operand row: 32 bf16
-constexpr int NT_STAGES = 4;       // key tiles in flight in shared memory
-constexpr int NT_CAP = 16;         // candidate chunks per query and warp set
-constexpr int NT_THREADS = 320;    // warp 0 producer, warp 1 MMA, warps 2..5 / 6..9 epilogue of the even / odd key tiles
-constexpr int NT_CPS = NT_N / 64;   // 32-key chunks per tile and warp set (the two sets split every tile)
+constexpr int NT_SETS = 4;         // epilogue warp sets (4 warps each: one per TMEM lane quarter)
+constexpr int NT_CPS = NT_N / 32 / NT_SETS;  // 32-key chunks per tile and set
+constexpr int NT_CAP = 8;          // running candidate chunks per query and set
+constexpr int NT_REC = 2;          // recorded candidate chunks per query and set
+constexpr int NT_THREADS = 64 + 128 * NT_SETS;  // warp 0 producer, warp 1 MMA, 16 epilogue warps
+constexpr int NT_EPI = 128 * NT_SETS;
 constexpr int NT_PREP_PARTS = 4;   // CTAs per cloud and side in the operand preparation
 constexpr int NT_TILE_BYTES = NT_N * NT_ROWB;
+constexpr int NT_MAX_KEYS = 2048;  // resident keys (8 tiles = 128 KiB) ...
+constexpr int NT_MAX_Q = 2048;     // ... and queries per CTA (records)
 // |score - exact distance| <= NT_CEPS * (|a|^2 + |b|^2): bf16x3 products dropped (3 * 2^-24 |a||b|), fp32 accumulation of
 // 24 non-zero terms in the tensor core, rounding of the translated coordinates and of the canonical fma chain.
-// tools/nn_tc_probe measures the actual maximum: 7.5e-7 over the S1 / S2 / S3 families; 2^-17 leaves a factor of 10.
+// tools/nn_tc_probe measures the actual maximum: 1.2e-6 over the S1 / S2 / S3 families; 2^-17 leaves a factor of 6.
 constexpr float NT_CEPS = 7.6293945e-6f;
 
 struct NtCtl {
-  uint64_t full[NT_STAGES], empty[NT_STAGES], tfull[2], tempty[2], afull;
+  uint64_t kfull[NT_MAX_KEYS / NT_N], afull[2], aempty[2], tfull[2], tempty[2];
   uint32_t tmem_base;
 };
 struct NtSmem {
-  unsigned char a[NT_M * NT_ROWB];
-  unsigned char b[NT_STAGES][NT_TILE_BYTES];
-  float lst_v[2][NT_CAP][NT_M];
-  unsigned short lst_c[2][NT_CAP][NT_M];
-  float mrow[2][NT_M];   // row minimum of each warp set
-  float rd[NT_M];        // best exact (distance, index) found by set 1
-  int ri[NT_M];
-  unsigned char flag[2][NT_M];  // bit 0: needs the exact scan, bit 1: found a candidate
+  unsigned char keys[NT_MAX_KEYS * NT_ROWB];
+  unsigned char a[2][NT_M * NT_ROWB];
+  float lst_v[NT_SETS][NT_CAP][NT_M];
+  unsigned short lst_c[NT_SETS][NT_CAP][NT_M];
+  float mrow[NT_SETS][NT_M];           // row minimum of each set (exchanged at the end of a query tile)
+  unsigned char flag[NT_SETS][NT_M];   // set asks for the exact scan of this query
+  unsigned short rec_c[NT_MAX_Q][NT_SETS][NT_REC];  // per query of the CTA: candidate chunks of each set
+  unsigned char rec_n[NT_MAX_Q][NT_SETS];           // ... how many; 255 = exact scan
   NtCtl ctl;
 };
 
@@ -217,7 +226,7 @@ __device__ __forceinline__ void nn_exact_warp(float qx, float qy, float qz, cons
   }
 }
 
-__device__ __forceinline__ void nt_bar_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void nt_bar_epilogue() { asm volatile("bar.sync 1, %0;" ::"n"(NT_EPI) : "memory"); }
 
 // rare: the list of candidate chunks is full -> keep what is still within the band of the current minimum
 __device__ __noinline__ int nt_compact(float *lv, unsigned short *lc, float lim) {
@@ -235,9 +244,10 @@ __device__ __noinline__ int nt_compact(float *lv, unsigned short *lc, float lim)
   return w2;
 }
 
-// grid (ceil(max(n,m)/128), b, 2): blockIdx.z = direction (0: queries xyz1, keys xyz2; 1: swapped)
-__global__ void __launch_bounds__(NT_THREADS, 2)
-nn_tc_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2, int npad1, int npad2,
+// grid (splits, b, 2): blockIdx.z = direction (0: queries xyz1, keys xyz2; 1: swapped); blockIdx.x owns the query tiles
+// [blockIdx.x * qt_per, ...).
+__global__ void __launch_bounds__(NT_THREADS, 1)
+nn_tc_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2, int npad1, int npad2, int qt_per,
              const unsigned char *__restrict__ opsA1, const unsigned char *__restrict__ opsB1,
              const unsigned char *__restrict__ opsA2, const unsigned char *__restrict__ opsB2,
              const float4 *__restrict__ key41, const float4 *__restrict__ key42, const float *__restrict__ nmax,
@@ -252,11 +262,13 @@ nn_tc_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restri
   NtSmem &S = *reinterpret_cast<NtSmem *>(smem_raw);
   const int dir = blockIdx.z;
   const int nq = dir ? m : n, nr = dir ? n : m;
-  const int q0 = blockIdx.x * NT_M;
-  if (q0 >= nq) return;  // uniform per CTA
   const size_t cloud = blockIdx.y;
   const int npadq = dir ? npad2 : npad1, npadr = dir ? npad1 : npad2;
-  const unsigned char *opsq = (dir ? opsA2 : opsA1) + (cloud * (size_t)npadq + q0) * NT_ROWB;
+  const int qt_total = (nq + NT_M - 1) / NT_M;
+  const int qt0 = blockIdx.x * qt_per, qt1 = min(qt_total, qt0 + qt_per);
+  if (qt0 >= qt1) return;  // uniform per CTA
+  const int nqt = qt1 - qt0;
+  const unsigned char *opsq = (dir ? opsA2 : opsA1) + cloud * (size_t)npadq * NT_ROWB;
   const unsigned char *opsr = (dir ? opsB1 : opsB2) + cloud * (size_t)npadr * NT_ROWB;
   const float4 *q4 = (dir ? key42 : key41) + cloud * (size_t)npadq;
   const float4 *r4 = (dir ? key41 : key42) + cloud * (size_t)npadr;
@@ -268,15 +280,13 @@ nn_tc_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restri
   NtCtl *ctl = &S.ctl;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NT_STAGES; ++s) {
-      mbar_init(&ctl->full[s], 1);
-      mbar_init(&ctl->empty[s], 1);
-    }
+    for (int t = 0; t < NT_MAX_KEYS / NT_N; ++t) mbar_init(&ctl->kfull[t], 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->afull[s], 1);
+      mbar_init(&ctl->aempty[s], 1);
       mbar_init(&ctl->tfull[s], 1);
-      mbar_init(&ctl->tempty[s], 8);
+      mbar_init(&ctl->tempty[s], 4 * NT_SETS);
     }
-    mbar_init(&ctl->afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&ctl->tmem_base, 2 * NT_N);
@@ -284,7 +294,7 @@ nn_tc_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restri
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
-#ifdef NT_DEBUG_SCORES
+#ifdef NT_DEBUG_STAMPS
   const bool probe_cta = stats && blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 0;
   const long long t_start = clock64();
 #define NT_STAMP(slot) if (probe_cta && lane == 0) stats[slot] = (unsigned int)(clock64() - t_start)
@@ -293,16 +303,20 @@ nn_tc_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restri
 #endif
 
   if (warp == 0) {
-    // ===== producer: the query tile once, then the key tiles, each one contiguous block =====
+    // ===== producer: first query tile, ALL key tiles (they stay), then the remaining query tiles through two slots =====
     if (lane == 0) {
-      mbar_expect_tx(&ctl->afull, NT_M * NT_ROWB);
-      bulk_load_1d(S.a, opsq, NT_M * NT_ROWB, &ctl->afull);
+      mbar_expect_tx(&ctl->afull[0], NT_M * NT_ROWB);
+      bulk_load_1d(S.a[0], opsq + (size_t)qt0 * NT_M * NT_ROWB, NT_M * NT_ROWB, &ctl->afull[0]);
       for (int t = 0; t < ntile; ++t) {
-        const int s = t % NT_STAGES, par = (t / NT_STAGES) & 1;
-        mbar_wait(&ctl->empty[s], par ^ 1);
-        mbar_expect_tx(&ctl->full[s], NT_TILE_BYTES);
-        bulk_load_1d(S.b[s], opsr + (size_t)t * NT_TILE_BYTES, NT_TILE_BYTES, &ctl->full[s]);
-        if (t == 0) NT_STAMP(2);
+        mbar_expect_tx(&ctl->kfull[t], NT_TILE_BYTES);
+        bulk_load_1d(S.keys + (size_t)t * NT_TILE_BYTES, opsr + (size_t)t * NT_TILE_BYTES, NT_TILE_BYTES, &ctl->kfull[t]);
+      }
+      NT_STAMP(2);
+      for (int i = 1; i < nqt; ++i) {
+        const int sa = i & 1;
+        mbar_wait(&ctl->aempty[sa], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&ctl->afull[sa], NT_M * NT_ROWB);
+        bulk_load_1d(S.a[sa], opsq + (size_t)(qt0 + i) * NT_M * NT_ROWB, NT_M * NT_ROWB, &ctl->afull[sa]);
       }
       NT_STAMP(3);
     }
@@ -310,165 +324,168 @@ nn_tc_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restri
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t IDESC = umma_idesc_bf16(NT_M, NT_N);
-      mbar_wait(&ctl->afull, 0);
-      const uint32_t a_addr = smem_u32(S.a);
-      for (int t = 0; t < ntile; ++t) {
-        const int s = t % NT_STAGES, par = (t / NT_STAGES) & 1;
-        const int acc = t & 1, apar = (t >> 1) & 1;
-        mbar_wait(&ctl->tempty[acc], apar ^ 1);  // the warp set of this accumulator has drained it
-        mbar_wait(&ctl->full[s], par);
-        fence_after();
-        const uint32_t b_addr = smem_u32(S.b[s]);
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * NT_N);
+      int it = 0;
+      for (int i = 0; i < nqt; ++i) {
+        const int sa = i & 1;
+        mbar_wait(&ctl->afull[sa], (i >> 1) & 1);
+        const uint32_t a_addr = smem_u32(S.a[sa]);
+        for (int t = 0; t < ntile; ++t, ++it) {
+          const int acc = it & 1;
+          if (i == 0) mbar_wait(&ctl->kfull[t], 0);
+          mbar_wait(&ctl->tempty[acc], ((it >> 1) & 1) ^ 1);  // every epilogue warp has this accumulator in registers
+          fence_after();
+          const uint32_t b_addr = smem_u32(S.keys + (size_t)t * NT_TILE_BYTES);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * NT_N);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)  // K = 16 bf16 per instruction = two core matrices = 256 B further along K
-          mma_bf16(tmem_d, umma_desc_k32(a_addr + ks * 256), umma_desc_k32(b_addr + ks * 256), IDESC, ks ? 1u : 0u);
-        mma_commit(&ctl->empty[s]);     // shared-memory stage free once the MMAs have read it
-        mma_commit(&ctl->tfull[acc]);   // accumulator ready
-        if (t == 0) NT_STAMP(4);
+          for (int ks = 0; ks < 2; ++ks)  // K = 16 bf16 per instruction = two core matrices = 256 B further along K
+            mma_bf16(tmem_d, umma_desc_k32(a_addr + ks * 256), umma_desc_k32(b_addr + ks * 256), IDESC, ks ? 1u : 0u);
+          mma_commit(&ctl->tfull[acc]);
+          if (it == 0) NT_STAMP(4);
+        }
+        mma_commit(&ctl->aempty[sa]);  // the query slot may be refilled once these MMAs have read it
       }
       NT_STAMP(5);
     }
   } else {
-    // ===== epilogue: one query per thread and warp set; the sets split the four 32-key chunks of every tile =====
+    // ===== epilogue: one query per thread and set; the four sets split the eight 32-key chunks of every key tile =====
     const int set = (warp - 2) >> 2;
     const int quarter = warp & 3;  // this warp may touch TMEM lanes 32*quarter .. +31
     const int e = quarter * 32 + lane;
-    const int q = q0 + e;
-    const bool live = q < nq;
     const float INF = __int_as_float(0x7f800000);
-    const float4 qc = q4[min(q, npadq - 1)];  // original coordinates (padding rows hold +inf)
     // band = 2 max_j eps_ij, with |a_i|^2 bounded by the maximum over the query side
     const float band = 2.f * NT_CEPS * (nmax[(size_t)dir * gridDim.y + cloud] + nmax[(size_t)(1 - dir) * gridDim.y + cloud]);
-    float mrow = INF;
-    int cnt = 0;
-    bool slow = false;
-    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * NT_CPS * 32);
     float *lv = &S.lst_v[set][0][e];
     unsigned short *lc = &S.lst_c[set][0][e];
-
-    for (int t = 0; t < ntile; ++t) {
-      const int acc = t & 1;
-      mbar_wait(&ctl->tfull[acc], (t >> 1) & 1);
-      fence_after();
-      if (warp == 2 && t == 0) NT_STAMP(9);
-      uint32_t w[NT_CPS][32];
+    const uint32_t tfull_a = smem_u32(&ctl->tfull[0]), tempty_a = smem_u32(&ctl->tempty[0]);
+    int it = 0;
+    for (int i = 0; i < nqt; ++i) {
+      float mrow = INF;
+      int cnt = 0;
+      bool slow = false;
+      for (int t = 0; t < ntile; ++t, ++it) {
+        const int acc = it & 1;
+        mbar_wait_a(tfull_a + acc * 8, (it >> 1) & 1);
+        fence_after();
+        if (warp == 2 && it == 0) NT_STAMP(9);
+        uint32_t w[NT_CPS][32];
 #pragma unroll
-      for (int c2 = 0; c2 < NT_CPS; ++c2)
-        tmem_ld32_issue(tlane + (uint32_t)(acc * NT_N + (set * NT_CPS + c2) * 32), w[c2]);
+        for (int c2 = 0; c2 < NT_CPS; ++c2) tmem_ld32_issue(tlane + (uint32_t)(acc * NT_N + c2 * 32), w[c2]);
 #pragma unroll
-      for (int c2 = 0; c2 < NT_CPS; ++c2) {
-        if (c2 == 0) {
+        for (int c2 = 0; c2 < NT_CPS; ++c2) {
+          if (c2 == 0) {
 #pragma unroll
-          for (int c3 = 0; c3 < NT_CPS; ++c3) tmem_ld_wait_dep(w[c3]);  // one wait covers every load issued above
-          fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ctl->tempty[acc]);  // the accumulator is in registers: the next MMA may overwrite it
-        }
-        const int ch = set * NT_CPS + c2;
-#ifdef NT_DEBUG_SCORES
-        if (dbg && cloud == 0 && dir == 0 && live)
-          for (int u = 0; u < 32; ++u) dbg[(size_t)q * npadr + t * NT_N + ch * 32 + u] = __uint_as_float(w[c2][u]);
-#endif
-        if (t == 0 && ch == 0) {
-          const float s0 = __uint_as_float(w[c2][0]);
-          slow = slow || (s0 != s0);  // a NaN distance to key 0 sticks in the reference
-        }
-        float c0 = fminf(__uint_as_float(w[c2][0]), __uint_as_float(w[c2][1]));
-        float c1 = fminf(__uint_as_float(w[c2][2]), __uint_as_float(w[c2][3]));
-#pragma unroll
-        for (int u = 4; u < 32; u += 4) {
-          c0 = fminf(fminf(__uint_as_float(w[c2][u]), __uint_as_float(w[c2][u + 1])), c0);
-          c1 = fminf(fminf(__uint_as_float(w[c2][u + 2]), __uint_as_float(w[c2][u + 3])), c1);
-        }
-        const float cm = fminf(c0, c1);
-        if (cm <= mrow + band) {
-          if (cnt == NT_CAP) cnt = nt_compact(lv, lc, fminf(mrow, cm) + band);
-          if (cnt < NT_CAP) {
-            lv[cnt * NT_M] = cm;
-            lc[cnt * NT_M] = (unsigned short)(t * (NT_N / 32) + ch);
-            ++cnt;
-          } else {
-            slow = true;  // more than NT_CAP chunks tie within the band
+            for (int c3 = 0; c3 < NT_CPS; ++c3) tmem_ld_wait_dep(w[c3]);  // one wait covers every load issued above
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(tempty_a + acc * 8);  // the accumulator is in registers: the next MMA may overwrite it
           }
+          const int ch = t * (NT_N / 32) + set * NT_CPS + c2;  // chunk = keys 32 ch .. 32 ch + 31
+#ifdef NT_DEBUG_SCORES
+          if (dbg && cloud == 0 && dir == 0 && (qt0 + i) * NT_M + e < nq)
+            for (int u = 0; u < 32; ++u) dbg[(size_t)((qt0 + i) * NT_M + e) * npadr + ch * 32 + u] = __uint_as_float(w[c2][u]);
+#endif
+          if (ch == 0) {
+            const float s0 = __uint_as_float(w[c2][0]);
+            slow = slow || (s0 != s0);  // a NaN distance to key 0 sticks in the reference
+          }
+          float c0 = fminf(__uint_as_float(w[c2][0]), __uint_as_float(w[c2][1]));
+          float c1 = fminf(__uint_as_float(w[c2][2]), __uint_as_float(w[c2][3]));
+#pragma unroll
+          for (int u = 4; u < 32; u += 4) {
+            c0 = fminf(fminf(__uint_as_float(w[c2][u]), __uint_as_float(w[c2][u + 1])), c0);
+            c1 = fminf(fminf(__uint_as_float(w[c2][u + 2]), __uint_as_float(w[c2][u + 3])), c1);
+          }
+          const float cm = fminf(c0, c1);
+          if (cm <= mrow + band) {
+            if (cnt == NT_CAP) cnt = nt_compact(lv, lc, fminf(mrow, cm) + band);
+            if (cnt < NT_CAP) {
+              lv[cnt * NT_M] = cm;
+              lc[cnt * NT_M] = (unsigned short)ch;
+              ++cnt;
+            } else {
+              slow = true;  // more than NT_CAP chunks tie within the band
+            }
+          }
+          mrow = fminf(mrow, cm);
         }
-        mrow = fminf(mrow, cm);
       }
+      // ---- end of the query tile: final row minimum over the sets, record the chunks still within its band ----
+      S.mrow[set][e] = mrow;
+      S.flag[set][e] = slow ? 1 : 0;
+      nt_bar_epilogue();
+      float mfin = S.mrow[0][e];
+      unsigned int fl = S.flag[0][e];
+#pragma unroll
+      for (int s2 = 1; s2 < NT_SETS; ++s2) {
+        mfin = fminf(mfin, S.mrow[s2][e]);
+        fl |= S.flag[s2][e];
+      }
+      const float lim = mfin + band;
+      const int ql = i * NT_M + e;
+      int nv = 0;
+      for (int r = 0; r < cnt; ++r)
+        if (lv[r * NT_M] <= lim) {
+          if (nv < NT_REC) S.rec_c[ql][set][nv] = lc[r * NT_M];
+          ++nv;
+        }
+      S.rec_n[ql][set] = (fl || !(mfin < INF) || nv > NT_REC) ? 255 : (unsigned char)nv;
+      nt_bar_epilogue();  // the exchange buffers are free for the next query tile
     }
-
     if (warp == 2) NT_STAMP(6);
-    // ---- both sets: final row minimum, then exact resolution of the own candidate chunks ----
-    S.mrow[set][e] = mrow;
-    S.flag[set][e] = slow ? 1 : 0;
-    nt_bar_epilogue();
-    const float mfin = fminf(S.mrow[0][e], S.mrow[1][e]);
-    slow = (S.flag[0][e] | S.flag[1][e]) != 0 || !(mfin < INF);
-    const float lim = mfin + band;
-    // The (query, chunk) pairs of the warp that are still within the band of the FINAL minimum are resolved by the
-    // whole warp, one pair at a time: lane l evaluates key 32 chunk + l (one coalesced 512-byte read of the float4
-    // copies), two REDUX give (min distance, lowest index attaining it), the owner lane keeps the lexicographic minimum.
-    // Pairs of one query come in ascending chunk order, so strict '<' keeps the lowest index.
-    int nv = 0;
-    if (live && !slow)
-      for (int r = 0; r < cnt; ++r)  // compact the own column in place
-        if (lv[r * NT_M] <= lim) lc[nv++ * NT_M] = lc[r * NT_M];
-    __syncwarp();
-    const unsigned short *lcw = &S.lst_c[set][0][quarter * 32];  // entry v of lane src: lcw[v * NT_M + src]
-    float bd = INF;
-    int bi = 0;
-    bool any = false;
-    auto resolve = [&](int src, int chunk) {
-      const float sx = __shfl_sync(0xffffffffu, qc.x, src), sy = __shfl_sync(0xffffffffu, qc.y, src),
-                  sz = __shfl_sync(0xffffffffu, qc.z, src);
-      const int j = chunk * 32 + lane;  // row j exists (npadr is a multiple of 128); padding rows hold +inf
-      const float4 kk = r4[j];
-      const float d = sqdist1(sx, sy, sz, kk.x, kk.y, kk.z);
-      const bool ok = d == d && j < nr;  // NaN keys are skipped (key 0 was checked above)
-      const unsigned int bits = ok ? __float_as_uint(d) : 0xffffffffu;  // d >= 0: unsigned order == float order
-      const unsigned int mnb = __reduce_min_sync(0xffffffffu, bits);
-      const unsigned int mni = __reduce_min_sync(0xffffffffu, bits == mnb ? (unsigned int)j : 0x7fffffffu);
-      if (lane == src && mnb != 0xffffffffu) {
-        const float dd = __uint_as_float(mnb);
-        if (!any || dd < bd) {
-          bd = dd;
-          bi = (int)mni;
-          any = true;
-        }
+
+    // ---- exact resolution.  Every warp takes 32 queries at a time; their (query, chunk) pairs are evaluated by the whole
+    //      warp, one pair per step: lane l computes the distance to key 32 chunk + l (ONE coalesced 512-byte read of the
+    //      float4 copies -- a thread-per-query scan touches 32 cache lines per load instruction and was 10x slower), two
+    //      REDUX give (minimum distance, lowest index attaining it), the owner lane keeps the lexicographic minimum ----
+    const int ew = warp - 2;  // 0 .. 15
+    for (int base = ew * 32; base < nqt * NT_M; base += (NT_EPI / 32) * 32) {
+      const int ql = base + lane;
+      const int q = qt0 * NT_M + ql;
+      const bool live = q < nq;  // base < nqt * NT_M is warp-uniform and a multiple of 32: ql is inside the records
+      float bd = INF;
+      int bi = 0;
+      bool any = false, slow = false;
+      float4 qc = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t cn = 0;  // counts of the four sets, one byte each
+      if (live) {
+        qc = q4[q];
+        cn = *reinterpret_cast<const uint32_t *>(&S.rec_n[ql][0]);
+        slow = ((cn & 0xffu) == 255u) || (((cn >> 8) & 0xffu) == 255u) || (((cn >> 16) & 0xffu) == 255u) || ((cn >> 24) == 255u);
+        if (slow) cn = 0;
       }
-    };
-#pragma unroll 4
-    for (int src = 0; src < 32; ++src) {
-      const int nvs = __shfl_sync(0xffffffffu, nv, src);
-      if (nvs > 0) resolve(src, (int)lcw[src]);
-    }
-    if (__reduce_max_sync(0xffffffffu, nv) > 1) {  // ties / near-ties: the remaining chunks, ascending per query
-      for (int src = 0; src < 32; ++src) {
-        const int nvs = __shfl_sync(0xffffffffu, nv, src);
-        for (int v = 1; v < nvs; ++v) resolve(src, (int)lcw[v * NT_M + src]);
-      }
-    }
-    if (stats) {
-      const unsigned int nres = __reduce_add_sync(0xffffffffu, (unsigned int)nv);
-      if (lane == 0) atomicAdd(&stats[1], nres);
-    }
-    if (warp == 2) NT_STAMP(7);
-    if (set == 1) {
-      S.rd[e] = bd;
-      S.ri[e] = bi;
-      S.flag[1][e] = any ? 2 : 0;
-    }
-    nt_bar_epilogue();
-    if (set == 0) {
-      if (S.flag[1][e] & 2) {  // merge: lexicographic (distance, index) -- the two sets interleave in key index
-        const float od = S.rd[e];
-        const int oi = S.ri[e];
-        if (!any || od < bd || (od == bd && oi < bi)) {
-          bd = od;
-          bi = oi;
-          any = true;
+      unsigned int nres = 0;
+#pragma unroll 1
+      for (int s2 = 0; s2 < NT_SETS; ++s2) {
+#pragma unroll 1
+        for (int v = 0; v < NT_REC; ++v) {
+          unsigned int have = __ballot_sync(0xffffffffu, (int)((cn >> (8 * s2)) & 0xffu) > v);
+          nres += __popc(have);
+          while (have) {
+            const int src = __ffs(have) - 1;
+            have &= have - 1;
+            const float sx = __shfl_sync(0xffffffffu, qc.x, src), sy = __shfl_sync(0xffffffffu, qc.y, src),
+                        sz = __shfl_sync(0xffffffffu, qc.z, src);
+            const int j = (int)S.rec_c[base + src][s2][v] * 32 + lane;  // row j exists; padding rows hold +inf
+            const float4 kk = r4[j];
+            const float d = sqdist1(sx, sy, sz, kk.x, kk.y, kk.z);
+            const bool ok = d == d && j < nr;  // NaN keys are skipped (key 0 was checked in the main loop)
+            const unsigned int bits = ok ? __float_as_uint(d) : 0xffffffffu;  // d >= 0: unsigned order == float order
+            const unsigned int mnb = __reduce_min_sync(0xffffffffu, bits);
+            const unsigned int mni = __reduce_min_sync(0xffffffffu, bits == mnb ? (unsigned int)j : 0x7fffffffu);
+            if (lane == src && mnb != 0xffffffffu) {
+              const float dd = __uint_as_float(mnb);
+              if (!any || dd < bd || (dd == bd && (int)mni < bi)) {  // the sets' chunks interleave: lexicographic
+                bd = dd;
+                bi = (int)mni;
+                any = true;
+              }
+            }
+          }
         }
       }
       slow = slow || !any;
+      if (stats && lane == 0 && nres) atomicAdd(&stats[1], nres);
       unsigned int need = __ballot_sync(0xffffffffu, live && slow);
       if (stats && lane == 0 && need) atomicAdd(&stats[0], (unsigned int)__popc(need));
       while (need) {
@@ -488,8 +505,8 @@ nn_tc_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restri
         dout[q] = bd;
         iout[q] = bi;
       }
-      if (warp == 2) NT_STAMP(8);
     }
+    if (warp == 2) NT_STAMP(8);
   }
 
   fence_before();
@@ -509,7 +526,7 @@ int nn_tc_forward(int b, int n, const float *xyz1, int m, const float *xyz2, flo
                   float *dbg
 #endif
 ) {
-  if (b <= 0 || b > 65535 || n < 256 || m < 256 || n > (1 << 20) || m > (1 << 20)) return PCC_ENOTSUP;  // chunk ids are 16 bit
+  if (b <= 0 || b > 65535 || n < 256 || m < 256 || n > NT_MAX_KEYS || m > NT_MAX_KEYS) return PCC_ENOTSUP;
   const int npad1 = nt_pad(n), npad2 = nt_pad(m);
   const size_t rows1 = (size_t)b * npad1, rows2 = (size_t)b * npad2;
   unsigned char *ws = nullptr;
@@ -525,15 +542,26 @@ int nn_tc_forward(int b, int n, const float *xyz1, int m, const float *xyz2, flo
     cudaFreeAsync(ws, st);
     return (int)e2;
   }
+  // query tiles per CTA: as many CTAs as fit one wave of the SMs (one CTA per SM: the keys take most of its shared memory)
+  static int sms[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int &nsm = sms[dev & 63];
+  if (!nsm && (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)) nsm = 148;
+  const int mx = n > m ? n : m;
+  const int qt_total = (mx + NT_M - 1) / NT_M;
+  int splits = nsm / (2 * b);
+  splits = splits < 1 ? 1 : (splits > qt_total ? qt_total : splits);
+  const int qt_per = (qt_total + splits - 1) / splits;
+  splits = (qt_total + qt_per - 1) / qt_per;
   cudaMemsetAsync(nmax, 0, sizeof(float) * 2 * b, st);
   nn_tc_prep_kernel<<<dim3(b, 2, NT_PREP_PARTS), 256, 0, st>>>(n, xyz1, m, xyz2, npad1, npad2, a1, b1, a2, b2, k1, k2,
                                                                 reinterpret_cast<unsigned int *>(nmax));
-  const int mx = n > m ? n : m;
-  nn_tc_kernel<<<dim3((mx + NT_M - 1) / NT_M, b, 2), NT_THREADS, smem, st>>>(n, xyz1, m, xyz2, npad1, npad2, a1, b1, a2, b2,
-                                                                           k1, k2, nmax, dist1, idx1, dist2, idx2, stats
+  nn_tc_kernel<<<dim3(splits, b, 2), NT_THREADS, smem, st>>>(n, xyz1, m, xyz2, npad1, npad2, qt_per, a1, b1, a2, b2, k1, k2, nmax,
+                                                           dist1, idx1, dist2, idx2, stats
 #ifdef NT_DEBUG_SCORES
-                                                                           ,
-                                                                           dbg
+                                                           ,
+                                                           dbg
 #endif
   );
   cudaFreeAsync(ws, st);

@@ -30,6 +30,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// the same wait on a precomputed shared-memory address: the common case (phase already complete) is one try_wait and one
+// branch; the watchdog only counts on the retry path
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  uint32_t spins = 0;
+  while (!ok) {
+    if (++spins > (1u << 26)) asm volatile("trap;");
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

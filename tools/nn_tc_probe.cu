@@ -127,7 +127,11 @@ int main(int argc, char **argv) {
     CK(cudaMemset(stats, 0, 64));
     CK(cudaMemset(dist[0], 0xff, p1 * 4));
     CK(cudaMemset(dist[1], 0xff, p2 * 4));
+#ifdef NT_DEBUG_SCORES
     int rc = pcc::nn_tc_forward(b, n, d1, m, d2, dist[0], idx[0], dist[1], idx[1], stats, 0, dbg);
+#else
+    int rc = pcc::nn_tc_forward(b, n, d1, m, d2, dist[0], idx[0], dist[1], idx[1], stats, 0);
+#endif
     if (rc != 0) {
       printf("nn_tc_forward rc=%d (%s)\n", rc, cudaGetErrorString((cudaError_t)rc));
       return 3;
@@ -137,7 +141,9 @@ int main(int argc, char **argv) {
     CK(cudaDeviceSynchronize());
     unsigned int hs[16];
     CK(cudaMemcpy(hs, stats, 64, cudaMemcpyDeviceToHost));
-    printf("  cycles in CTA(1,3,0): first load issued %u, all loads issued %u, first mma committed %u, all mma %u, first tile ready %u, main loop done %u, resolved %u, written %u\n", hs[2], hs[3], hs[4], hs[5], hs[9], hs[6], hs[7], hs[8]);
+#ifdef NT_DEBUG_STAMPS
+    printf("  cycles in CTA(1,3,0): key loads issued %u, all loads issued %u, first mma committed %u, all mma %u, first tile ready %u, main loops done %u, written %u\n", hs[2], hs[3], hs[4], hs[5], hs[9], hs[6], hs[8]);
+#endif
     int bad = 0, shown = 0;
     for (int s = 0; s < 2; ++s) {
       std::vector<float> hd(cnt[s]), hb(cnt[s]);
@@ -157,6 +163,7 @@ int main(int argc, char **argv) {
     }
     // score error of cloud 0, direction 0 against the exact distance in double, relative to |a|^2 + |b|^2 (centred)
     double worst = 0.0, worst_abs = 0.0;
+#ifdef NT_DEBUG_SCORES
     {
       std::vector<float> hs2((size_t)n * npad2);
       CK(cudaMemcpy(hs2.data(), dbg, hs2.size() * 4, cudaMemcpyDeviceToHost));
@@ -186,9 +193,20 @@ int main(int argc, char **argv) {
           if (na + nb > 0) worst = std::max(worst, err / (na + nb));
         }
     }
-    for (int w = 0; w < 3; ++w) pcc::nn_tc_forward(b, n, d1, m, d2, dist[0], idx[0], dist[1], idx[1], nullptr, 0, nullptr);
+#endif
+    for (int w = 0; w < 3; ++w) pcc::nn_tc_forward(b, n, d1, m, d2, dist[0], idx[0], dist[1], idx[1], nullptr, 0
+#ifdef NT_DEBUG_SCORES
+                                                    ,
+                                                    nullptr
+#endif
+    );
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < 20; ++r) pcc::nn_tc_forward(b, n, d1, m, d2, dist[0], idx[0], dist[1], idx[1], nullptr, 0, nullptr);
+    for (int r = 0; r < 20; ++r) pcc::nn_tc_forward(b, n, d1, m, d2, dist[0], idx[0], dist[1], idx[1], nullptr, 0
+#ifdef NT_DEBUG_SCORES
+                                                    ,
+                                                    nullptr
+#endif
+    );
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms = 0.f;
