@@ -53,6 +53,14 @@ int64_t pcc_route_count(const char *name);
 int pcc_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *result, int *result_i,
                    float *result2, int *result2_i, pcc_stream_t stream);
 
+/* The same search on the tcgen05 tensor cores (csrc/chamfer_tc.cu): fp16 operand rows built from the clouds, one
+ * tcgen05.mma (K = 16) per 128 x 256 tile of scores, packed 16-bit read-out of the accumulators, and exact resolution of
+ * the candidate keys with the arithmetic above -- results are BIT-IDENTICAL to pcc_nndistance.  PCC_ENOTSUP unless
+ * 256 <= n, m <= 2560.  Not the default: reading the scores out of tensor memory (128 B per clock and SM) bounds it at
+ * about the speed of the SIMT kernel for 3-dimensional points. */
+int pcc_nndistance_tc(int b, int n, const float *xyz, int m, const float *xyz2, float *result, int *result_i,
+                      float *result2, int *result2_i, pcc_stream_t stream);
+
 /* Replaces `void nndistancegrad(...)` (structural_loss.cpp:14, nndistance.cu:149-154).
  * grad_xyz1 (b,n,3) / grad_xyz2 (b,m,3) are fully written (no memset needed).  Deterministic: per target point
  * the own term is added first, then the scatter terms in ascending source index (the reference uses float

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "pcc_route_names": (ctypes.c_char_p, []),
     "pcc_route_count": (ctypes.c_int64, [ctypes.c_char_p]),
     "pcc_nndistance": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcc_nndistance_tc": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_nndistancegrad": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_chamfer_reduce": (_i, [_i, _i, _vp, _i, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_chamfer_reduce_grad": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),

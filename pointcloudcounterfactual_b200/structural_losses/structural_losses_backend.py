@@ -32,6 +32,21 @@ def NNDistance(set_d: torch.Tensor, set_q: torch.Tensor) -> list[torch.Tensor]:
     return [dist1, idx1, dist2, idx2]
 
 
+def NNDistanceTC(set_d: torch.Tensor, set_q: torch.Tensor) -> list[torch.Tensor]:
+    """B200 addition: NNDistance through the tcgen05 tensor cores (``pcc_nndistance_tc``, csrc/chamfer_tc.cu); same outputs,
+    bit-identical values; raises for clouds outside 256..2560 points."""
+    L.require_cuda(set_d, set_q)
+    b, n, m = _dims(set_d, set_q)
+    with torch.cuda.device(set_d.device):
+        dist1 = torch.empty((b, n), dtype=torch.float32, device=set_d.device)
+        idx1 = torch.empty((b, n), dtype=torch.int32, device=set_d.device)
+        dist2 = torch.empty((b, m), dtype=torch.float32, device=set_d.device)
+        idx2 = torch.empty((b, m), dtype=torch.int32, device=set_d.device)
+        L.check(L.load().pcc_nndistance_tc(b, n, L.ptr(set_d), m, L.ptr(set_q), L.ptr(dist1), L.ptr(idx1), L.ptr(dist2),
+                                           L.ptr(idx2), L.stream_of(set_d)), "NNDistanceTC")
+    return [dist1, idx1, dist2, idx2]
+
+
 def NNDistanceGrad(set_d: torch.Tensor, set_q: torch.Tensor, idx1: torch.Tensor, idx2: torch.Tensor,
                    grad_dist1: torch.Tensor, grad_dist2: torch.Tensor) -> list[torch.Tensor]:
     """-> [grad1 (B,N,3), grad2 (B,M,3)]  (structural_loss.cpp:102-125)."""

@@ -136,3 +136,42 @@ def test_fused_chamfer_losses_match_the_unfused_composition(cuda, b, n, m):
         assert rel_err(loss.detach().cpu().numpy(), ref.detach().cpu().numpy()) < TOL
         assert rel_err(x.grad.cpu().numpy(), u.grad.cpu().numpy()) < TOL
         assert rel_err(y.grad.cpu().numpy(), v.grad.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("kind,b,n,m", [("s1", 32, 2048, 2048), ("s2", 4, 1500, 2048), ("s3", 4, 2048, 2048), ("s3", 3, 700, 333),
+                                        ("s1", 2, 2560, 256), ("collapsed", 2, 512, 768), ("nan", 2, 600, 600),
+                                        ("far_origin", 3, 1024, 1024)])
+def test_tensor_core_nndistance_bit_identical_to_simt(cuda, kind, b, n, m):
+    """pcc_nndistance_tc (tcgen05 candidate filter + exact resolution) returns the SAME bits as pcc_nndistance: near / far /
+    massively tied / collapsed clouds, ragged sizes, NaN and inf coordinates (exact-scan path), clouds far from the origin
+    (the operands are translated and scaled per cloud)."""
+    from pointcloudcounterfactual_b200.structural_losses.structural_losses_backend import NNDistance, NNDistanceTC
+
+    if kind == "s1":
+        a, c = synthetic.s1_near(b, max(n, m))
+    elif kind == "s2":
+        a, c = synthetic.s2_far(b, n, m)
+    elif kind == "s3":
+        a, c = synthetic.s3_ties(b, max(n, m))
+    elif kind == "collapsed":
+        a, c = torch.full((b, n, 3), 0.25), torch.full((b, m, 3), 0.25)
+        c[:, 5] += 0.5
+    elif kind == "nan":
+        a, c = synthetic.s2_far(b, n, m)
+        a[0, 3] = float("nan")
+        c[0, 0, 1] = float("nan")      # key 0 NaN: sticks for every query of cloud 0 (nndistance.cu:26)
+        c[1, 7] = float("inf")
+        a[1, 11, 2] = float("-inf")
+    else:
+        a, c = synthetic.s2_far(b, n, m)
+        a, c = a * 3.0 + 1000.0, c * 3.0 + 1000.0
+    a, c = a[:, :n].contiguous(), c[:, :m].contiguous()
+    got = NNDistanceTC(a.to(cuda), c.to(cuda))
+    if kind == "nan":
+        # the reference's rule (oracle, nndistance.cu:26 `if (k==0 || d<best)`): a NaN distance to key 0 sticks, later NaNs
+        # are skipped.  (The SIMT kernel skips a NaN at key 0 as well -- the one corner where it departs from the rule.)
+        want = [torch.from_numpy(np.asarray(t)) for t in oracle.nn_distance(a.numpy(), c.numpy())]
+    else:
+        want = [t.cpu() for t in NNDistance(a.to(cuda), c.to(cuda))]
+    for w, g in zip(want, got):
+        assert torch.equal(torch.nan_to_num(w.float(), nan=-1.0), torch.nan_to_num(g.cpu().float(), nan=-1.0))

@@ -105,7 +105,7 @@ int main(int argc, char **argv) {
   const int npad2 = pcc::nt_pad(m);
   CK(cudaMalloc(&d1, p1 * 12));
   CK(cudaMalloc(&d2, p2 * 12));
-  CK(cudaMalloc(&stats, 64));
+  CK(cudaMalloc(&stats, 512));
   CK(cudaMalloc(&dbg, (size_t)n * npad2 * 4));
   const size_t cnt[2] = {p1, p2};
   for (int s = 0; s < 2; ++s) {
@@ -124,7 +124,11 @@ int main(int argc, char **argv) {
     make_clouds(b, n, m, kind, a, c);
     CK(cudaMemcpy(d1, a.data(), p1 * 12, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d2, c.data(), p2 * 12, cudaMemcpyHostToDevice));
-    CK(cudaMemset(stats, 0, 64));
+    CK(cudaMemset(stats, 0, 512));
+    if (getenv("NT_MODE")) {
+      unsigned int md = (unsigned int)atoi(getenv("NT_MODE"));
+      CK(cudaMemcpy(stats + 127, &md, 4, cudaMemcpyHostToDevice));
+    }
     CK(cudaMemset(dist[0], 0xff, p1 * 4));
     CK(cudaMemset(dist[1], 0xff, p2 * 4));
 #ifdef NT_DEBUG_SCORES
@@ -139,10 +143,11 @@ int main(int argc, char **argv) {
     brute_kernel<<<dim3((n + 127) / 128, b), 128>>>(n, d1, m, d2, bdist[0], bidx[0]);
     brute_kernel<<<dim3((m + 127) / 128, b), 128>>>(m, d2, n, d1, bdist[1], bidx[1]);
     CK(cudaDeviceSynchronize());
-    unsigned int hs[16];
-    CK(cudaMemcpy(hs, stats, 64, cudaMemcpyDeviceToHost));
+    unsigned int hs[128];
+    CK(cudaMemcpy(hs, stats, 512, cudaMemcpyDeviceToHost));
 #ifdef NT_DEBUG_STAMPS
     printf("  cycles in CTA(1,3,0): key loads issued %u, all loads issued %u, first mma committed %u, all mma %u, first tile ready %u, main loops done %u, written %u\n", hs[2], hs[3], hs[4], hs[5], hs[9], hs[6], hs[8]);
+    for (int k = 0; k < 8; ++k) printf("    tile %2d: mma issued %u | epilogue: data landed %u, next tile ready %u, minima done %u\n", 8 + k, hs[32 + k], hs[48 + k], hs[64 + k], hs[80 + k]);
 #endif
     int bad = 0, shown = 0;
     for (int s = 0; s < 2; ++s) {
@@ -162,36 +167,37 @@ int main(int argc, char **argv) {
       }
     }
     // score error of cloud 0, direction 0 against the exact distance in double, relative to |a|^2 + |b|^2 (centred)
+    // score error of cloud 0, direction 0 against the exact distance in double, as a fraction of the bound the kernel
+    // assumes: NT_REL d + NT_CEPS (|a|^2 + |b|^2), norms about the kernel's centre (mean of 32 sample points of cloud 2)
     double worst = 0.0, worst_abs = 0.0;
 #ifdef NT_DEBUG_SCORES
     {
       std::vector<float> hs2((size_t)n * npad2);
       CK(cudaMemcpy(hs2.data(), dbg, hs2.size() * 4, cudaMemcpyDeviceToHost));
-      double lo[3] = {1e30, 1e30, 1e30}, hi3[3] = {-1e30, -1e30, -1e30};
-      for (int i = 0; i < n; ++i)
-        for (int d = 0; d < 3; ++d) {
-          lo[d] = std::min(lo[d], (double)a[i * 3 + d]);
-          hi3[d] = std::max(hi3[d], (double)a[i * 3 + d]);
-        }
-      for (int i = 0; i < m; ++i)
-        for (int d = 0; d < 3; ++d) {
-          lo[d] = std::min(lo[d], (double)c[i * 3 + d]);
-          hi3[d] = std::max(hi3[d], (double)c[i * 3 + d]);
-        }
+      double ctr[3] = {0, 0, 0};
+      for (int t = 0; t < 32; ++t)
+        for (int d = 0; d < 3; ++d) ctr[d] += c[(size_t)((long long)t * m / 32) * 3 + d] / 32.0;
+      int ninf = 0;
       for (int i = 0; i < n; i += 7)
         for (int j = 0; j < m; ++j) {
           double dd = 0, na = 0, nb = 0;
           for (int d = 0; d < 3; ++d) {
-            const double ctr = 0.5 * (lo[d] + hi3[d]);
             const double u = a[i * 3 + d], v = c[j * 3 + d];
             dd += (u - v) * (u - v);
-            na += (u - ctr) * (u - ctr);
-            nb += (v - ctr) * (v - ctr);
+            na += (u - ctr[d]) * (u - ctr[d]);
+            nb += (v - ctr[d]) * (v - ctr[d]);
           }
-          const double err = fabs((double)hs2[(size_t)i * npad2 + j] - dd);
+          const float sc = hs2[(size_t)i * npad2 + j];
+          if (std::isinf(sc)) {
+            ++ninf;
+            continue;
+          }
+          const double err = fabs((double)sc - dd);
           worst_abs = std::max(worst_abs, err);
-          if (na + nb > 0) worst = std::max(worst, err / (na + nb));
+          const double bound = (double)pcc::NT_REL * dd + (double)pcc::NT_CEPS * (na + nb);
+          if (bound > 0) worst = std::max(worst, err / bound);
         }
+      printf("  (%d sampled scores beyond the fp16 range)\n", ninf);
     }
 #endif
     for (int w = 0; w < 3; ++w) pcc::nn_tc_forward(b, n, d1, m, d2, dist[0], idx[0], dist[1], idx[1], nullptr, 0
@@ -211,7 +217,7 @@ int main(int argc, char **argv) {
     CK(cudaEventSynchronize(e1));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
-    printf("%-9s b=%d n=%d m=%d mismatches=%d of %zu  exact rescans=%u  resolved chunks/query=%.2f  score err: max |s-d|/(na+nb)=%.3g "
+    printf("%-9s b=%d n=%d m=%d mismatches=%d of %zu  exact rescans=%u  resolved chunks/query=%.2f  score err / assumed bound: max %.3g "
            "(NT_CEPS %.3g) abs %.3g  forward (prep+search): %.1f us\n",
            names[kind], b, n, m, bad, p1 + p2, hs[0], hs[1] / (double)(p1 + p2), worst, (double)pcc::NT_CEPS, worst_abs,
            ms / 20 * 1e3);
