@@ -30,6 +30,7 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 B_PER_GPU = 32
+GLOBAL_BATCH = 32  # strong scaling: BASELINE's B=32 split over the GPUs
 N_POINTS = 2048
 KNN_N, KNN_K, KNN_C = 1024, 20, 64
 METRIC = "chamfer_emd_fwd_bwd_clouds_per_sec"
@@ -49,6 +50,8 @@ def parse_args():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--no-sub", action="store_true", help="skip sub-metrics (Chamfer-only, EMD-only, kNN)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="weak: 32 clouds per GPU (default); strong: the global batch of 32 clouds split over the GPUs")
     return p.parse_args()
 
 
@@ -144,6 +147,11 @@ def run_b200(args) -> None:
     torch.cuda.set_device(dev)
     lib = _lib.load()
     K, W = args.steps, max(args.warmup, 3)
+    global B_PER_GPU
+    if args.scaling == "strong":
+        if GLOBAL_BATCH % world:
+            raise RuntimeError(f"--scaling strong needs a GPU count that divides {GLOBAL_BATCH}")
+        B_PER_GPU = GLOBAL_BATCH // world
 
     # identical bits on CPU and GPU: generated on the CPU, this rank's slice of the global batch
     recon_h, ref_h = synthetic.s1_near(B_PER_GPU, N_POINTS, first=rank * B_PER_GPU)
@@ -260,7 +268,11 @@ def run_b200(args) -> None:
             return
         e2e_pipe.prefetch()  # H2D of the first step's clouds
         host_values = []
-        for _ in range(nsteps):
+        for s_i in range(nsteps):
+            e2e_pipe.wait_prefetch()  # the copy that reads the pinned buffers has finished: refill them for the next step
+            nxt_r, nxt_t = host_batches[(s_i + 1) & 1]
+            recon_h.copy_(nxt_r)
+            ref_h.copy_(nxt_t)
             prev = e2e_pipe.step()  # launches this step (graph), starts the next step's H2D, returns the previous loss
             e2e_pending.append(sharding.global_mean_loss_async(e2e_pipe.loss_device))
             if prev is not None:
@@ -272,6 +284,9 @@ def run_b200(args) -> None:
             float(e2e_pending.pop(0).wait().cpu())
         assert len(host_values) == nsteps
 
+    # two host batches alternate in the pinned buffers (a data loader's role): every step's inputs are rewritten on the host
+    host_batches = [(recon_h.clone(), ref_h.clone()),
+                    tuple(t.clone() for t in synthetic.s1_near(B_PER_GPU, N_POINTS, first=(world + rank) * B_PER_GPU))]
     run_e2e(W)
     barrier()
     t0 = time.perf_counter()
@@ -313,7 +328,8 @@ def run_b200(args) -> None:
         "frac": pairs / (sweep_ms * 1e-3) / 1e9 / mufu_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one am_sweep_kernel launch, ncu --set full capture
         # (profiles/r01b_ncu_full_summary.md): the clouds and the scaling vectors, everything else stays on chip
-        "traffic": 2108416,
+        "traffic": 2108416, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one am_sweep_kernel launch, "
+                                              "profiles/r02_ncu_full_summary.md (ncu --set full of this command)",
         "hbm_view": {"algorithmic_bytes": 3 * B_PER_GPU * N_POINTS * 4 * 2 + 3 * B_PER_GPU * N_POINTS * 4,
                      "achieved_gbs": 2108416 / (sweep_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                      "frac": 2108416 / (sweep_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
@@ -403,6 +419,53 @@ def run_b200(args) -> None:
                       "note": "tcgen05 kind::tf32 candidate generator (issues the contraction twice) + exact fp32 re-rank "
                               "from the shared-memory key tiles; time includes the transpose/norm prep launch"}
             sub[name] = {"ms": ms, "graphs_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr, "roofline": rl}
+
+        # ---- the same operators reached the way the reference's UNCHANGED scripts reach them: install() registers the KeOps
+        # shim, and the reference's own expressions (src/utils/neighbour_ops.py:35-40,77-82: transpose + LazyTensor on (x, x)
+        # + argKmin; src/train/metrics_and_losses.py:32-41: two argmin of one expression + gathers) run on top of it --------
+        from pointcloudcounterfactual_b200 import install as pcc_install
+
+        pcc_install.install(patch_reference=False)
+        from pykeops.torch import LazyTensor  # the shim
+
+        def ref_pykeops_square_distance(t1, t2):
+            return ((LazyTensor(t1[:, :, None, :]) - LazyTensor(t2[:, None, :, :])) ** 2).sum(-1)
+
+        def ref_pykeops_knn(x, k):
+            x = x.transpose(2, 1).contiguous()
+            return ref_pykeops_square_distance(x, x).argKmin(k, dim=2)
+
+        def ref_pykeops_chamfer(t1, t2):
+            dist = ref_pykeops_square_distance(t1, t2)
+            idx1 = dist.argmin(axis=1).expand(-1, -1, t1.shape[2])
+            squared1 = ((t2 - t1.gather(1, idx1)) ** 2).sum(2).mean(1)
+            idx2 = dist.argmin(axis=2).expand(-1, -1, t1.shape[2])
+            squared2 = ((t1 - t2.gather(1, idx2)) ** 2).sum(2).mean(1)
+            return squared1 + squared2
+
+        def chamfer_fb_shim():
+            torch.autograd.grad(ref_pykeops_chamfer(rr, ref_d).sum(), rr)
+
+        for name, x, k in (("knn_xyz_k20_n1024", x3, KNN_K), ("knn_feat64_k20_n1024", xf, KNN_K)):
+            r0 = _lib.route_counts()
+            ms, gr = graph_or_eager(lambda x=x, k=k: ref_pykeops_knn(x, k))
+            r1 = _lib.route_counts()
+            sub[name + "_via_install"] = {
+                "ms": ms, "graphs_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr, "direct_ms": sub[name]["ms"],
+                "ratio_to_direct": ms / sub[name]["ms"],
+                "kernel_families": sorted(k2 for k2 in r1 if r1[k2] > r0[k2]),
+                "note": "the reference's pykeops_knn body (transpose(2,1).contiguous() + LazyTensor expression + argKmin) on "
+                        "the KeOps shim: includes torch's transposition, reaches the point-major self-kNN route"}
+        r0 = _lib.route_counts()
+        ms, gr = graph_or_eager(chamfer_fb_shim)
+        r1 = _lib.route_counts()
+        sub["chamfer_fwd_bwd_via_install"] = {
+            "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
+            "direct_ms": sub["chamfer_fwd_bwd"]["ms"], "ratio_to_direct": ms / sub["chamfer_fwd_bwd"]["ms"],
+            "kernel_families": sorted(k2 for k2 in r1 if r1[k2] > r0[k2]),
+            "note": "the reference's pykeops_chamfer BODY on the KeOps shim: one fused nn_sym launch serves both argmin calls, "
+                    "the gathers, differences, means and their autograd backward stay torch's (about 20 small kernels); the "
+                    "post-import hook of install() replaces the whole function by the fused operator = the direct number"}
 
         # ---- EdgeConv front-end: get_graph_features forward / backward, HBM-bound -----------------------
         idx25 = neighbour_ops.knn(f64a_, 25)
@@ -556,17 +619,41 @@ def run_b200(args) -> None:
             "note": "synthetic stand-in for configs[4] (the reference's generate.py has no optimisation loop): graph_filtering "
                     "(kNN k=4) + Chamfer, forward and backward w.r.t. the cloud, + Adam on a (32,2048,3) leaf per GPU"}
 
+    # ---- strong scaling (BASELINE.md protocol): the GLOBAL batch of 32 clouds split over the ranks; reported in
+    # every weak-scaling run beside the headline (the driver launches the default mode only) --------------------------
+    strong = None
+    if args.scaling == "weak" and GLOBAL_BATCH % world == 0:
+        bs = GLOBAL_BATCH // world
+        lo = rank * bs
+        g_strong = losses.GraphedLossStep(losses.chamfer_emd, recon_d[:bs].contiguous(), ref_d[:bs].contiguous(), dev) \
+            if world > 1 else graphed_dev
+        if g_strong is not None:
+            def step_strong():
+                g_strong()
+                return (sharding.global_mean_loss_async(g_strong.loss_device),)
+
+            st_times = timed(step_strong, K, W)
+            st_ms = reduce_max(sum(st_times))
+            strong = {"value": GLOBAL_BATCH * K / (st_ms * 1e-3), "unit": "clouds/s", "ms_per_step": st_ms / K,
+                      "global_batch": GLOBAL_BATCH, "batch_per_gpu": bs, "first_cloud": lo,
+                      "note": "same graphed step and timing as the headline, 32 clouds in total: at 8 GPUs a rank holds 4 "
+                              "clouds, i.e. 32 CTAs of EMD sweep per launch on 148 SMs -- launch- and occupancy-bound"}
+
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref_cuda = ref_cuda_timings(dev, ev_time)
+
     clocks = sampler.stop() if rank == 0 else {}  # sampled from the headline region through the sub-metrics
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_reference_value(sample_clouds=4, reps=2)
+        cpu_baseline = cpu_reference_value(sample_clouds=B_PER_GPU, reps=1)
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "points": N_POINTS,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "global_batch": world * B_PER_GPU, "points": N_POINTS,
                        "parallelism": f"batch-sharded x{world}, one all-reduce of the loss per step (asynchronous, consumed one step later)",
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA events); inputs are 1.5 MB",
                        "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
@@ -580,6 +667,13 @@ def run_b200(args) -> None:
                                "the step is losses.GraphedLossStep (copies + kernels captured as one CUDA graph)"
                                if graphed is not None else "eager launches")},
             "gpu_launches": int(launches),
+            # the kNN half of BASELINE's metric, at top level (sub_metrics holds the rooflines)
+            "knn_xyz_k20_n1024_graphs_per_s": sub.get("knn_xyz_k20_n1024", {}).get("graphs_per_s"),
+            "knn_feat64_k20_n1024_graphs_per_s": sub.get("knn_feat64_k20_n1024", {}).get("graphs_per_s"),
+            "chamfer_fwd_bwd_clouds_per_s": sub.get("chamfer_fwd_bwd", {}).get("clouds_per_s"),
+            "emd_fwd_bwd_clouds_per_s": sub.get("emd_fwd_bwd", {}).get("clouds_per_s"),
+            "strong_scaling": strong,
+            "ref_cuda": ref_cuda,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
@@ -593,7 +687,7 @@ def run_b200(args) -> None:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_value(sample_clouds: int, reps: int) -> dict:
+def cpu_reference_value(sample_clouds: int, reps: int, with_knn: bool = True) -> dict:
     """The reference's CPU path on the host cores, bounded sample of the same workload.
 
     Chamfer: the reference's torch CPU path (torch_chamfer, metrics_and_losses.py:44-47) forward+backward, restated
@@ -621,8 +715,8 @@ def cpu_reference_value(sample_clouds: int, reps: int) -> dict:
     dt = (time.perf_counter() - t0) / reps
     # the kNN half of the metric: the reference's torch CPU path (torch_knn, neighbour_ops.py:71-74), full batch
     knn = {}
-    for name, x in (("knn_xyz_k20_n1024_graphs_per_s", synthetic.knn_xyz(B_PER_GPU, KNN_N)),
-                    ("knn_feat64_k20_n1024_graphs_per_s", synthetic.knn_features(B_PER_GPU, KNN_C, KNN_N))):
+    for name, x in (() if not with_knn else (("knn_xyz_k20_n1024_graphs_per_s", synthetic.knn_xyz(B_PER_GPU, KNN_N)),
+                    ("knn_feat64_k20_n1024_graphs_per_s", synthetic.knn_features(B_PER_GPU, KNN_C, KNN_N)))):
         torch_ref.torch_knn(x, KNN_K)
         t1 = time.perf_counter()
         for _ in range(3):
@@ -633,20 +727,88 @@ def cpu_reference_value(sample_clouds: int, reps: int) -> dict:
                       f"(reference path) + C oracle approxmatch/matchcost/matchcostgrad (no CPU EMD exists in the reference)"}
 
 
+def ref_cuda_timings(dev, ev_time) -> dict:
+    """BASELINE configs[2] names the reference's CUDA op as the bar: the reference's own kernels, compiled UNMODIFIED from
+    /root/reference into oracle/_ref (oracle/build_ref.py; test infrastructure), timed with the same CUDA-event harness on
+    the same GPU in the same run, beside this library's operators.  Baseline leg only: never on the product path."""
+    import torch
+
+    from oracle import build_ref
+    from pointcloudcounterfactual_b200 import synthetic
+    from pointcloudcounterfactual_b200.structural_losses.structural_losses_backend import (MatchCostFused, NNDistance,
+                                                                                          NNDistanceGrad)
+
+    if not build_ref.available("structural_losses_backend_ref"):
+        return {"unavailable": "oracle/_ref/structural is not built (needs /root/reference at build time)"}
+    ref = build_ref.load_ref("structural_losses_backend_ref")
+    a, c = (t.to(dev) for t in synthetic.s1_near(B_PER_GPU, N_POINTS))
+    g1 = torch.full((B_PER_GPU, N_POINTS), 1.0 / N_POINTS, device=dev)
+    _, ri1, _, ri2 = ref.NNDistance(a, c)
+
+    def ref_emd():
+        match, _ = ref.ApproxMatch(a, c)
+        ref.MatchCost(a, c, match)
+        ref.MatchCostGrad(a, c, match)
+
+    out = {"unit": "ms", "shape": f"B={B_PER_GPU} x {N_POINTS}", "timing": "CUDA events, eager launches",
+           "nn_distance_fwd": {"reference_cuda": ev_time(lambda: ref.NNDistance(a, c), 10),
+                               "b200": ev_time(lambda: NNDistance(a, c), 10)},
+           "nn_distance_bwd": {"reference_cuda": ev_time(lambda: ref.NNDistanceGrad(a, c, ri1, ri2, g1, g1), 10),
+                               "b200": ev_time(lambda: NNDistanceGrad(a, c, ri1, ri2, g1, g1), 10)},
+           "approxmatch_matchcost_matchcostgrad": {"reference_cuda": ev_time(ref_emd, 3, warm=1),
+                                                   "b200": ev_time(lambda: MatchCostFused(a, c, True, True), 5, warm=1)}}
+    if build_ref.available("emd_backend_ref"):
+        from pointcloudcounterfactual_b200.emd import emdModule
+
+        refe = build_ref.load_ref("emd_backend_ref")
+        ua, uc = (t.to(dev) for t in synthetic.auction_clouds(B_PER_GPU, N_POINTS))
+        bn = (B_PER_GPU, N_POINTS)
+
+        def buf(shape, dtype, fill=0):
+            return torch.full(shape, fill, dtype=dtype, device=dev)
+
+        def ref_auction():  # work buffers initialised per call exactly as emd_module.py:34-45 does
+            refe.forward(ua, uc, buf(bn, torch.float32), buf(bn, torch.int32, -1), buf(bn, torch.float32),
+                         buf(bn, torch.int32, -1), buf(bn, torch.int32), buf(bn, torch.float32), buf(bn, torch.float32),
+                         buf((bn[0] * bn[1],), torch.int32), buf((512,), torch.int32), buf((512,), torch.int32),
+                         buf((512,), torch.int32), buf((bn[0] * bn[1],), torch.int32), 0.005, 50)
+
+        mod = emdModule()
+        out["auction_emd_fwd_eps0.005_iters50"] = {"reference_cuda": ev_time(ref_auction, 3, warm=1),
+                                                   "b200": ev_time(lambda: mod(ua, uc, 0.005, 50), 5, warm=1)}
+    for v in out.values():
+        if isinstance(v, dict) and "reference_cuda" in v:
+            v["speedup"] = v["reference_cuda"] / v["b200"]
+    return out
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     K, W = args.steps, args.warmup
-    sample = 2  # clouds per step: ~0.5 s of host work per step
+    # every step is the FULL workload (32 clouds): approxmatch is OpenMP-parallel over the points of a cloud, matchcost /
+    # matchcostgrad over (cloud, point), the torch Chamfer path over the batch -- all host cores work, same config as the
+    # GPU arm
+    sample = B_PER_GPU
     base = None
     t_all0 = time.perf_counter()
     vals = []
-    for i in range(W + K):
-        r = cpu_reference_value(sample_clouds=sample, reps=1)
+    budget_s = 200.0  # the whole run must end within a few minutes: if one full batch is too slow on this host, fewer clouds
+    i = 0
+    while i < W + K:
+        t_step = time.perf_counter()
+        r = cpu_reference_value(sample_clouds=sample, reps=1, with_knn=(i == W + K - 1))
+        t_step = time.perf_counter() - t_step
+        if i == 0 and sample > 4 and t_step * (W + K) > budget_s:  # re-size once, after the first (untimed) step
+            while sample > 4 and t_step * (W + K) * sample / B_PER_GPU > budget_s:
+                sample //= 2
+            if W == 0:
+                continue  # the first step was sized wrong and would be a timed one: redo it
         if i >= W:
             vals.append(r["value"])
         base = r
+        i += 1
     total = sum(sample / v for v in vals)
     value = sample * K / total
     out = {
@@ -654,7 +816,8 @@ def run_reference(args) -> None:
         "warmup": W, "ms_per_step": total / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "points": N_POINTS,
-                   "sample": f"each step = {sample} clouds of the workload (bounded sample)"},
+                   "sample": f"each step = {sample} clouds" + (" = the full batch" if sample == B_PER_GPU else
+                                                                 f" of the {B_PER_GPU} (host too slow for the full batch in the time budget)")},
         "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": base["cores"], "kind": "port", "sample": base["sample"]},
         "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all0,
