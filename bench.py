@@ -164,10 +164,9 @@ def run_b200(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The reported global mean is one all-reduce of (sum, count) per step.  It is launched asynchronously and consumed one
-    # step later (the last one inside the last step), so a rank never idles on a reporting collective: with a blocking
-    # all-reduce every step ends at the slowest rank and the skew of 8 GPUs adds up (2.00 instead of 1.8 ms per step).
-    e2e_pending = []
+    # The reported global mean is ONE all-reduce of (sum, count) per logging interval -- here: per timed region, issued and
+    # waited for INSIDE it -- not one per step: sharding.LossAccumulator (the reference's drytorch metrics work the same way).
+    loss_acc = sharding.LossAccumulator(dev)
     graphed = graphed_dev = None
     if not args.eager:
         try:  # the public fixed-shape step: [H2D copies +] loss forward/backward + D2H of the loss as ONE graph launch
@@ -186,7 +185,8 @@ def run_b200(args) -> None:
             r = recon_d.detach().requires_grad_(True)
             loss = losses.chamfer_emd(r, ref_d)
             (grad,) = torch.autograd.grad(loss.sum(), r)
-        return loss, grad, sharding.global_mean_loss_async(loss)
+        loss_acc.add(loss)
+        return loss, grad
 
     def step_e2e():
         if graphed is not None:
@@ -198,33 +198,28 @@ def run_b200(args) -> None:
             loss = losses.chamfer_emd(r, t)
             (grad,) = torch.autograd.grad(loss.sum(), r)
             local = loss.cpu()
-        e2e_pending.append(sharding.global_mean_loss_async(loss))
+        loss_acc.add(loss)
         torch.cuda.current_stream(dev).synchronize()  # the step's result is on the host now
         host_value = float(local[0])
-        mean = float(e2e_pending.pop(0).wait().cpu()) if len(e2e_pending) > 1 else None  # previous step's global mean
-        return host_value, mean, grad
+        return host_value, grad
 
     def timed(fn, steps, warm):
-        """per-step CUDA events on the launching stream; L2 flushed between steps outside the events."""
-        pending = None
+        """per-step CUDA events on the launching stream; L2 flushed between steps outside the events; the global mean of
+        the interval's losses is reduced over the ranks inside the last step's events."""
         for _ in range(warm):
-            out = fn()
-            if pending is not None:
-                pending.wait()
-            pending = out[-1]
+            fn()
+        loss_acc.reduce()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         for i, (e0, e1) in enumerate(evs):
             flush.zero_()
             e0.record()
-            out = fn()
-            if pending is not None:
-                pending.wait()  # global mean of the previous step: complete by now
-            pending = out[-1]
+            fn()
             if i == steps - 1:
-                pending.wait()  # ... and the last step's own inside its interval
+                timed.last_mean = loss_acc.reduce()  # the one collective of the interval
             e1.record()
         barrier()
+        timed.last_mean = float(timed.last_mean)
         return [e0.elapsed_time(e1) for e0, e1 in evs]
 
     def reduce_max(x: float) -> float:
@@ -263,9 +258,7 @@ def run_b200(args) -> None:
         if e2e_pipe is None:
             for _ in range(nsteps):
                 step_e2e()
-            while e2e_pending:
-                float(e2e_pending.pop(0).wait().cpu())  # the last global mean arrives inside the timed region
-            return
+            return float(loss_acc.reduce().cpu())  # the interval's global mean arrives on the host inside the timed region
         e2e_pipe.prefetch()  # H2D of the first step's clouds
         host_values = []
         for s_i in range(nsteps):
@@ -274,15 +267,12 @@ def run_b200(args) -> None:
             recon_h.copy_(nxt_r)
             ref_h.copy_(nxt_t)
             prev = e2e_pipe.step()  # launches this step (graph), starts the next step's H2D, returns the previous loss
-            e2e_pending.append(sharding.global_mean_loss_async(e2e_pipe.loss_device))
+            loss_acc.add(e2e_pipe.loss_device)
             if prev is not None:
                 host_values.append(float(prev[0]))  # the previous step's per-cloud loss, read on the host
-            if len(e2e_pending) > 1:
-                float(e2e_pending.pop(0).wait().cpu())
         host_values.append(float(e2e_pipe.drain()[0]))
-        while e2e_pending:
-            float(e2e_pending.pop(0).wait().cpu())
         assert len(host_values) == nsteps
+        return float(loss_acc.reduce().cpu())  # the interval's global mean, on the host inside the timed region
 
     # two host batches alternate in the pinned buffers (a data loader's role): every step's inputs are rewritten on the host
     host_batches = [(recon_h.clone(), ref_h.clone()),
@@ -587,20 +577,42 @@ def run_b200(args) -> None:
                     "(its cudnn convolution runs TF32 by default; the fused path's point GEMMs are fp32 unless "
                     "torch.backends.cuda.matmul.allow_tf32 is set -- ms_with_tf32_point_gemms)"}
 
-        def ae_step():
-            encoder_fb(True)  # encoder: per layer kNN graph (k=25) + fused EdgeConv layer, forward and backward
-            gfilt()  # decoder graph_filtering (kNN k=4 + smoothing forward / backward)
-            loss = losses.chamfer_emd(rr, ref_d)
-            torch.autograd.grad(loss.sum(), rr)
-            if world > 1:
-                dist.all_reduce(grad_buf)
+        # gradient exchange of the training step: 45 MB of fp32 in three buckets, each all-reduced on a communication stream
+        # as soon as "its" part of the backward is done (what DistributedDataParallel does with its buckets), so that only
+        # the last bucket is exposed; the whole step -- kernels of this library, torch glue and the NCCL calls -- is captured
+        # as ONE CUDA graph per rank when the capture is accepted
+        buckets = list(grad_buf.chunk(3))
+        comm = torch.cuda.Stream(dev)
 
-        ms = ev_time(ae_step, 10) if world > 1 else graph_or_eager(ae_step, reps=10)[0]
+        def reduce_bucket(i):
+            if world > 1:
+                comm.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(comm):
+                    dist.all_reduce(buckets[i])
+
+        def ae_step():
+            loss = losses.chamfer_emd(rr, ref_d)  # ChamferEMD forward + backward: the decoder's gradients come first
+            torch.autograd.grad(loss.sum(), rr)
+            reduce_bucket(0)
+            gfilt()  # decoder graph_filtering (kNN k=4 + smoothing forward / backward)
+            reduce_bucket(1)
+            encoder_fb(True)  # encoder: per layer kNN graph (k=25) + fused EdgeConv layer, forward and backward
+            reduce_bucket(2)
+            if world > 1:
+                torch.cuda.current_stream(dev).wait_stream(comm)
+
+        if world > 1:  # NCCL communicator warm-up outside any capture
+            for i in range(3):
+                reduce_bucket(i)
+            torch.cuda.current_stream(dev).wait_stream(comm)
+            torch.cuda.synchronize()
+        ms, ae_graphed = graph_or_eager(ae_step, reps=10)
         sub["ae_step_hotpath"] = {
-            "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": world == 1,
+            "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": ae_graphed,
             "note": "stand-in for configs[3]: DGCNN edge-convolution stack (4 layers, dynamic kNN k=25, fused EdgeConv) "
                     "forward and backward + decoder graph_filtering (kNN k=4) fwd+bwd + ChamferEMD fwd+bwd"
-                    + (" + NCCL all-reduce of 45 MB fp32 gradients" if world > 1 else "") + "; 32 clouds per GPU.  "
+                    + (" + NCCL all-reduce of 45 MB fp32 gradients in 3 buckets on a communication stream, overlapped with "
+                       "the rest of the backward" if world > 1 else "") + "; 32 clouds per GPU.  "
                     "Not included (plain torch layers of the reference): final_conv, the PCGen decoder MLPs, optimizer"}
 
         leaf = recon_d.detach().clone().requires_grad_(True)
@@ -630,7 +642,7 @@ def run_b200(args) -> None:
         if g_strong is not None:
             def step_strong():
                 g_strong()
-                return (sharding.global_mean_loss_async(g_strong.loss_device),)
+                loss_acc.add(g_strong.loss_device)
 
             st_times = timed(step_strong, K, W)
             st_ms = reduce_max(sum(st_times))
@@ -654,7 +666,8 @@ def run_b200(args) -> None:
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "global_batch": world * B_PER_GPU, "points": N_POINTS,
-                       "parallelism": f"batch-sharded x{world}, one all-reduce of the loss per step (asynchronous, consumed one step later)",
+                       "parallelism": f"batch-sharded x{world}, no data-path collective; ONE all-reduce of the (sum, count) of the losses per "
+                                      "timed region, inside it (sharding.LossAccumulator)",
                        "l2": "flushed between steps (256 MiB memset outside the per-step CUDA events); inputs are 1.5 MB",
                        "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
                        "launch": "losses.GraphedLossStep (one CUDA-graph launch per step)" if graphed_dev is not None

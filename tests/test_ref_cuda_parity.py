@@ -46,7 +46,8 @@ def test_nn_distance_vs_reference_cuda(cuda, ref_sl, maker, b, n):
     assert rel_err(g1.cpu().numpy(), rg1.cpu().numpy()) < TOL and rel_err(g2.cpu().numpy(), rg2.cpu().numpy()) < TOL
 
 
-@pytest.mark.parametrize("maker,b,n,m", [("s1", 4, 2048, 2048), ("s2", 3, 512, 512), ("s2", 2, 1024, 512)])
+@pytest.mark.parametrize("maker,b,n,m", [("s1", 4, 2048, 2048), ("s2", 3, 512, 512), ("s2", 2, 1024, 512),
+                                         ("s1", 32, 2048, 2048)])  # the last one is BASELINE configs[2] at full size
 def test_approxmatch_vs_reference_cuda(cuda, ref_sl, maker, b, n, m):
     a, c = synthetic.s1_near(b, n) if maker == "s1" else synthetic.s2_far(b, n, m)
     ta, tc = a.to(cuda), c.to(cuda)
@@ -56,7 +57,7 @@ def test_approxmatch_vs_reference_cuda(cuda, ref_sl, maker, b, n, m):
     match, _ = ApproxMatch(ta, tc)
     # the solver reproduces the reference's arithmetic and summation order: match agrees to rounding level
     assert (match - rmatch).abs().max().item() < 1e-6 * max(1.0, rmatch.max().item())
-    assert (match == rmatch).float().mean().item() > 0.95  # the rest differ in the last bit or are denormal/zero
+    assert (match == rmatch).sum().item() > 0.95 * match.numel()  # the rest differ in the last bit or are denormal/zero
     assert rel_err(MatchCost(ta, tc, match).cpu().numpy(), rcost.cpu().numpy()) < TOL
     g1, g2 = MatchCostGrad(ta, tc, match)
     assert rel_err(g1.cpu().numpy(), rg1.cpu().numpy()) < TOL and rel_err(g2.cpu().numpy(), rg2.cpu().numpy()) < TOL
