@@ -28,8 +28,8 @@ enum Route {
   R_ARGMIN_SMALL,   // one-thread-per-query argmin (vector quantisation)
   R_NN_SYM,         // symmetric brute-force Chamfer forward (nn_sym_kernel)
   R_NN_ASYM,        // one-direction Chamfer forward (nn_fwd_kernel)
-  R_NN_GRID,        // grid-pruned exact Chamfer forward
-  R_KNN3_GRID,      // grid-pruned exact xyz kNN
+  R_NN_TC,          // tcgen05 candidate filter + exact resolution (chamfer_tc.cu)
+  R_KNN3_TC,        // xyz kNN with the tcgen05 candidate filter (knn3_tc.cu)
   R_PM_SELF,        // pcc_argkmin recognised q == r (point-major self kNN)
   R_COUNT
 };
@@ -158,6 +158,8 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 
 // knn_tc.cu: tcgen05 candidate generator + exact re-rank; PCC_ENOTSUP when the shape is outside that path
 int knn_tc_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st);
+// knn3_tc.cu: xyz kNN through the fp16 tensor-core candidate filter; PCC_ENOTSUP outside 256 <= n <= 2048, k <= 32
+int knn3_tc_launch(int b, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -693,7 +693,17 @@ static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const
   // LazyTensor expression on (x, x)), so both layouts reach the same fast kernels.
   const bool self = q == r && nq == nr;
   if (PM && self) note_route(R_PM_SELF);
-  if (self && c == 3 && k <= 32) return launch_knn3(b, nq, k, PM, q, idx, dist, st);
+  if (self && c == 3 && k <= 32) {
+    const bool no_tc = getenv("PCC_KNN3_SIMT") != nullptr;  // test hook (read per call): the SIMT xyz kernels only
+    if (!no_tc && !force_simt) {
+      const int rc = knn3_tc_launch(b, nq, k, PM, q, idx, dist, st);  // tcgen05 candidate filter (256 <= n <= 2048)
+      if (rc != PCC_ENOTSUP) {
+        note_route(R_KNN3_TC);
+        return rc;
+      }
+    }
+    return launch_knn3(b, nq, k, PM, q, idx, dist, st);
+  }
   if (self && !force_simt && c % 32 == 0) {
     static const bool tc_v1 = getenv("PCC_KNN_TC1") != nullptr;  // test hook: first-generation tcgen05 kernel only
     int rc = tc_v1 ? PCC_ENOTSUP : knn_tc2_launch(b, c, nq, k, PM, q, idx, dist, st);

@@ -1,6 +1,6 @@
 """GPU: the reference's UNCHANGED call sites (tests/ref_callsites.py restates them) reach the fast kernels after
 install() -- indices bit-exact, and the library's dispatch counters (pcc_route_count) prove WHICH kernel family ran:
-  * through the KeOps shim alone (the reference's own function bodies run): point-major self kNN -> knn3w / knn_tc2,
+  * through the KeOps shim alone (the reference's own function bodies run): point-major self kNN -> knn3w (N = 1024) / knn3_tc (N = 2048) / knn_tc2,
     the two argmin reductions of pykeops_chamfer -> ONE nn_sym launch;
   * through the post-import hook: the fused operators (one-launch graph gather, graph_filtering, fused Chamfer loss).
 Sizes are BASELINE.json's: B=32, N=1024 / 2048, C=3 / 64."""
@@ -42,7 +42,7 @@ def test_unchanged_knn_call_sites_reach_fast_kernels(cuda, ref_pkg, patched):
     x3 = synthetic.knn_xyz(32, 1024).to(cuda)                     # (B,3,N) channels-first, as the encoders hold it
     xf = synthetic.knn_features(32, 64, 1024).to(cuda)
     x25 = synthetic.knn_xyz(32, 2048).to(cuda)
-    for x, k, fam in ((x3, 20, "knn3w"), (xf, 20, "knn_tc2"), (x25, 25, "knn3w"), (x25, 4, "knn3w")):
+    for x, k, fam in ((x3, 20, "knn3w"), (xf, 20, "knn_tc2"), (x25, 25, "knn3_tc"), (x25, 4, "knn3_tc")):
         c0 = _lib.route_counts()
         idx = nops.knn(x, k)                                       # the reference's dispatcher -> pykeops_knn
         d = _delta(c0)
@@ -64,7 +64,7 @@ def test_unchanged_chamfer_call_site_is_one_fused_launch(cuda, ref_pkg, patched)
     c0 = _lib.route_counts()
     loss = mal.pykeops_chamfer(r, t)                               # two argmin reductions of ONE symbolic expression
     d = _delta(c0)
-    assert d.get("nn_sym", 0) + d.get("nn_grid", 0) == 1 and "knn_simt" not in d, d
+    assert d.get("nn_sym", 0) + d.get("nn_tc", 0) == 1 and "knn_simt" not in d, d
     loss.sum().backward()
     d1, i1, d2, i2 = oracle.nn_distance(recon[:4].numpy(), ref[:4].numpy())
     assert rel_err(loss[:4].detach().cpu().numpy(), d1.mean(1) + d2.mean(1)) < 1e-5

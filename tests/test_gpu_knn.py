@@ -254,3 +254,29 @@ def test_fused_graph_filtering_forward_backward(cuda, b, n, k):
     (f2 * w8).sum().backward()
     assert rel_err(o2.detach().cpu().numpy(), f2.detach().cpu().numpy()) < 1e-5
     assert rel_err(a2.grad.cpu().numpy(), r2.grad.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("n,k,b", [(1024, 20, 4), (2048, 25, 33), (2048, 4, 2), (300, 8, 3), (1500, 20, 2), (2000, 32, 1), (257, 1, 2),
+                                   (512, 16, 2)])
+def test_xyz_knn_tensor_core_filter_bit_exact(cuda, monkeypatch, n, k, b):
+    """knn3_tc_kernel (fp16 tcgen05 scores as the candidate filter, exact re-evaluation of the candidates): indices AND
+    distances equal the oracle's bit for bit on every shape it accepts -- forced here also where the dispatcher prefers the
+    SIMT kernel -- including duplicated points (massive exact ties -> the exact-scan path), both layouts."""
+    monkeypatch.setenv("PCC_KNN3_TC", "1")
+    x = synthetic.knn_xyz(b, n)
+    x[0, :, 1::7] = x[0, :, 0::7][..., :x[0, :, 1::7].shape[-1]]   # exact duplicates in cloud 0
+    if b > 1:
+        x[1] = x[1, :, :1]                                          # cloud 1 collapsed to one point
+    c0 = _lib_routes()
+    idx, dist = neighbour_ops.knn_indices(x.to(cuda), k, return_dist=True)
+    assert _lib_routes()["knn3_tc"] == c0["knn3_tc"] + 1
+    eidx, edist = oracle.knn(x.numpy(), k, return_dist=True)
+    assert np.array_equal(idx.cpu().numpy(), eidx) and np.array_equal(dist.cpu().numpy(), edist)
+    xt = x.transpose(1, 2).contiguous().to(cuda)                    # point-major through the KeOps pattern
+    assert torch.equal(keops.argkmin(xt, xt, k), idx)
+
+
+def _lib_routes():
+    from pointcloudcounterfactual_b200 import _lib
+
+    return _lib.route_counts()
