@@ -157,6 +157,18 @@ int pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const 
                           const float *exty, const float *sy, const unsigned char *slot, const float *grad_out,
                           float *grad_uv, float *grad_gamma, float *grad_beta, pcc_stream_t stream);
 
+/* Batched fp32 GEMM on the tcgen05 tensor cores with fp32-level accuracy (3xTF32: hi.hi + hi.lo + lo.hi, error 2^-21
+ * relative) -- the point contraction of the fused EdgeConv layer (the Conv2d 1x1 of src/module/layers.py:159-203 applied
+ * to the points) and its two backward products, which were cuBLAS calls.
+ *   D[z*ksplit + p](i,j) = sum_{l in part p of [0,k)} A[z](i,l) * B[z](j,l),   i < m, j < n, z < batch, p < ksplit
+ * (ksplit = 1: the plain product; ksplit > 1 splits a long reduction over more CTAs, the caller adds the ksplit slices)
+ * element (i,l) of A[z] at A[z*sAb + i*sAm + l*sAk], (j,l) of B[z] at B[z*sBb + j*sBn + l*sBk], (i,j) of D[z] at
+ * D[z*sDb + i*sDm + j*sDn] (z over batch*ksplit slices; strides in elements; any of the two dimensions of an operand may be the contiguous one, a
+ * batch stride of 0 shares the operand).  D is fully written. */
+int pcc_gemm_tf32x3(int batch, int ksplit, int m, int n, int k, const float *A, long long sAb, long long sAm, long long sAk,
+                    const float *B, long long sBb, long long sBn, long long sBk, float *D, long long sDb, long long sDm,
+                    long long sDn, pcc_stream_t stream);
+
 /* Decoder-output smoothing `graph_filtering` (src/utils/neighbour_ops.py:122-133), one launch per
  * direction.  x (b,3,n), idx (b,n,k) int64 = the kNN list of x itself (column 0 is the point), 2 <= k <= 8, n <= 6144.
  * out (b,3,n); mean_dist (b) receives the per-cloud mean nearest-neighbour distance (sigma before the 0.005 clamp),

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "pcc_edgeconv_forward": (_i, [_i, _i, _i, _i] + [_vp] * 6 + [_i, ctypes.c_float, ctypes.c_float, _i, ctypes.c_float]
                              + [_vp] * 7),
     "pcc_edgeconv_backward": (_i, [_i, _i, _i, _i] + [_vp] * 6 + [_i, _i, ctypes.c_float] + [_vp] * 8),
+    "pcc_gemm_tf32x3": (_i, [_i, _i, _i, _i, _i, _vp] + [ctypes.c_longlong] * 3 + [_vp] + [ctypes.c_longlong] * 3 + [_vp]
+                        + [ctypes.c_longlong] * 3 + [_vp]),
     "pcc_graph_filtering": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pcc_graph_filtering_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_emd_forward": (_i, [_i, _i, _i] + [_vp] * 14 + [ctypes.c_float, _i, _vp]),

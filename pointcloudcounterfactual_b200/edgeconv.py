@@ -7,8 +7,8 @@ Reference sequence (``src/module/encoders.py:49-54``, ``classifier.py:55-60``)::
     x = conv(x)                                                # layers.py:159-203: act(bn(dense(x)))
     x = x.max(dim=3, keepdim=False)[0]                         # (B,Cout,N)
 
-Here the convolution weight W = [W1 | W2] is applied to the POINTS once -- ``u = W1 x``, ``v = (W2 - W1) x``, one plain
-library GEMM, 1/k of the reference's convolution work -- and ``pcc_edgeconv_forward`` does everything that touches
+Here the convolution weight W = [W1 | W2] is applied to the POINTS once -- ``u = W1 x``, ``v = (W2 - W1) x``, one
+hand-written tcgen05 GEMM (3xTF32, fp32-accurate), 1/k of the reference's convolution work -- and ``pcc_edgeconv_forward`` does everything that touches
 edges: y(i,t) = u[idx[i,t]] + v[i], the batch statistics of BatchNorm2d over all B*N*k edges, the per-channel affine
 map, the activation and the max over k.  ``pcc_edgeconv_backward`` propagates through all of it (every edge gets a
 gradient through the batch statistics), deterministically.  Results agree with the torch composition to fp32
@@ -33,10 +33,23 @@ BN_EVAL, BN_TRAIN, AFFINE = 0, 1, 2
 ACT_NONE, ACT_LEAKY = 0, 1
 
 
+def gemm_nt(a: torch.Tensor, a_strides: tuple[int, int, int], b: torch.Tensor, b_strides: tuple[int, int, int],
+            out: torch.Tensor, out_strides: tuple[int, int, int], batch: int, m: int, n: int, k: int,
+            ksplit: int = 1) -> torch.Tensor:
+    """out[z](i,j) = sum_l a[z](i,l) b[z](j,l) on the tcgen05 tensor cores with fp32-level accuracy (``pcc_gemm_tf32x3``,
+    csrc/gemm_tc.cu); every operand is addressed through (batch, row, k) element strides, so neither x nor the gradient is
+    ever transposed in memory.  ``ksplit`` > 1 writes batch * ksplit partial products (slice z * ksplit + p) for the caller
+    to add: a long reduction spread over more CTAs."""
+    L.check(L.load().pcc_gemm_tf32x3(batch, ksplit, m, n, k, L.ptr(a), *a_strides, L.ptr(b), *b_strides, L.ptr(out), *out_strides,
+                                     L.stream_of(out)), "gemm_tf32x3")
+    return out
+
+
 class _EdgeConvMax(Function):
     """x (B,C,N) channels-first, weight (Cout,2C), idx (B,N,k) int64 -> out (B,Cout,N).
 
-    The two GEMMs around the edge kernels are plain library calls (torch.bmm -> cuBLAS fp32), written out here instead of
+    The three GEMMs around the edge kernels run on the tcgen05 tensor cores with fp32-level accuracy (``gemm_nt`` ->
+    ``pcc_gemm_tf32x3``: 3xTF32, operands split and laid out by the kernel's loader warps), written out here instead of
     left to autograd so that the weight gradient is a BATCHED product over clouds (K = N per problem) rather than one
     GEMM with K = B*N and two output tiles, and so that no transposed copy of x or of the gradient is made."""
 
@@ -52,8 +65,11 @@ class _EdgeConvMax(Function):
         w1 = weight[:, :c]
         ws = torch.cat([w1, weight[:, c:] - w1], dim=0)            # (2Cout, C): [W1 ; W2 - W1]
         with torch.cuda.device(dev):
-            # uv[b,i,:] = [W1 x_i | (W2-W1) x_i], point-major rows: x^T (B,N,C) is a strided view, no copy
-            uv = torch.bmm(x.transpose(1, 2), ws.t().unsqueeze(0).expand(b, -1, -1))
+            # uv[b,i,:] = [W1 x_i | (W2-W1) x_i], point-major rows, straight from the channels-first x (any strides)
+            uv = torch.empty((b, n, 2 * cout), dtype=torch.float32, device=dev)
+            ws = ws.contiguous()
+            gemm_nt(x, (x.stride(0), x.stride(2), x.stride(1)), ws, (0, c, 1), uv, (n * 2 * cout, 2 * cout, 1),
+                    b, n, 2 * cout, c)
             out = torch.empty((b, cout, n), dtype=torch.float32, device=dev)
             exty = torch.empty((b, n, cout), dtype=torch.float32, device=dev)
             sy = torch.empty((b, n, cout), dtype=torch.float32, device=dev) if bn_mode == BN_TRAIN else None
@@ -87,10 +103,15 @@ class _EdgeConvMax(Function):
                 bn_mode, act, slope, L.ptr(exty), L.ptr(sy), L.ptr(slot), L.ptr(g), L.ptr(guv), L.ptr(ggamma),
                 L.ptr(gbeta), L.stream_of(uv)), "edgeconv_backward")
             gx = gw = None
-            if ctx.needs_input_grad[0]:   # (B,C,N) = ws^T (C,2Cout) . guv^T (2Cout,N)
-                gx = torch.bmm(ws.t().unsqueeze(0).expand(b, -1, -1), guv.transpose(1, 2))
+            if ctx.needs_input_grad[0]:   # gx^T (N,C) = guv (N,2Cout) . ws (2Cout,C), stored channels-first
+                gx = torch.empty((b, c, n), dtype=torch.float32, device=dev)
+                gemm_nt(guv, (n * c2, c2, 1), ws, (0, 1, c), gx, (c * n, 1, n), b, n, c, c2)
             if ctx.needs_input_grad[1]:   # per cloud (2Cout,N) . (N,C), then summed over the clouds
-                gws = torch.bmm(guv.transpose(1, 2), x.transpose(1, 2)).sum(0)
+                ksplit = max(1, min(8, n // 512))  # K = N points per cloud: a few hundred CTAs instead of b * ceil(2Cout/128)
+                gwb = torch.empty((b * ksplit, c2, c), dtype=torch.float32, device=dev)
+                gemm_nt(guv, (n * c2, 1, c2), x, (x.stride(0), x.stride(1), x.stride(2)), gwb, (c2 * c, c, 1), b, c2, c, n,
+                        ksplit)
+                gws = gwb.sum(0)
                 gw = torch.cat([gws[:cout] - gws[cout:], gws[cout:]], dim=1)
         return (gx, gw, None, ggamma if ctx.needs_input_grad[3] else None, gbeta if ctx.needs_input_grad[4] else None,
                 None, None, None, None, None, None, None)

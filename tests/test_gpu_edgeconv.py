@@ -235,3 +235,32 @@ def test_fused_layer_under_autocast_stays_fp32(cuda):
     with torch.autocast("cuda", dtype=torch.bfloat16):
         out = edgeconv.edge_conv_max(x0, idx, w, bn_mode=edgeconv.AFFINE)
     assert out.dtype == torch.float32 and torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("b,m,n,k", [(3, 300, 130, 3), (2, 2048, 128, 64), (2, 128, 64, 2048), (1, 257, 512, 128), (4, 64, 3, 70),
+                                     (2, 1000, 256, 33)])
+def test_tcgen05_gemm_fp32_accuracy(cuda, b, m, n, k):
+    """pcc_gemm_tf32x3 (3xTF32 on tcgen05, operands split hi/lo by the loader warps): every stride pattern the EdgeConv
+    products use -- A contiguous along rows or along K, B shared over the batch or not, D row-major or transposed --
+    against a float64 product; 3e-6 of the largest entry (fp32 SIMT GEMMs land at ~1e-6)."""
+    g = torch.Generator().manual_seed(b * 1000 + m + n + k)
+    a_km = torch.randn(b, k, m, generator=g).to(cuda)          # A(i,l) contiguous along i  (x channels-first)
+    a_mk = a_km.transpose(1, 2).contiguous()                   # A(i,l) contiguous along l
+    bm = torch.randn(b, n, k, generator=g).to(cuda)
+    want = torch.einsum("bil,bjl->bij", a_mk.double(), bm.double())
+    scale = want.abs().max().item()
+    for a, sa in ((a_km, (k * m, 1, m)), (a_mk, (m * k, k, 1))):
+        out = torch.full((b, m, n), float("nan"), device=cuda)
+        edgeconv.gemm_nt(a, sa, bm, (n * k, k, 1), out, (m * n, n, 1), b, m, n, k)
+        assert (out.double() - want).abs().max().item() < 3e-6 * scale
+        out_t = torch.full((b, n, m), float("nan"), device=cuda)   # transposed store (the input-gradient product)
+        edgeconv.gemm_nt(a, sa, bm, (n * k, k, 1), out_t, (n * m, 1, m), b, m, n, k)
+        assert torch.equal(out_t.transpose(1, 2), out)
+    shared = torch.full((b, m, n), float("nan"), device=cuda)      # one B for the whole batch (the weights)
+    edgeconv.gemm_nt(a_mk, (m * k, k, 1), bm[0], (0, k, 1), shared, (m * n, n, 1), b, m, n, k)
+    want0 = torch.einsum("bil,jl->bij", a_mk.double(), bm[0].double())
+    assert (shared.double() - want0).abs().max().item() < 3e-6 * want0.abs().max().item()
+    for ks in (2, 5):                                              # split reduction: the slices add up to the product
+        parts = torch.full((b * ks, m, n), float("nan"), device=cuda)
+        edgeconv.gemm_nt(a_mk, (m * k, k, 1), bm, (n * k, k, 1), parts, (m * n, n, 1), b, m, n, k, ks)
+        assert (parts.view(b, ks, m, n).sum(1).double() - want).abs().max().item() < 3e-6 * scale
