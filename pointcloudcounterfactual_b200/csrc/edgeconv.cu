@@ -486,7 +486,7 @@ ec_fill_kernel(int n, int k, int stride, const int64_t *__restrict__ idx, const 
 // spread over many threads instead of serialising one.
 __global__ void __launch_bounds__(256)
 ec_sort_kernel(int n, int k, int stride, const int *__restrict__ off, const int *__restrict__ base2,
-               const unsigned int *__restrict__ rev_tmp, unsigned int *__restrict__ rev) {
+               const unsigned int *__restrict__ rev_tmp, unsigned int *__restrict__ rev, bool interleave) {
   const int cloud = blockIdx.y, total = n * k;
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= total) return;
@@ -507,7 +507,7 @@ ec_sort_kernel(int n, int k, int stride, const int *__restrict__ off, const int 
     rank += ((v.x < mine) ? 1 : 0) + ((v.y < mine) ? 1 : 0) + ((v.z < mine) ? 1 : 0) + ((v.w < mine) ? 1 : 0);
   }
   for (; s2 < end; ++s2) rank += (src[s2] < mine) ? 1 : 0;
-  rev[(size_t)cloud * stride + beg + rank] = mine;
+  rev[(size_t)cloud * stride + (interleave ? edge_pos(beg + rank) : beg + rank)] = mine;
 }
 
 // Segmented sum over the target-sorted edge list in CHUNKS of EC_CHUNK consecutive edges -- uniform work per group
@@ -745,6 +745,35 @@ ec_bwd_finish_kernel(int n, int k, int cout, int nchunks, const float *__restric
   }
 }
 
+// Target-sorted edge lists for callers outside this file (graph.cu's deterministic gather backward): the workspace
+// holds off | hist2 | base2 | rev_tmp | rev; *off and *rev point into it, *stride is the per-cloud stride of rev.
+static inline size_t es_up(size_t v) { return (v + 255) & ~(size_t)255; }
+static inline int es_stride(int n, int k) { return (n * k + 511) / 512 * 512; }  // whole interleave blocks
+size_t edge_sort_ws_bytes(int b, int n, int k) {
+  return es_up(sizeof(int) * (size_t)b * (n + 1)) + 2 * es_up(sizeof(int) * (size_t)b * EC_PARTS * n) +
+         2 * es_up(sizeof(int) * (size_t)b * es_stride(n, k));
+}
+bool edge_sort_ok(int b, int n, int k) { return b > 0 && b <= 65535 && n > 0 && n <= EC_MAX_N && k > 0 && k <= EC_MAX_K; }
+void edge_sort_launch(int b, int n, int k, const int64_t *idx, char *ws, bool interleave, const int **off_out,
+                      const unsigned int **rev_out, int *stride, cudaStream_t st) {
+  const int per_cloud = n * k, estride = es_stride(n, k);
+  const size_t cnt_bytes = es_up(sizeof(int) * (size_t)b * EC_PARTS * n), rev_bytes = es_up(sizeof(int) * (size_t)b * estride);
+  int *off = reinterpret_cast<int *>(ws);
+  char *w = ws + es_up(sizeof(int) * (size_t)b * (n + 1));
+  int *hist2 = reinterpret_cast<int *>(w);
+  int *base2 = reinterpret_cast<int *>(w + cnt_bytes);
+  unsigned int *rev_tmp = reinterpret_cast<unsigned int *>(w + 2 * cnt_bytes);
+  unsigned int *rev = reinterpret_cast<unsigned int *>(w + 2 * cnt_bytes + rev_bytes);
+  const dim3 egrid((per_cloud + 255) / 256, b), pgrid(EC_PARTS, b);
+  ec_hist_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, idx, hist2);
+  ec_scan_kernel<<<b, 1024, 0, st>>>(n, per_cloud, hist2, off, base2);
+  ec_fill_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, estride, idx, base2, rev_tmp);
+  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, estride, off, base2, rev_tmp, rev, interleave);
+  *off_out = off;
+  *rev_out = rev;
+  *stride = estride;
+}
+
 static bool ec_shape_ok(int b, int n, int k, int cout) {
   return b > 0 && b <= 65535 && n > 0 && n <= EC_MAX_N && k > 0 && k <= EC_MAX_K && cout >= 4 && cout <= 1024 &&
          cout % 4 == 0;
@@ -846,7 +875,7 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   ec_hist_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, idx, hist2);
   ec_scan_kernel<<<b, 1024, 0, st>>>(n, per_cloud, hist2, off, base2);
   ec_fill_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, estride, idx, base2, rev_tmp);
-  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, estride, off, base2, rev_tmp, rev);
+  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, estride, off, base2, rev_tmp, rev, false);
   const int groups = EC_THREADS / (cout >> 2);
   const dim3 cgrid((nchunks + groups - 1) / groups, b), grid((n + EC_PTS - 1) / EC_PTS, b);
   const bool staged = n <= EC_STAGE_MAX_N;

@@ -8,12 +8,18 @@
 //   mode 1  out (B,2C,N,k):  out[c][i][t] = x[c][idx[i][t]] - x[c][i],   out[C+c][i][t] = x[c][i]
 // Both kernels are HBM-bound by construction: the forward writes the result exactly once (rows of x are staged in
 // shared memory, 8 KB per channel at N = 2048, and gathered from there), the backward reads the upstream gradient
-// exactly once and scatter-adds into a shared-memory row (float atomics: summation order is not fixed, like
-// torch.gather's own backward).  Measured at C=64, N=2048, k=25, B=32: forward 195 us (66 % of the HBM copy peak),
-// backward 511 us -- bound by the 105 M shared-memory atomics (1.4 cycles per lane).  A variant that sorts the edges by
-// target once per cloud and sums runs with warp shuffles before one atomic per run was measured at 795 us (the ten
-// shuffles per 32 edges cost more than the atomics they save) and dropped.
+// exactly once.  Two backward kernels:
+//   * sorted (default while one (point, neighbour) plane of the gradient, n*k floats, fits shared memory): the edges of
+//     every cloud are sorted by target once per call (edgeconv.cu's edge_sort_launch), the plane of one (cloud, channel)
+//     is brought into shared memory with one bulk copy, and every thread sums GS_E consecutive entries of the sorted list
+//     in list order.  No atomics anywhere; the order of every addition is a function of idx alone, so the result is
+//     bitwise reproducible (torch.gather's own backward is not).
+//   * atomic (planes that do not fit, or n*k not a multiple of 4): scatter-add into a shared-memory row with float
+//     atomics -- 511 us at C=64, N=2048, k=25, B=32, bound by the 105 M shared-memory atomics (1.4 cycles per lane).
+// Measured at that shape: forward 195 us (66 % of the HBM copy peak).  A variant of the sorted scheme that segmented-summed
+// runs with warp shuffles per 32 edges (ten shuffles each) before one atomic per run was measured at 795 us and dropped.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace pcc {
 
@@ -125,6 +131,157 @@ graph_gather_grad_kernel(int c, int n, int k, const int64_t *__restrict__ idx, c
   for (int i = threadIdx.x; i < n; i += GG_THREADS) gr[i] = acc[i];
 }
 
+// ---- deterministic backward over the target-sorted edge list ------------------------------------------------------
+// One CTA per (cloud, channel).  Shared memory: one (point, neighbour) plane of the gradient (n*k floats, bulk copies),
+// acc[n], and one partial per chunk of GS_E sorted entries.  The kernel is issue-bound next to the two plane loads, so
+// every phase is written for few instructions per edge:
+//   1. (mode 1) the bottom plane g[C+c] is loaded; thread = point sums its k slots: own[j] (registers)
+//   2. the top plane g[c] replaces it; own[j] -= sum_t top[j][t]
+//   3. thread = chunk of GS_E consecutive sorted entries, predicated straight-line code: every run piece is summed in
+//      list order; a piece whose run STARTS in the chunk is stored to acc[target] (exactly one writer per target), the
+//      piece that continues the previous chunk's run goes to pb[chunk]
+//   4. thread = target: acc[j] + the continuation pieces of its run in chunk order + own[j] -> grad_x
+constexpr int GS_THREADS = 1024;
+constexpr int GS_E = 16;
+constexpr int GS_MAXN = 4096;
+constexpr int GS_OWN = GS_MAXN / GS_THREADS;  // targets per thread
+
+__host__ __device__ inline size_t gs_smem_bytes(int n, int k) {
+  const size_t total = (size_t)n * k;
+  return 16 + sizeof(float) * (total + n + (total + GS_E - 1) / GS_E);
+}
+
+__device__ __forceinline__ void gs_load_plane(float *row, const float *src, uint32_t bytes, uint64_t *bar) {
+  mbar_expect_tx(bar, bytes);
+  for (uint32_t o = 0; o < bytes; o += 32768u)
+    bulk_load_1d(reinterpret_cast<unsigned char *>(row) + o, reinterpret_cast<const unsigned char *>(src) + o,
+                 min(32768u, bytes - o), bar);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(GS_THREADS, 1)
+graph_gather_grad_sorted_kernel(int c, int n, int k, int estride, const int *__restrict__ off,
+                                const unsigned int *__restrict__ rev, const float *__restrict__ gout,
+                                float *__restrict__ gx) {
+  extern __shared__ __align__(128) unsigned char gs_raw[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(gs_raw);
+  float *row = reinterpret_cast<float *>(gs_raw + 16);
+  const int total = n * k, nchunk = (total + GS_E - 1) / GS_E;
+  float *acc = row + total, *pb = acc + n;
+  const size_t cloud = blockIdx.y;
+  const int ch = blockIdx.x, co = MODE ? 2 * c : c;
+  const float *g_top = gout + (cloud * (size_t)co + ch) * total;
+  const float *g_bot = gout + (cloud * (size_t)co + c + ch) * total;
+  const int *offb = off + cloud * (size_t)(n + 1);
+  const unsigned int *revb = rev + cloud * (size_t)estride;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    gs_load_plane(row, MODE ? g_bot : g_top, (uint32_t)total * 4u, bar);
+  }
+  // the first chunk's entries do not depend on the plane: fetch them under the plane load
+  uint4 nx[GS_E / 4];
+  unsigned int nprev = 0xffffffffu;
+  auto fetch = [&](int ck) {
+    if (ck < nchunk) {
+      // interleaved list (edge_pos): the q-th 16 bytes of the warp's 32 chunks are contiguous
+      const unsigned int *src = revb + (size_t)(ck >> 5) * 512 + (ck & 31) * 4;
+#pragma unroll
+      for (int q = 0; q < GS_E / 4; ++q) nx[q] = *reinterpret_cast<const uint4 *>(src + 128 * q);
+      nprev = ck ? (revb[edge_pos(ck * GS_E - 1)] >> 19) : 0xffffffffu;
+    }
+  };
+  fetch(threadIdx.x);
+  __syncthreads();
+  float own[GS_OWN];
+#pragma unroll
+  for (int u = 0; u < GS_OWN; ++u) own[u] = 0.f;
+  auto plane_row_sum = [&](int j) {
+    const float *r = row + j * k;
+    float a = 0.f;
+    int t = 0;
+    for (; t + 5 <= k; t += 5) a = ((((a + r[t]) + r[t + 1]) + r[t + 2]) + r[t + 3]) + r[t + 4];
+    for (; t < k; ++t) a += r[t];
+    return a;
+  };
+  if (MODE) {
+    mbar_wait(bar, 0);
+#pragma unroll
+    for (int u = 0; u < GS_OWN; ++u) {
+      const int j = threadIdx.x + u * GS_THREADS;
+      if (j < n) own[u] = plane_row_sum(j);
+    }
+    __syncthreads();  // every read of the bottom plane is done: the async proxy may overwrite it
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      gs_load_plane(row, g_top, (uint32_t)total * 4u, bar);
+    }
+    mbar_wait(bar, 1);
+#pragma unroll
+    for (int u = 0; u < GS_OWN; ++u) {
+      const int j = threadIdx.x + u * GS_THREADS;
+      if (j < n) own[u] -= plane_row_sum(j);
+    }
+  } else {
+    mbar_wait(bar, 0);
+  }
+  for (int ck = threadIdx.x; ck < nchunk; ck += GS_THREADS) {
+    unsigned int ent[GS_E];
+#pragma unroll
+    for (int q = 0; q < GS_E / 4; ++q)
+      ent[4 * q] = nx[q].x, ent[4 * q + 1] = nx[q].y, ent[4 * q + 2] = nx[q].z, ent[4 * q + 3] = nx[q].w;
+    const unsigned int prev = nprev;
+    fetch(ck + GS_THREADS);  // the next round's entries fly while this chunk is summed
+    const int cnt = total - ck * GS_E;
+    float *dst = (ent[0] >> 19) != prev ? acc + (ent[0] >> 19) : pb + ck;
+    float sum = 0.f;
+    if (cnt >= GS_E) {
+#pragma unroll
+      for (int q = 0; q < GS_E; ++q) {
+        const unsigned int e = ent[q];
+        sum += row[((e >> 6) & 8191u) * (unsigned int)k + (e & 63u)];
+        if (q + 1 == GS_E) {
+          *dst = sum;
+        } else if ((ent[q + 1] >> 19) != (e >> 19)) {
+          *dst = sum;
+          sum = 0.f;
+          dst = acc + (ent[q + 1] >> 19);
+        }
+      }
+    } else {  // the cloud's last chunk
+#pragma unroll
+      for (int q = 0; q < GS_E - 1; ++q) {
+        if (q < cnt) {
+          const unsigned int e = ent[q];
+          sum += row[((e >> 6) & 8191u) * (unsigned int)k + (e & 63u)];
+          if (q + 1 == cnt) {
+            *dst = sum;
+          } else if ((ent[q + 1] >> 19) != (e >> 19)) {
+            *dst = sum;
+            sum = 0.f;
+            dst = acc + (ent[q + 1] >> 19);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float *gr = gx + (cloud * (size_t)c + ch) * n;
+#pragma unroll
+  for (int u = 0; u < GS_OWN; ++u) {
+    const int j = threadIdx.x + u * GS_THREADS;
+    if (j < n) {
+      const int beg = offb[j], end = offb[j + 1];
+      float a = 0.f;
+      if (end > beg) {
+        a = acc[j];
+        for (int ck = beg / GS_E + 1; ck <= (end - 1) / GS_E; ++ck) a += pb[ck];
+      }
+      gr[j] = a + own[u];
+    }
+  }
+}
+
 template <int MODE>
 static int launch_gather(int b, int c, int n, int k, const float *x, const int64_t *idx, float *out, cudaStream_t st) {
   const size_t smem = sizeof(float) * GG_CH * n;
@@ -137,6 +294,22 @@ static int launch_gather(int b, int c, int n, int k, const float *x, const int64
 template <int MODE>
 static int launch_gather_grad(int b, int c, int n, int k, const int64_t *idx, const float *gout, float *gx,
                               cudaStream_t st) {
+  const size_t sorted_smem = gs_smem_bytes(n, k);
+  static const bool force_atomic = getenv("PCC_GATHER_GRAD_ATOMIC") != nullptr;  // measurement switch
+  if (!force_atomic && k <= 32 && (n * k) % 4 == 0 && sorted_smem <= 227 * 1024 && n <= GS_MAXN && edge_sort_ok(b, n, k) &&
+      (reinterpret_cast<uintptr_t>(gout) & 15) == 0) {
+    static size_t attr[64];
+    if (cudaError_t e = smem_optin(graph_gather_grad_sorted_kernel<MODE>, sorted_smem, attr); e != cudaSuccess) return (int)e;
+    char *ws = nullptr;
+    if (cudaError_t e = ws_alloc((void **)&ws, edge_sort_ws_bytes(b, n, k), st); e != cudaSuccess) return (int)e;
+    const int *off;
+    const unsigned int *rev;
+    int estride;
+    edge_sort_launch(b, n, k, idx, ws, true, &off, &rev, &estride, st);
+    graph_gather_grad_sorted_kernel<MODE><<<dim3(c, b), GS_THREADS, sorted_smem, st>>>(c, n, k, estride, off, rev, gout, gx);
+    cudaFreeAsync(ws, st);
+    return finish_launch(5);
+  }
   const size_t smem = sizeof(float) * n;
   graph_gather_grad_kernel<MODE><<<dim3(c, b), GG_THREADS, smem, st>>>(c, n, k, idx, gout, gx);
   return finish_launch(1);

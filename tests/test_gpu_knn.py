@@ -206,6 +206,37 @@ def test_fused_graph_gather_forward_backward(cuda, b, c, n, k):
         assert rel_err(a.grad.cpu().numpy(), r.grad.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("b,c,n,k,kind", [(2, 8, 2048, 25, "hub"), (2, 8, 1024, 20, "random"), (1, 4, 301, 5, "random"),
+                                          (1, 4, 512, 16, "one_target")])
+def test_graph_gather_backward_is_reproducible(cuda, b, c, n, k, kind):
+    """The gather backward sums over the target-sorted edge list in a fixed order (no atomics): two runs agree bit for
+    bit, also when a few targets collect most edges (feature-space hubs) or one target collects all of them; shapes
+    whose (point, neighbour) plane is not a multiple of 4 floats take the atomic kernel and still match float64."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(b, c, n, generator=g).to(cuda)
+    if kind == "hub":
+        idx = torch.randint(0, n, (b, n, k), generator=g)
+        idx[:, :, : k // 2] = torch.randint(0, 4, (b, n, k // 2), generator=g)  # four hubs with in-degree ~ n*k/8
+    elif kind == "one_target":
+        idx = torch.full((b, n, k), 7, dtype=torch.int64)
+    else:
+        idx = torch.randint(0, n, (b, n, k), generator=g)
+    idx = idx.to(cuda)
+    w = torch.randn(b, 2 * c, n, k, generator=g).to(cuda)
+    grads = []
+    for _ in range(2):
+        a = x.clone().requires_grad_(True)
+        (neighbour_ops.get_graph_features(a, idx, k)[1] * w).sum().backward()
+        grads.append(a.grad.clone())
+    if (n * k) % 4 == 0:
+        assert torch.equal(grads[0], grads[1])
+    w64 = w.double()
+    ref = torch.zeros(b, c, n, dtype=torch.float64, device=cuda)
+    ref.scatter_add_(2, idx.view(b, 1, n * k).expand(-1, c, -1), w64[:, :c].reshape(b, c, n * k))
+    ref += (w64[:, c:] - w64[:, :c]).sum(3)
+    assert rel_err(grads[0].cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
 def test_vq_nearest_codeword_pattern_large_batch(cuda):
     """quantize.py:20-32 at training size: B * n_codes = 131072 one-query problems against a repeated 16 x 4 book
     (more problems than the 65535-cloud grid limit of the general kernels) run on the one-thread-per-query kernel."""
