@@ -161,13 +161,16 @@ int knn_tc_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t *
 // knn3_tc.cu: xyz kNN through the fp16 tensor-core candidate filter; PCC_ENOTSUP outside 256 <= n <= 2048, k <= 32
 int knn3_tc_launch(int b, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st);
 
-// edgeconv.cu: per-cloud edge lists sorted by TARGET (packed target << 19 | source << 6 | slot, ascending inside a run;
-// off[cloud][n + 1] = run starts).  Four launches on st; the workspace is the caller's.
-size_t edge_sort_ws_bytes(int b, int n, int k);
-bool edge_sort_ok(int b, int n, int k);
-// interleave: inside every block of 512 entries the q-th 16-byte group of all 32 sixteen-entry chunks is contiguous
-// (edge_pos), so a warp whose lanes own consecutive chunks fetches them with coalesced 16-byte loads.
-void edge_sort_launch(int b, int n, int k, const int64_t *idx, char *ws, bool interleave, const int **off,
+// edgeconv.cu: edge lists sorted by TARGET (packed target << 19 | source << 6 | slot, ascending inside a run;
+// off[n + 1] = run starts), one list per (cloud, piece of the source range) -- see edge_sort_launch.  Four launches on
+// st; the workspace is the caller's.
+// interleave: the consumer is graph.cu's gather backward -- inside every block of 512 entries the q-th 16-byte group of
+// all 32 sixteen-entry chunks is contiguous (edge_pos), so a warp whose lanes own consecutive chunks fetches them with
+// coalesced 16-byte loads, and an entry is (edge id within the piece * 4) << 12 | target: the byte offset of the edge's
+// gradient inside the piece's plane needs one shift (n <= 4096, n / pieces * k <= 2^18).
+size_t edge_sort_ws_bytes(int b, int n, int k, int pieces);
+bool edge_sort_ok(int b, int n, int k, int pieces);
+void edge_sort_launch(int b, int n, int k, int pieces, const int64_t *idx, char *ws, bool interleave, const int **off,
                       const unsigned int **rev, int *stride, cudaStream_t st);
 __host__ __device__ inline int edge_pos(int p) {
   const int r = p & 511, l = r >> 4, q = r & 15;

@@ -404,9 +404,9 @@ constexpr int EC_PARTS = 8;  // the edges of a cloud are histogrammed / filled i
 
 // hist2[cloud][part][j] = edges of the part's range that point at j: shared-memory atomics only
 __global__ void __launch_bounds__(512)
-ec_hist_kernel(int n, int k, const int64_t *__restrict__ idx, int *__restrict__ hist2) {
+ec_hist_kernel(int n, int total, const int64_t *__restrict__ idx, int *__restrict__ hist2) {
   extern __shared__ int sc[];  // [n]
-  const int cloud = blockIdx.y, part = blockIdx.x, total = n * k;
+  const int cloud = blockIdx.y, part = blockIdx.x;
   const int per = (total + EC_PARTS - 1) / EC_PARTS;
   const int e0 = min(part * per, total), e1 = min(e0 + per, total);
   for (int j = threadIdx.x; j < n; j += 512) sc[j] = 0;
@@ -463,10 +463,10 @@ ec_scan_kernel(int n, int total, const int *__restrict__ hist2, int *__restrict_
 
 // every part places its edges with shared-memory cursors that start at base2: no global atomics
 __global__ void __launch_bounds__(512)
-ec_fill_kernel(int n, int k, int stride, const int64_t *__restrict__ idx, const int *__restrict__ base2,
+ec_fill_kernel(int n, int k, int total, int stride, const int64_t *__restrict__ idx, const int *__restrict__ base2,
                unsigned int *__restrict__ rev_tmp) {
   extern __shared__ int sc[];  // [n] cursors
-  const int cloud = blockIdx.y, part = blockIdx.x, total = n * k;
+  const int cloud = blockIdx.y, part = blockIdx.x;
   const int per = (total + EC_PARTS - 1) / EC_PARTS;
   const int e0 = min(part * per, total), e1 = min(e0 + per, total);
   const int *bs = base2 + ((size_t)cloud * EC_PARTS + part) * n;
@@ -485,9 +485,9 @@ ec_fill_kernel(int n, int k, int stride, const int64_t *__restrict__ idx, const 
 // one or two segments together (broadcast loads); hub targets (in-degree of several hundred in feature space) are
 // spread over many threads instead of serialising one.
 __global__ void __launch_bounds__(256)
-ec_sort_kernel(int n, int k, int stride, const int *__restrict__ off, const int *__restrict__ base2,
+ec_sort_kernel(int n, int k, int total, int stride, const int *__restrict__ off, const int *__restrict__ base2,
                const unsigned int *__restrict__ rev_tmp, unsigned int *__restrict__ rev, bool interleave) {
-  const int cloud = blockIdx.y, total = n * k;
+  const int cloud = blockIdx.y;
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= total) return;
   const unsigned int *src = rev_tmp + (size_t)cloud * stride;
@@ -507,7 +507,10 @@ ec_sort_kernel(int n, int k, int stride, const int *__restrict__ off, const int 
     rank += ((v.x < mine) ? 1 : 0) + ((v.y < mine) ? 1 : 0) + ((v.z < mine) ? 1 : 0) + ((v.w < mine) ? 1 : 0);
   }
   for (; s2 < end; ++s2) rank += (src[s2] < mine) ? 1 : 0;
-  rev[(size_t)cloud * stride + (interleave ? edge_pos(beg + rank) : beg + rank)] = mine;
+  if (interleave)  // the gather backward's format: byte offset of g[source][slot] inside the plane << 12 | target
+    rev[(size_t)cloud * stride + edge_pos(beg + rank)] = ((unsigned int)e << 14) | (unsigned int)j;
+  else
+    rev[(size_t)cloud * stride + beg + rank] = mine;
 }
 
 // Segmented sum over the target-sorted edge list in CHUNKS of EC_CHUNK consecutive edges -- uniform work per group
@@ -745,30 +748,36 @@ ec_bwd_finish_kernel(int n, int k, int cout, int nchunks, const float *__restric
   }
 }
 
-// Target-sorted edge lists for callers outside this file (graph.cu's deterministic gather backward): the workspace
-// holds off | hist2 | base2 | rev_tmp | rev; *off and *rev point into it, *stride is the per-cloud stride of rev.
+// Target-sorted edge lists for callers outside this file (graph.cu's deterministic gather backward).  With pieces > 1
+// the SOURCES of every cloud are cut into `pieces` equal ranges and every (cloud, piece) is sorted on its own (sources
+// are packed relative to the piece): sub-cloud s = cloud * pieces + piece has its run starts at off + s * (n + 1) and
+// its list at rev + s * stride.  The workspace holds off | hist2 | base2 | rev_tmp | rev.
 static inline size_t es_up(size_t v) { return (v + 255) & ~(size_t)255; }
-static inline int es_stride(int n, int k) { return (n * k + 511) / 512 * 512; }  // whole interleave blocks
-size_t edge_sort_ws_bytes(int b, int n, int k) {
-  return es_up(sizeof(int) * (size_t)b * (n + 1)) + 2 * es_up(sizeof(int) * (size_t)b * EC_PARTS * n) +
-         2 * es_up(sizeof(int) * (size_t)b * es_stride(n, k));
+static inline int es_stride(int total) { return (total + 511) / 512 * 512; }  // whole interleave blocks
+size_t edge_sort_ws_bytes(int b, int n, int k, int pieces) {
+  const size_t subs = (size_t)b * pieces;
+  return es_up(sizeof(int) * subs * (n + 1)) + 2 * es_up(sizeof(int) * subs * EC_PARTS * n) +
+         2 * es_up(sizeof(int) * subs * es_stride(n / pieces * k));
 }
-bool edge_sort_ok(int b, int n, int k) { return b > 0 && b <= 65535 && n > 0 && n <= EC_MAX_N && k > 0 && k <= EC_MAX_K; }
-void edge_sort_launch(int b, int n, int k, const int64_t *idx, char *ws, bool interleave, const int **off_out,
+bool edge_sort_ok(int b, int n, int k, int pieces) {
+  return b > 0 && n > 0 && n <= EC_MAX_N && k > 0 && k <= EC_MAX_K && pieces > 0 && n % pieces == 0 &&
+         (long long)b * pieces <= 65535;
+}
+void edge_sort_launch(int b, int n, int k, int pieces, const int64_t *idx, char *ws, bool interleave, const int **off_out,
                       const unsigned int **rev_out, int *stride, cudaStream_t st) {
-  const int per_cloud = n * k, estride = es_stride(n, k);
-  const size_t cnt_bytes = es_up(sizeof(int) * (size_t)b * EC_PARTS * n), rev_bytes = es_up(sizeof(int) * (size_t)b * estride);
+  const int subs = b * pieces, total = n / pieces * k, estride = es_stride(total);
+  const size_t cnt_bytes = es_up(sizeof(int) * (size_t)subs * EC_PARTS * n), rev_bytes = es_up(sizeof(int) * (size_t)subs * estride);
   int *off = reinterpret_cast<int *>(ws);
-  char *w = ws + es_up(sizeof(int) * (size_t)b * (n + 1));
+  char *w = ws + es_up(sizeof(int) * (size_t)subs * (n + 1));
   int *hist2 = reinterpret_cast<int *>(w);
   int *base2 = reinterpret_cast<int *>(w + cnt_bytes);
   unsigned int *rev_tmp = reinterpret_cast<unsigned int *>(w + 2 * cnt_bytes);
   unsigned int *rev = reinterpret_cast<unsigned int *>(w + 2 * cnt_bytes + rev_bytes);
-  const dim3 egrid((per_cloud + 255) / 256, b), pgrid(EC_PARTS, b);
-  ec_hist_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, idx, hist2);
-  ec_scan_kernel<<<b, 1024, 0, st>>>(n, per_cloud, hist2, off, base2);
-  ec_fill_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, estride, idx, base2, rev_tmp);
-  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, estride, off, base2, rev_tmp, rev, interleave);
+  const dim3 egrid((total + 255) / 256, subs), pgrid(EC_PARTS, subs);
+  ec_hist_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, total, idx, hist2);
+  ec_scan_kernel<<<subs, 1024, 0, st>>>(n, total, hist2, off, base2);
+  ec_fill_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, total, estride, idx, base2, rev_tmp);
+  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, total, estride, off, base2, rev_tmp, rev, interleave);
   *off_out = off;
   *rev_out = rev;
   *stride = estride;
@@ -872,10 +881,10 @@ pcc_edgeconv_backward(int b, int n, int k, int cout, const float *uv, const int6
   ec_bwd_stats_kernel<<<cout, 128, 0, st>>>(cout, nparts, (double)b * n * k, bn_mode, partials, gamma, invstd,
                                             grad_gamma, grad_beta, coef);
   const dim3 egrid((per_cloud + 255) / 256, b), pgrid(EC_PARTS, b);
-  ec_hist_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, idx, hist2);
+  ec_hist_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, per_cloud, idx, hist2);
   ec_scan_kernel<<<b, 1024, 0, st>>>(n, per_cloud, hist2, off, base2);
-  ec_fill_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, estride, idx, base2, rev_tmp);
-  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, estride, off, base2, rev_tmp, rev, false);
+  ec_fill_kernel<<<pgrid, 512, n * sizeof(int), st>>>(n, k, per_cloud, estride, idx, base2, rev_tmp);
+  ec_sort_kernel<<<egrid, 256, 0, st>>>(n, k, per_cloud, estride, off, base2, rev_tmp, rev, false);
   const int groups = EC_THREADS / (cout >> 2);
   const dim3 cgrid((nchunks + groups - 1) / groups, b), grid((n + EC_PTS - 1) / EC_PTS, b);
   const bool staged = n <= EC_STAGE_MAX_N;

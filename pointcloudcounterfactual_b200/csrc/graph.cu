@@ -144,7 +144,7 @@ graph_gather_grad_kernel(int c, int n, int k, const int64_t *__restrict__ idx, c
 constexpr int GS_THREADS = 1024;
 constexpr int GS_E = 16;
 constexpr int GS_MAXN = 4096;
-constexpr int GS_OWN = GS_MAXN / GS_THREADS;  // targets per thread
+constexpr int GS_OWN = GS_MAXN / GS_THREADS;  // targets per thread (the 512-thread variant is used up to half GS_MAXN)
 
 __host__ __device__ inline size_t gs_smem_bytes(int n, int k) {
   const size_t total = (size_t)n * k;
@@ -158,8 +158,8 @@ __device__ __forceinline__ void gs_load_plane(float *row, const float *src, uint
                  min(32768u, bytes - o), bar);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(GS_THREADS, 1)
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 graph_gather_grad_sorted_kernel(int c, int n, int k, int estride, const int *__restrict__ off,
                                 const unsigned int *__restrict__ rev, const float *__restrict__ gout,
                                 float *__restrict__ gx) {
@@ -188,7 +188,7 @@ graph_gather_grad_sorted_kernel(int c, int n, int k, int estride, const int *__r
       const unsigned int *src = revb + (size_t)(ck >> 5) * 512 + (ck & 31) * 4;
 #pragma unroll
       for (int q = 0; q < GS_E / 4; ++q) nx[q] = *reinterpret_cast<const uint4 *>(src + 128 * q);
-      nprev = ck ? (revb[edge_pos(ck * GS_E - 1)] >> 19) : 0xffffffffu;
+      nprev = ck ? revb[edge_pos(ck * GS_E - 1)] : 0xffffffffu;  // masked where it is used: no wait on the load here
     }
   };
   fetch(threadIdx.x);
@@ -208,7 +208,7 @@ graph_gather_grad_sorted_kernel(int c, int n, int k, int estride, const int *__r
     mbar_wait(bar, 0);
 #pragma unroll
     for (int u = 0; u < GS_OWN; ++u) {
-      const int j = threadIdx.x + u * GS_THREADS;
+      const int j = threadIdx.x + u * THREADS;
       if (j < n) own[u] = plane_row_sum(j);
     }
     __syncthreads();  // every read of the bottom plane is done: the async proxy may overwrite it
@@ -219,33 +219,41 @@ graph_gather_grad_sorted_kernel(int c, int n, int k, int estride, const int *__r
     mbar_wait(bar, 1);
 #pragma unroll
     for (int u = 0; u < GS_OWN; ++u) {
-      const int j = threadIdx.x + u * GS_THREADS;
+      const int j = threadIdx.x + u * THREADS;
       if (j < n) own[u] -= plane_row_sum(j);
     }
   } else {
     mbar_wait(bar, 0);
   }
-  for (int ck = threadIdx.x; ck < nchunk; ck += GS_THREADS) {
+  int ob[GS_OWN], oe[GS_OWN];  // run starts of this thread's targets: in flight during the chunk pass
+#pragma unroll
+  for (int u = 0; u < GS_OWN; ++u) {
+    const int j = threadIdx.x + u * THREADS;
+    ob[u] = j < n ? offb[j] : 0;
+    oe[u] = j < n ? offb[j + 1] : 0;
+  }
+  const unsigned char *rowb = reinterpret_cast<const unsigned char *>(row);
+  for (int ck = threadIdx.x; ck < nchunk; ck += THREADS) {
     unsigned int ent[GS_E];
 #pragma unroll
     for (int q = 0; q < GS_E / 4; ++q)
       ent[4 * q] = nx[q].x, ent[4 * q + 1] = nx[q].y, ent[4 * q + 2] = nx[q].z, ent[4 * q + 3] = nx[q].w;
     const unsigned int prev = nprev;
-    fetch(ck + GS_THREADS);  // the next round's entries fly while this chunk is summed
+    fetch(ck + THREADS);  // the next round's entries fly while this chunk is summed
     const int cnt = total - ck * GS_E;
-    float *dst = (ent[0] >> 19) != prev ? acc + (ent[0] >> 19) : pb + ck;
+    float *dst = (ck == 0 || ((ent[0] ^ prev) & 0xfffu) != 0) ? acc + (ent[0] & 0xfffu) : pb + ck;
     float sum = 0.f;
     if (cnt >= GS_E) {
 #pragma unroll
       for (int q = 0; q < GS_E; ++q) {
         const unsigned int e = ent[q];
-        sum += row[((e >> 6) & 8191u) * (unsigned int)k + (e & 63u)];
+        sum += *reinterpret_cast<const float *>(rowb + (e >> 12));
         if (q + 1 == GS_E) {
           *dst = sum;
-        } else if ((ent[q + 1] >> 19) != (e >> 19)) {
+        } else if (((ent[q + 1] ^ e) & 0xfffu) != 0) {
           *dst = sum;
           sum = 0.f;
-          dst = acc + (ent[q + 1] >> 19);
+          dst = acc + (ent[q + 1] & 0xfffu);
         }
       }
     } else {  // the cloud's last chunk
@@ -253,13 +261,13 @@ graph_gather_grad_sorted_kernel(int c, int n, int k, int estride, const int *__r
       for (int q = 0; q < GS_E - 1; ++q) {
         if (q < cnt) {
           const unsigned int e = ent[q];
-          sum += row[((e >> 6) & 8191u) * (unsigned int)k + (e & 63u)];
+          sum += *reinterpret_cast<const float *>(rowb + (e >> 12));
           if (q + 1 == cnt) {
             *dst = sum;
-          } else if ((ent[q + 1] >> 19) != (e >> 19)) {
+          } else if (((ent[q + 1] ^ e) & 0xfffu) != 0) {
             *dst = sum;
             sum = 0.f;
-            dst = acc + (ent[q + 1] >> 19);
+            dst = acc + (ent[q + 1] & 0xfffu);
           }
         }
       }
@@ -269,9 +277,9 @@ graph_gather_grad_sorted_kernel(int c, int n, int k, int estride, const int *__r
   float *gr = gx + (cloud * (size_t)c + ch) * n;
 #pragma unroll
   for (int u = 0; u < GS_OWN; ++u) {
-    const int j = threadIdx.x + u * GS_THREADS;
+    const int j = threadIdx.x + u * THREADS;
     if (j < n) {
-      const int beg = offb[j], end = offb[j + 1];
+      const int beg = ob[u], end = oe[u];
       float a = 0.f;
       if (end > beg) {
         a = acc[j];
@@ -296,17 +304,25 @@ static int launch_gather_grad(int b, int c, int n, int k, const int64_t *idx, co
                               cudaStream_t st) {
   const size_t sorted_smem = gs_smem_bytes(n, k);
   static const bool force_atomic = getenv("PCC_GATHER_GRAD_ATOMIC") != nullptr;  // measurement switch
-  if (!force_atomic && k <= 32 && (n * k) % 4 == 0 && sorted_smem <= 227 * 1024 && n <= GS_MAXN && edge_sort_ok(b, n, k) &&
+  if (!force_atomic && k <= 32 && (n * k) % 4 == 0 && sorted_smem <= 227 * 1024 && n <= GS_MAXN && edge_sort_ok(b, n, k, 1) &&
       (reinterpret_cast<uintptr_t>(gout) & 15) == 0) {
-    static size_t attr[64];
-    if (cudaError_t e = smem_optin(graph_gather_grad_sorted_kernel<MODE>, sorted_smem, attr); e != cudaSuccess) return (int)e;
+    // planes of up to ~100 KB: two 512-thread CTAs per SM, one sums while the other's plane loads
+    const bool half = sorted_smem <= 110 * 1024 && n <= GS_MAXN / 2;
+    static size_t attr[64], attr_h[64];
+    if (cudaError_t e = half ? smem_optin(graph_gather_grad_sorted_kernel<MODE, 512>, sorted_smem, attr_h)
+                             : smem_optin(graph_gather_grad_sorted_kernel<MODE, 1024>, sorted_smem, attr);
+        e != cudaSuccess)
+      return (int)e;
     char *ws = nullptr;
-    if (cudaError_t e = ws_alloc((void **)&ws, edge_sort_ws_bytes(b, n, k), st); e != cudaSuccess) return (int)e;
+    if (cudaError_t e = ws_alloc((void **)&ws, edge_sort_ws_bytes(b, n, k, 1), st); e != cudaSuccess) return (int)e;
     const int *off;
     const unsigned int *rev;
     int estride;
-    edge_sort_launch(b, n, k, idx, ws, true, &off, &rev, &estride, st);
-    graph_gather_grad_sorted_kernel<MODE><<<dim3(c, b), GS_THREADS, sorted_smem, st>>>(c, n, k, estride, off, rev, gout, gx);
+    edge_sort_launch(b, n, k, 1, idx, ws, true, &off, &rev, &estride, st);
+    if (half)
+      graph_gather_grad_sorted_kernel<MODE, 512><<<dim3(c, b), 512, sorted_smem, st>>>(c, n, k, estride, off, rev, gout, gx);
+    else
+      graph_gather_grad_sorted_kernel<MODE, 1024><<<dim3(c, b), 1024, sorted_smem, st>>>(c, n, k, estride, off, rev, gout, gx);
     cudaFreeAsync(ws, st);
     return finish_launch(5);
   }
