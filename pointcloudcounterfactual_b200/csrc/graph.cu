@@ -16,8 +16,12 @@
 //     bitwise reproducible (torch.gather's own backward is not).
 //   * atomic (planes that do not fit, or n*k not a multiple of 4): scatter-add into a shared-memory row with float
 //     atomics -- 511 us at C=64, N=2048, k=25, B=32, bound by the 105 M shared-memory atomics (1.4 cycles per lane).
-// Measured at that shape: forward 195 us (66 % of the HBM copy peak).  A variant of the sorted scheme that segmented-summed
-// runs with warp shuffles per 32 edges (ten shuffles each) before one atomic per run was measured at 795 us and dropped.
+// Measured at that shape: forward 195 us (66 % of the HBM copy peak); sorted backward 279 us (50 us of it the sort), i.e.
+// 3.0 TB/s of gradient read; N=1024, k=20: 124 us.  Measured and dropped: (a) segmented sums with warp shuffles per 32
+// edges before one atomic per run, 795 us; (b) the sorted kernel with the source range cut into four pieces and two
+// alternating shared-memory stages so that copies overlap sums inside one CTA, 335 us -- the loads disappear from the
+// stall profile but four times the run boundaries, eight barriers and the per-piece continuation pass cost more
+// instructions (153 M against 110 M warp-level) than the overlap returns.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
