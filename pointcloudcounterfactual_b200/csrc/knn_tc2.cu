@@ -18,8 +18,10 @@
 //     finally  the ~1.5 k candidates of a query are ranked by counting, one query per warp step and one candidate per
 //              lane; rank r < k is output slot r.
 // The candidate set provably contains the exact top-k: the TF32 score s~ of pair (i,j) is off by at most
-//     eps_ij = 2^-7.5 |x_i| |x_j| + 4e-5 (|x_i|^2 + |x_j|^2)
-// (truncation of both operands, Cauchy-Schwarz, 41 % slack; second term: fp32 rounding of norms / distances), a bound
+//     eps_ij = 1.03 * 2^-8 |x_i| |x_j| + 4e-5 (|x_i|^2 + |x_j|^2)
+// (truncation of both operands -- < 2^-10 relative each, so < 2^-9 on every product, x2 for the -2 x.y term -- and
+// Cauchy-Schwarz, 3 % slack: the tensor core's own accumulation error was measured at 1.6e-8 relative per MMA step;
+// second term: fp32 rounding of norms / distances), a bound
 // PER KEY: sweep 1 takes the k-th smallest group minimum of the UPPER bounds s~ + eps_ij (at least k keys are truly
 // below it), sweep 2 keeps the keys whose LOWER bound s~ - eps_ij does not exceed it.  With one bound per cloud
 // (max norm) instead, heavy-tailed features -- a dense core plus a few far outliers, what chained EdgeConv layers
@@ -50,7 +52,7 @@ struct T2 {
       A_BYTES + 2 * B_BYTES + 2 * 3 * R * 4 + (size_t)QUERIES * W * 4 + (size_t)NEPI * (PCAP + 64) * 4 + 256;
 };
 
-constexpr float T2_C1 = 0.0055242717f;  // 2^-7.5
+constexpr float T2_C1 = 0.00402832f;  // 2^-8 * 1.03125: truncation of both operands (< 2^-10 each), x2, Cauchy-Schwarz; 3 % slack
 constexpr float T2_C2 = 4e-5f;
 
 // transpose (B,C,N) -> (B,N,C), squared norms, and per key the three factors of the score bounds:

@@ -29,9 +29,10 @@ def ev(fn, reps=50):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-for (b, n, k) in ((32, 1024, 20), (32, 2048, 25), (32, 2048, 4), (32, 512, 16), (4, 2048, 25), (256, 1024, 20)):
-    x = synthetic.knn_xyz(b, n).to(dev)
-    r0 = _lib.route_counts()
-    us = ev(lambda: neighbour_ops.knn(x, k))
-    r1 = _lib.route_counts()
-    print(f"xyz kNN b={b} n={n} k={k}: {us:7.1f} us  routes {sorted(kk for kk in r1 if r1[kk] > r0[kk])}")
+if __name__ == "__main__":
+  for (b, n, k) in ((32, 1024, 20), (32, 2048, 25), (32, 2048, 4), (32, 512, 16), (4, 2048, 25), (256, 1024, 20)):
+      x = synthetic.knn_xyz(b, n).to(dev)
+      r0 = _lib.route_counts()
+      us = ev(lambda: neighbour_ops.knn(x, k))
+      r1 = _lib.route_counts()
+      print(f"xyz kNN b={b} n={n} k={k}: {us:7.1f} us  routes {sorted(kk for kk in r1 if r1[kk] > r0[kk])}")
