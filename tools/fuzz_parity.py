@@ -106,3 +106,88 @@ for it in range(20):
         fails += 1
         print("CHAMFER MISMATCH", dict(b=b, n=n, m=m, it=it), flush=True)
 print(f"fuzz: {cases} cases, {fails} failures")
+
+# ---- round-2 paths: the tensor-core xyz filter (forced), the sorted gather backward, the tcgen05 GEMM ----
+import os  # noqa: E402
+from pointcloudcounterfactual_b200 import _lib as L  # noqa: E402
+
+os.environ["PCC_KNN3_TC"] = "1"
+for it in range(24):
+    n = int(rng.integers(256, 2049))
+    npad = (n + 127) // 128 * 128
+    k = int(rng.integers(1, min(32, npad // 32) + 1))
+    b = int(rng.integers(1, 4))
+    style = int(rng.integers(0, 4))
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    x = torch.randn(b, 3, n, generator=g) * torch.tensor([1.0, 0.6, 0.3]).view(1, 3, 1)
+    if style == 1:
+        x = (x * 16).round() / 16                      # many exact ties
+    elif style == 2:
+        x = x * 1e-3 + torch.tensor([50.0, -20.0, 7.0]).view(1, 3, 1)   # tiny cloud far from the origin
+    elif style == 3:
+        x[:, :, ::97] *= 200.0                          # outliers stretch the fp16 scale
+    pm = bool(rng.integers(0, 2))
+    r0 = L.route_counts()
+    if pm:
+        from pointcloudcounterfactual_b200.keops import LazyTensor
+        xt = x.transpose(2, 1).contiguous().to(dev)
+        idx = ((LazyTensor(xt[:, :, None, :]) - LazyTensor(xt[:, None, :, :])) ** 2).sum(-1).argKmin(k, dim=2)
+    else:
+        idx = neighbour_ops.knn(x.to(dev), k)
+    r1 = L.route_counts()
+    eidx = oracle.knn(x.numpy(), k)
+    cases += 1
+    if r1.get("knn3_tc", 0) == r0.get("knn3_tc", 0) or not np.array_equal(idx.cpu().numpy(), eidx):
+        fails += 1
+        print("KNN3_TC MISMATCH / not routed", dict(n=n, k=k, b=b, style=style, pm=pm), flush=True)
+del os.environ["PCC_KNN3_TC"]
+
+for it in range(16):
+    c = int(rng.choice([1, 3, 8, 20]))
+    n = int(rng.integers(8, 2200))
+    k = int(rng.integers(1, 33))
+    b = int(rng.integers(1, 3))
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    x = torch.randn(b, c, n, generator=g).to(dev)
+    idx = torch.randint(0, n, (b, n, k), generator=g)
+    if it % 4 == 1:
+        idx[:, :, : max(1, k // 2)] = torch.randint(0, 3, (b, n, max(1, k // 2)), generator=g)  # hubs
+    idx = idx.to(dev)
+    for mode, fn in ((0, neighbour_ops.get_neighbours), (1, neighbour_ops.get_graph_features)):
+        w = torch.randn(b, (2 if mode else 1) * c, n, k, generator=g).to(dev)
+        a = x.clone().requires_grad_(True)
+        (fn(a, idx, k)[1] * w).sum().backward()
+        w64 = w.double()
+        ref = torch.zeros(b, c, n, dtype=torch.float64, device=dev)
+        ref.scatter_add_(2, idx.view(b, 1, n * k).expand(-1, c, -1), w64[:, :c].reshape(b, c, n * k))
+        if mode:
+            ref += (w64[:, c:] - w64[:, :c]).sum(3)
+        err = float((a.grad.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        cases += 1
+        if err > 1e-5:
+            fails += 1
+            print("GATHER GRAD MISMATCH", dict(c=c, n=n, k=k, b=b, mode=mode), err, flush=True)
+
+for it in range(16):
+    bt = int(rng.integers(1, 5))
+    m, n, k = int(rng.integers(1, 700)), int(rng.integers(1, 300)), int(rng.integers(1, 600))
+    ksplit = int(rng.choice([1, 1, 2, 4]))
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    ta, tb = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    A = torch.randn(bt, k, m, generator=g).to(dev) if ta else torch.randn(bt, m, k, generator=g).to(dev)
+    Bm = torch.randn(bt, k, n, generator=g).to(dev) if tb else torch.randn(bt, n, k, generator=g).to(dev)
+    sa = (A.stride(0), 1, m) if ta else (A.stride(0), k, 1)
+    sb = (Bm.stride(0), 1, n) if tb else (Bm.stride(0), k, 1)
+    out = torch.empty(bt * ksplit, m, n, device=dev)
+    edgeconv.gemm_nt(A, sa, Bm, sb, out, (m * n, n, 1), bt, m, n, k, ksplit=ksplit)
+    got = out.view(bt, ksplit, m, n).sum(1)
+    if got is not None:
+        A2 = A.transpose(1, 2) if ta else A
+        B2 = Bm.transpose(1, 2) if tb else Bm
+        ref = torch.bmm(A2.double(), B2.double().transpose(1, 2))
+        err = float((got.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        cases += 1
+        if err > 3e-6:
+            fails += 1
+            print("GEMM MISMATCH", dict(bt=bt, m=m, n=n, k=k, ta=ta, tb=tb), err, flush=True)
+print(f"fuzz (round-2 paths included): {cases} cases, {fails} failures")
