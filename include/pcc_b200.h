@@ -38,7 +38,7 @@ const char *pcc_status_string(int status);
 uint64_t pcc_launch_count(void);
 /* Dispatch evidence: how often an entry point chose a kernel family since the library was loaded.  `name` is one of
  * pcc_route_names() (comma separated: knn3w, knn3_thread, knn_tc2, knn_tc1, knn_simt, argmin_small, nn_sym, nn_asym,
- * nn_tc, knn3_tc, pm_self); -1 for an unknown name.  tests/ and bench.py use the deltas to prove that calls made
+ * nn_tc, knn3_tc, pm_self, knn_bf); -1 for an unknown name.  tests/ and bench.py use the deltas to prove that calls made
  * through the reference's unchanged call sites (KeOps LazyTensor shim) reach the fast kernels. */
 const char *pcc_route_names(void);
 int64_t pcc_route_count(const char *name);

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT_DIR = PKG / "_lib"
 LIB = OUT_DIR / "libpcc_b200.so"
-SOURCES = ["lib.cu", "chamfer.cu", "chamfer_tc.cu", "knn3_tc.cu", "knn.cu", "knn_tc.cu", "knn_tc2.cu", "approxmatch.cu", "auction.cu", "graph.cu", "edgeconv.cu", "gemm_tc.cu"]
+SOURCES = ["lib.cu", "chamfer.cu", "chamfer_tc.cu", "knn3_tc.cu", "knn.cu", "knn_tc.cu", "knn_tc2.cu", "knn_bf.cu", "approxmatch.cu", "auction.cu", "graph.cu", "edgeconv.cu", "gemm_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

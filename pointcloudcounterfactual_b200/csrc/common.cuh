@@ -31,6 +31,7 @@ enum Route {
   R_NN_TC,          // tcgen05 candidate filter + exact resolution (chamfer_tc.cu)
   R_KNN3_TC,        // xyz kNN with the tcgen05 candidate filter (knn3_tc.cu)
   R_PM_SELF,        // pcc_argkmin recognised q == r (point-major self kNN)
+  R_KNN_BF,         // feature kNN, bf16-split precise scores on tcgen05 (knn_bf.cu)
   R_COUNT
 };
 extern std::atomic<uint64_t> g_routes[R_COUNT];
@@ -158,6 +159,8 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 
 // knn_tc.cu: tcgen05 candidate generator + exact re-rank; PCC_ENOTSUP when the shape is outside that path
 int knn_tc_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st);
+// knn_bf.cu: feature kNN (C = 32 / 64, indices only) with bf16-split scores that order the candidates
+int knn_bf_launch(int b, int c, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st);
 // knn3_tc.cu: xyz kNN through the fp16 tensor-core candidate filter; PCC_ENOTSUP outside 256 <= n <= 2048, k <= 32
 int knn3_tc_launch(int b, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st);
 

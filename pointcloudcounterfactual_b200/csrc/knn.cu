@@ -706,7 +706,12 @@ static int launch_knn(int b, int c, int nq, int nr, int k, const float *q, const
   }
   if (self && !force_simt && c % 32 == 0) {
     static const bool tc_v1 = getenv("PCC_KNN_TC1") != nullptr;  // test hook: first-generation tcgen05 kernel only
-    int rc = tc_v1 ? PCC_ENOTSUP : knn_tc2_launch(b, c, nq, k, PM, q, idx, dist, st);
+    int rc = tc_v1 ? PCC_ENOTSUP : knn_bf_launch(b, c, nq, k, PM, q, idx, dist, st);  // indices only, C = 32 / 64
+    if (rc != PCC_ENOTSUP) {
+      note_route(R_KNN_BF);
+      return rc;
+    }
+    rc = tc_v1 ? PCC_ENOTSUP : knn_tc2_launch(b, c, nq, k, PM, q, idx, dist, st);
     if (rc != PCC_ENOTSUP) {
       note_route(R_KNN_TC2);
       return rc;

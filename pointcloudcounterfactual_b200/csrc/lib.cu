@@ -13,7 +13,7 @@ namespace pcc {
 std::atomic<uint64_t> g_launches{0};
 std::atomic<uint64_t> g_routes[R_COUNT];
 static const char *const kRouteNames[R_COUNT] = {"knn3w", "knn3_thread", "knn_tc2", "knn_tc1", "knn_simt", "argmin_small",
-                                                 "nn_sym", "nn_asym", "nn_tc", "knn3_tc", "pm_self"};
+                                                 "nn_sym", "nn_asym", "nn_tc", "knn3_tc", "pm_self", "knn_bf"};
 cudaError_t ws_alloc(void **ptr, size_t bytes, cudaStream_t st) {
   static std::mutex mu;
   static cudaMemPool_t pools[64] = {};
@@ -56,7 +56,7 @@ extern "C" __attribute__((visibility("default"))) const char *pcc_version(void) 
 extern "C" __attribute__((visibility("default"))) uint64_t pcc_launch_count(void) { return pcc::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" __attribute__((visibility("default"))) const char *pcc_route_names(void) {
-  return "knn3w,knn3_thread,knn_tc2,knn_tc1,knn_simt,argmin_small,nn_sym,nn_asym,nn_tc,knn3_tc,pm_self";
+  return "knn3w,knn3_thread,knn_tc2,knn_tc1,knn_simt,argmin_small,nn_sym,nn_asym,nn_tc,knn3_tc,pm_self,knn_bf";
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t pcc_route_count(const char *name) {

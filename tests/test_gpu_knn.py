@@ -5,7 +5,7 @@ import torch
 
 import oracle
 from conftest import rel_err
-from pointcloudcounterfactual_b200 import keops, neighbour_ops, synthetic
+from pointcloudcounterfactual_b200 import _lib, keops, neighbour_ops, synthetic
 
 pytestmark = pytest.mark.gpu
 
@@ -55,6 +55,57 @@ def test_feature_knn_structured_heavy_tailed_features(cuda, b, c, n, k):
     eidx, edist = oracle.knn(x.numpy(), k, return_dist=True)
     assert np.array_equal(idx.cpu().numpy(), eidx)
     assert np.array_equal(dist.cpu().numpy(), edist)
+
+
+def _heavy_tailed(b, c, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(b, 3, n, generator=g)
+    a = torch.randn(1, c, 3, generator=g)
+    x = torch.nn.functional.leaky_relu(a @ z + torch.randn(1, c, 1, generator=g) * 2.0, 0.2)
+    x[:, :, ::97] *= 30.0
+    x[:, :, 1::211] = x[:, :, 0::211][..., :x[:, :, 1::211].shape[-1]]
+    return x.contiguous()
+
+
+@pytest.mark.parametrize("kind,b,c,n,k", [
+    ("iid", 2, 64, 1024, 20), ("iid", 2, 64, 2048, 25), ("iid", 1, 32, 2048, 32), ("iid", 1, 64, 1000, 31),
+    ("iid", 2, 64, 777, 20), ("iid", 1, 32, 1111, 4), ("iid", 3, 64, 300, 16), ("iid", 1, 64, 256, 1),
+    ("scaled", 2, 64, 1024, 20), ("dup16", 1, 64, 1024, 20), ("dup8", 1, 32, 512, 20), ("heavy", 2, 64, 1024, 20),
+    ("heavy", 2, 32, 600, 8), ("heavy", 1, 64, 2048, 25), ("grid", 1, 64, 1024, 20), ("tiny", 1, 64, 512, 12),
+])
+def test_feature_knn_bf16_split_path_bit_exact(cuda, monkeypatch, kind, b, c, n, k):
+    """The experimental bf16-split tcgen05 path for indices-only feature kNN (opt-in: PCC_KNN_BF=1, read per call):
+    precise scores order the candidates, the exact fp32 chain is evaluated only inside the ambiguity band.  The indices
+    must equal the oracle's bit for bit on iid, rescaled, duplicated (massive exact ties), heavy-tailed (outliers with
+    huge norms, exact duplicates), quantised (many near-ties) and tiny-magnitude features, in both layouts."""
+    if kind == "iid":
+        x = synthetic.knn_features(b, c, n)
+    elif kind == "scaled":
+        x = synthetic.knn_features(b, c, n) * 7.5 + 1.0
+    elif kind == "dup16":
+        x = synthetic.knn_features(b, c, n // 16).repeat(1, 1, 16)
+    elif kind == "dup8":
+        x = synthetic.knn_features(b, c, n // 8).repeat(1, 1, 8)
+    elif kind == "heavy":
+        x = _heavy_tailed(b, c, n, 31 + n)
+    elif kind == "grid":
+        x = (synthetic.knn_features(b, c, n) * 2).round() / 2
+    else:
+        x = synthetic.knn_features(b, c, n) * 1e-4
+    x = x.contiguous()
+    monkeypatch.setenv("PCC_KNN_BF", "1")
+    want = oracle.knn(x.numpy(), k)
+    r0 = _lib.route_counts()
+    got = neighbour_ops.knn(x.to(cuda), k)
+    r1 = _lib.route_counts()
+    assert r1["knn_bf"] == r0["knn_bf"] + 1
+    assert np.array_equal(got.cpu().numpy(), want)
+    # point-major, through the KeOps expression of the reference's pykeops_knn
+    from pointcloudcounterfactual_b200.keops import LazyTensor
+    xt = x.transpose(2, 1).contiguous().to(cuda)
+    got_pm = ((LazyTensor(xt[:, :, None, :]) - LazyTensor(xt[:, None, :, :])) ** 2).sum(-1).argKmin(k, dim=2)
+    assert _lib.route_counts()["knn_bf"] == r1["knn_bf"] + 1
+    assert np.array_equal(got_pm.cpu().numpy(), want)
 
 
 def test_knn_ties_lowest_index(cuda):

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 name=$1; flags=$2
 out=pointcloudcounterfactual_b200/_lib/variants; mkdir -p $out/obj_$name
 objs=""
-for f in lib chamfer knn knn_tc knn_tc2 approxmatch auction graph edgeconv; do
+for f in $(python -c "from pointcloudcounterfactual_b200.build import SOURCES; print(' '.join(s[:-3] for s in SOURCES))"); do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $flags \
        -c pointcloudcounterfactual_b200/csrc/$f.cu -o $out/obj_$name/$f.o &
   objs="$objs $out/obj_$name/$f.o"
