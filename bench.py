@@ -577,11 +577,17 @@ def run_b200(args) -> None:
                     "(its cudnn convolution runs TF32 by default; the fused path's point GEMMs are fp32 unless "
                     "torch.backends.cuda.matmul.allow_tf32 is set -- ms_with_tf32_point_gemms)"}
 
-        # gradient exchange of the training step: 45 MB of fp32 in three buckets, each all-reduced on a communication stream
-        # as soon as "its" part of the backward is done (what DistributedDataParallel does with its buckets), so that only
-        # the last bucket is exposed; the whole step -- kernels of this library, torch glue and the NCCL calls -- is captured
-        # as ONE CUDA graph per rank when the capture is accepted
-        buckets = list(grad_buf.chunk(3))
+        # gradient exchange of the training step: 45 MB of fp32, bucketed the way DistributedDataParallel would bucket the
+        # reference's autoencoder (25 MB cap, reverse parameter order).  Where the parameters are (configs/experiment/
+        # autoencoder/model: w_dim 1024, PCGen with 8 components of conv_dims [1024, 256, 16]): decoder 10.5 M parameters =
+        # 42 MB, encoder final_conv 0.5 M = 2 MB, the four EdgeConv layers 0.09 M = 0.36 MB.  The decoder's gradients are
+        # complete once its backward is (loss -> graph_filtering -> MLPs), i.e. BEFORE the encoder's backward starts: buckets
+        # 0 (25 MB) and 1 (19.6 MB: rest of the decoder + final_conv) are all-reduced on a communication stream under the
+        # encoder's backward, and only bucket 2 (the EdgeConv weights, 0.4 MB) is exposed at the end.  The whole step -- kernels
+        # of this library, torch glue and the NCCL calls -- is captured as ONE CUDA graph per rank when the capture is accepted
+        n_all = grad_buf.numel()
+        n0, n2 = int(n_all * 25.0 / 45.0), int(n_all * 0.4 / 45.0)
+        buckets = [grad_buf[:n0], grad_buf[n0:n_all - n2], grad_buf[n_all - n2:]]
         comm = torch.cuda.Stream(dev)
 
         def reduce_bucket(i):
@@ -593,8 +599,8 @@ def run_b200(args) -> None:
         def ae_step():
             loss = losses.chamfer_emd(rr, ref_d)  # ChamferEMD forward + backward: the decoder's gradients come first
             torch.autograd.grad(loss.sum(), rr)
+            gfilt()  # decoder graph_filtering (kNN k=4 + smoothing forward / backward); the decoder MLPs would follow
             reduce_bucket(0)
-            gfilt()  # decoder graph_filtering (kNN k=4 + smoothing forward / backward)
             reduce_bucket(1)
             encoder_fb(True)  # encoder: per layer kNN graph (k=25) + fused EdgeConv layer, forward and backward
             reduce_bucket(2)
@@ -611,8 +617,9 @@ def run_b200(args) -> None:
             "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": ae_graphed,
             "note": "stand-in for configs[3]: DGCNN edge-convolution stack (4 layers, dynamic kNN k=25, fused EdgeConv) "
                     "forward and backward + decoder graph_filtering (kNN k=4) fwd+bwd + ChamferEMD fwd+bwd"
-                    + (" + NCCL all-reduce of 45 MB fp32 gradients in 3 buckets on a communication stream, overlapped with "
-                       "the rest of the backward" if world > 1 else "") + "; 32 clouds per GPU.  "
+                    + (" + NCCL all-reduce of 45 MB fp32 gradients in DDP-style buckets (25 + 19.6 MB = decoder and final_conv, "
+                       "reduced on a communication stream under the encoder's backward; 0.4 MB of EdgeConv weights exposed)"
+                       if world > 1 else "") + "; 32 clouds per GPU.  "
                     "Not included (plain torch layers of the reference): final_conv, the PCGen decoder MLPs, optimizer"}
 
         leaf = recon_d.detach().clone().requires_grad_(True)
