@@ -38,8 +38,15 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
     h1 = sharding.global_mean_loss_async(local)
     h2 = sharding.global_mean_loss_async(local * 2)
     amean, amean2 = h1.wait(), h2.wait()
+    # the per-interval form: local accumulation over several "steps", ONE collective when the value is read
+    acc = sharding.LossAccumulator(torch.device("cpu"))
+    for step in range(3):
+        acc.add(local * (step + 1))
+    acc_mean = acc.reduce()
+    acc.add(local)
+    acc_mean2 = acc.reduce()  # the reset worked: only the last add counts
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), local=local.numpy(), mean=mean.numpy(), grad=grad.numpy(),
-             amean=amean.numpy(), amean2=amean2.numpy())
+             amean=amean.numpy(), amean2=amean2.numpy(), acc_mean=acc_mean.numpy(), acc_mean2=acc_mean2.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,5 +64,7 @@ def test_sharded_loss_matches_single_process(tmp_path):
         assert abs(float(p["mean"]) - full.mean()) < 1e-7
         assert np.allclose(p["grad"], 1.5)
         assert abs(float(p["amean"]) - full.mean()) < 1e-7 and abs(float(p["amean2"]) - 2 * full.mean()) < 1e-6
+        assert abs(float(p["acc_mean"]) - 2 * full.mean()) < 1e-6  # (1 + 2 + 3) / 3 times the mean over all ranks' clouds
+        assert abs(float(p["acc_mean2"]) - full.mean()) < 1e-7
     lo, hi = sharding.shard_bounds(5, 2, 0)
     assert (lo, hi) == (0, 3)
