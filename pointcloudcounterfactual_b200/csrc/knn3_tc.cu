@@ -276,7 +276,10 @@ knn3_tc_kernel(int n, int k, int npad, int qt_per, const unsigned char *__restri
     const float babs = 2.f * K3T_CEPS * (nmax + nmax), brel = 1.f + 2.f * K3T_REL;
     const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * 2 * K3T_N);
     const uint32_t tfull_a = smem_u32(&ctl->tfull[set][0]), tempty_a = smem_u32(&ctl->tempty[set][0]);
-    const int ng = ntile * 4;  // two packed loads per tile, two groups (even / odd keys) per load
+    // two packed loads per tile; per load two groups (even / odd keys of the 64), or four groups of 16 keys (even / odd keys of
+    // the registers u % 4 < 2 and of the others) while 64 group minima hold them: a tighter tau, fewer candidates
+    const bool fine = ntile * 8 <= K3T_MAX_G;
+    const int ng = fine ? ntile * 8 : ntile * 4;
     const int ew = warp - 2;
     __half *gm = reinterpret_cast<__half *>(&S.cd[ew][0]) + lane;  // group g at gm[g * 32]
     float *cd = &S.cd[ew][lane * K3T_CSTRIDE];
@@ -315,9 +318,16 @@ knn3_tc_kernel(int n, int k, int npad, int qt_per, const unsigned char *__restri
             h0 = __hmin2(__hmin2(*reinterpret_cast<const __half2 *>(&w[u]), *reinterpret_cast<const __half2 *>(&w[u + 1])), h0);
             h1 = __hmin2(__hmin2(*reinterpret_cast<const __half2 *>(&w[u + 2]), *reinterpret_cast<const __half2 *>(&w[u + 3])), h1);
           }
-          const __half2 m2 = __hmin2(h0, h1);
-          gm[(t * 4 + h * 2) * 32] = __low2half(m2);
-          gm[(t * 4 + h * 2 + 1) * 32] = __high2half(m2);
+          if (fine) {
+            gm[(t * 8 + h * 4) * 32] = __low2half(h0);
+            gm[(t * 8 + h * 4 + 1) * 32] = __high2half(h0);
+            gm[(t * 8 + h * 4 + 2) * 32] = __low2half(h1);
+            gm[(t * 8 + h * 4 + 3) * 32] = __high2half(h1);
+          } else {
+            const __half2 m2 = __hmin2(h0, h1);
+            gm[(t * 4 + h * 2) * 32] = __low2half(m2);
+            gm[(t * 4 + h * 2 + 1) * 32] = __high2half(m2);
+          }
         }
       }
       // ---- tau = k-th smallest group minimum; limit in fp16, rounded up ----
@@ -482,12 +492,13 @@ knn3_tc_kernel(int n, int k, int npad, int qt_per, const unsigned char *__restri
 int knn3_tc_launch(int b, int n, int k, bool pm, const float *x, int64_t *idx, float *dist, cudaStream_t st) {
   if (b <= 0 || b > 65535 || n < 256 || n > K3T_MAX_N || k < 1 || k > K3T_MAX_K) return PCC_ENOTSUP;
   const int npad = (n + K3T_N - 1) / K3T_N * K3T_N;
-  if (npad / 32 < k) return PCC_ENOTSUP;
+  const int ngroups = npad / 128 * 8 <= K3T_MAX_G ? npad / 16 : npad / 32;  // group minima per query (see the kernel)
+  if (ngroups < k) return PCC_ENOTSUP;
   // Where this path wins over knn3w_kernel (tools/knn_time.py on B200, B = 32): N = 2048 -- 107 vs 160 us at k = 25, 78 vs
   // 142 us at k = 4; at N = 1024 the two tie (47 vs 44 us at k = 20) and below that, with few clouds (fewer than ~100 query
   // tiles in flight) or with k close to N / 32 (a loose threshold) the SIMT kernel is faster.  PCC_KNN3_TC=1 forces it.
   const bool force = getenv("PCC_KNN3_TC") != nullptr;  // read per call: tests switch it
-  if (!force && (n <= 1024 || npad / 32 < 2 * k || (long long)b * (npad / K3T_M) < 96)) return PCC_ENOTSUP;
+  if (!force && (n <= 1024 || ngroups < 2 * k || (long long)b * (npad / K3T_M) < 96)) return PCC_ENOTSUP;
   const size_t rows = (size_t)b * npad;
   unsigned char *ws = nullptr;
   cudaError_t e = ws_alloc((void **)&ws, rows * (2 * T16_ROWB + sizeof(float4)) + sizeof(float) * 2 * b, st);

@@ -30,7 +30,7 @@ def ev(fn, reps=50):
 
 
 if __name__ == "__main__":
-  for (b, n, k) in ((32, 1024, 20), (32, 2048, 25), (32, 2048, 4), (32, 512, 16), (4, 2048, 25), (256, 1024, 20)):
+  for (b, n, k) in ((32, 1024, 20), (32, 1024, 8), (32, 2048, 25), (32, 2048, 4), (32, 512, 16), (4, 2048, 25), (256, 1024, 20)):
       x = synthetic.knn_xyz(b, n).to(dev)
       r0 = _lib.route_counts()
       us = ev(lambda: neighbour_ops.knn(x, k))
