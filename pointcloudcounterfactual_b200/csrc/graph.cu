@@ -115,7 +115,7 @@ graph_gather_grad_kernel(int c, int n, int k, const int64_t *__restrict__ idx, c
       const float g = g_top[o];
       atomicAdd(&acc[(int)min(max(j, 0LL), (long long)n - 1)], g);
       if (MODE) {
-        pid = (int)__umulhi(o, magic);
+        pid = k > 1 ? (int)__umulhi(o, magic) : (int)o;  // k == 1: the magic constant 2^32 does not fit 32 bits
         v = g_bot[o] - g;
       }
     }

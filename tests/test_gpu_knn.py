@@ -258,7 +258,7 @@ def test_fused_graph_gather_forward_backward(cuda, b, c, n, k):
 
 
 @pytest.mark.parametrize("b,c,n,k,kind", [(2, 8, 2048, 25, "hub"), (2, 8, 1024, 20, "random"), (1, 4, 301, 5, "random"),
-                                          (1, 4, 512, 16, "one_target")])
+                                          (1, 4, 512, 16, "one_target"), (2, 8, 1605, 1, "random"), (1, 3, 77, 3, "random")])
 def test_graph_gather_backward_is_reproducible(cuda, b, c, n, k, kind):
     """The gather backward sums over the target-sorted edge list in a fixed order (no atomics): two runs agree bit for
     bit, also when a few targets collect most edges (feature-space hubs) or one target collects all of them; shapes

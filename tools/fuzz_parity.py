@@ -142,6 +142,38 @@ for it in range(24):
         print("KNN3_TC MISMATCH / not routed", dict(n=n, k=k, b=b, style=style, pm=pm), flush=True)
 del os.environ["PCC_KNN3_TC"]
 
+os.environ["PCC_KNN_BF"] = "1"   # the experimental bf16-split feature kNN (indices only)
+for it in range(24):
+    c = int(rng.choice([32, 64]))
+    n = int(rng.integers(256, 2049))
+    npad = (n + 127) // 128 * 128
+    ng = npad // 16 if npad // 64 <= 16 else npad // 32
+    k = int(rng.integers(1, min(32, ng) + 1))
+    b = int(rng.integers(1, 4))
+    style = int(rng.integers(0, 5))
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    x = torch.randn(b, c, n, generator=g)
+    if style == 1:
+        x = torch.nn.functional.leaky_relu(x, 0.2) + 3.0        # far from the origin
+    elif style == 2:
+        z = torch.randn(b, 4, n, generator=g)
+        x = torch.randn(1, c, 4, generator=g) @ z               # low-rank manifold
+        x[:, :, ::53] *= 25.0                                   # outliers
+    elif style == 3:
+        x = (x * 4).round() / 4                                 # exact ties in feature space
+    elif style == 4:
+        x = x * float(10.0 ** rng.integers(-6, 5))              # extreme scales
+    x = x.contiguous()
+    r0 = L.route_counts()
+    idx = neighbour_ops.knn(x.to(dev), k)
+    r1 = L.route_counts()
+    eidx = oracle.knn(x.numpy(), k)
+    cases += 1
+    if r1.get("knn_bf", 0) == r0.get("knn_bf", 0) or not np.array_equal(idx.cpu().numpy(), eidx):
+        fails += 1
+        print("KNN_BF MISMATCH / not routed", dict(c=c, n=n, k=k, b=b, style=style), flush=True)
+del os.environ["PCC_KNN_BF"]
+
 for it in range(16):
     c = int(rng.choice([1, 3, 8, 20]))
     n = int(rng.integers(8, 2200))
