@@ -28,6 +28,8 @@ typedef void *pcc_stream_t; /* a cudaStream_t */
 #define PCC_OK 0
 #define PCC_EINVAL (-1)    /* shape rule violated (mirrors emd_cuda_forward's -1, emd_cuda.cu:235-248) */
 #define PCC_ENOTSUP (-2)   /* configuration outside what the kernels support (e.g. k > PCC_KNN_MAX_K) */
+#define PCC_ELAUNCH (-3)   /* pcc_emd_forward / _backward only (they return 1 for success like emd_cuda_forward): the launch
+                              failed with cudaErrorInvalidValue, whose numeric value is 1 as well */
 #define PCC_KNN_MAX_K 128
 
 /* Library / build identification. */

@@ -434,13 +434,13 @@ extern "C" __attribute__((visibility("default"))) int pcc_emd_forward(int b, int
         cnt, eps, iters);
     if (pool) cudaFreeAsync(pool, (cudaStream_t)stream);
     const int rc = finish_launch(1);
-    return rc == 0 ? 1 : rc;
+    return rc == 0 ? 1 : (rc == 1 ? PCC_ELAUNCH : rc);  // 1 means success here: keep cudaErrorInvalidValue apart
   }
   auction_kernel<<<b, AU_THREADS, smem, (cudaStream_t)stream>>>(n, xyz1, xyz2, dist, assignment, price,
                                                                  assignment_inv, bid, bid_increments, max_increments,
                                                                  unass_idx, max_idx, eps, iters);
   const int rc = finish_launch(1);
-  return rc == 0 ? 1 : rc;
+  return rc == 0 ? 1 : (rc == 1 ? PCC_ELAUNCH : rc);  // 1 means success here: keep cudaErrorInvalidValue apart
 }
 
 extern "C" __attribute__((visibility("default"))) int pcc_emd_backward(int b, int n, const float *xyz1, const float *xyz2, float *gradxyz,
@@ -452,5 +452,5 @@ extern "C" __attribute__((visibility("default"))) int pcc_emd_backward(int b, in
   if (blocks > 148 * 32) blocks = 148 * 32;
   auction_grad_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(total, n, xyz1, xyz2, graddist, idx, gradxyz);
   const int rc = finish_launch(1);
-  return rc == 0 ? 1 : rc;
+  return rc == 0 ? 1 : (rc == 1 ? PCC_ELAUNCH : rc);  // 1 means success here: keep cudaErrorInvalidValue apart
 }

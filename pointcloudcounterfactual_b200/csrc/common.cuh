@@ -45,8 +45,10 @@ cudaError_t ws_alloc(void **ptr, size_t bytes, cudaStream_t st);
 
 // Opt-in to more than 48 KiB of dynamic shared memory.  The attribute is PER DEVICE: one process may drive several GPUs
 // (the Python wrappers take tensors on any device), so the high-water mark is kept per device ordinal.
+// The 48 KiB limit without opt-in counts STATIC shared memory too, so the opt-in starts well below it (at exactly 48 KiB of
+// dynamic memory -- n = 3072 in the auction kernels -- a kernel with a few static words was rejected at launch).
 template <typename Kernel>
-inline cudaError_t smem_optin(Kernel kernel, size_t bytes, size_t (&done)[64], size_t threshold = 48 * 1024) {
+inline cudaError_t smem_optin(Kernel kernel, size_t bytes, size_t (&done)[64], size_t threshold = 32 * 1024) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;

@@ -74,6 +74,8 @@ extern "C" __attribute__((visibility("default"))) const char *pcc_status_string(
       return "invalid shape (pcc: shape rule of the operator violated)";
     case PCC_ENOTSUP:
       return "unsupported configuration (pcc: outside kernel limits)";
+    case PCC_ELAUNCH:
+      return "kernel launch rejected (cudaErrorInvalidValue)";
     default:
       return cudaGetErrorString((cudaError_t)status);
   }

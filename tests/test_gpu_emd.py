@@ -107,7 +107,9 @@ def test_fused_is_deterministic(cuda):
     assert all(torch.equal(p, q) for p, q in zip(x, y))
 
 
-@pytest.mark.parametrize("b,n,eps,iters", [(3, 1024, 0.005, 50), (2, 2048, 0.005, 50), (1, 1024, 0.002, 3000), (2, 1024, 0.01, 1)])
+@pytest.mark.parametrize("b,n,eps,iters", [(3, 1024, 0.005, 50), (2, 2048, 0.005, 50), (1, 1024, 0.002, 3000), (2, 1024, 0.01, 1),
+                                           (2, 3072, 0.005, 30),   # exactly 48 KiB of dynamic shared memory + static words
+                                           (1, 4096, 0.01, 20), (1, 5120, 0.005, 10)])
 def test_auction_vs_oracle(cuda, b, n, eps, iters):
     a, c = synthetic.auction_clouds(b, n)
     edist, easg, _ = oracle.auction_emd(a.numpy(), c.numpy(), eps, iters)
