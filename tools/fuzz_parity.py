@@ -142,6 +142,29 @@ for it in range(24):
         print("KNN3_TC MISMATCH / not routed", dict(n=n, k=k, b=b, style=style, pm=pm), flush=True)
 del os.environ["PCC_KNN3_TC"]
 
+# point-major feature kNN through the KeOps expression of the reference's pykeops_knn (knn_tc2 / knn_tc / SIMT with pm = true)
+from pointcloudcounterfactual_b200.keops import LazyTensor as _LT  # noqa: E402
+for it in range(16):
+    c = int(rng.choice([32, 64, 96, 128, 17, 160, 5]))
+    n = int(rng.integers(40, 2300))
+    k = int(rng.integers(1, min(33, n)))
+    b = int(rng.integers(1, 4))
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    x = torch.randn(b, c, n, generator=g)
+    if it % 3 == 1:
+        x = torch.nn.functional.leaky_relu(x, 0.2) * 3.0 + 2.0
+    elif it % 3 == 2:
+        x = (x * 4).round() / 4
+    xt = x.transpose(2, 1).contiguous().to(dev)
+    r0 = L.route_counts()
+    idx = ((_LT(xt[:, :, None, :]) - _LT(xt[:, None, :, :])) ** 2).sum(-1).argKmin(k, dim=2)
+    r1 = L.route_counts()
+    eidx = oracle.knn(x.contiguous().numpy(), k)
+    cases += 1
+    if r1.get("pm_self", 0) == r0.get("pm_self", 0) or not np.array_equal(idx.cpu().numpy(), eidx):
+        fails += 1
+        print("PM FEATURE KNN MISMATCH / not routed", dict(c=c, n=n, k=k, b=b), flush=True)
+
 os.environ["PCC_KNN_BF"] = "1"   # the experimental bf16-split feature kNN (indices only)
 for it in range(24):
     c = int(rng.choice([32, 64]))
