@@ -142,6 +142,31 @@ for it in range(24):
         print("KNN3_TC MISMATCH / not routed", dict(n=n, k=k, b=b, style=style, pm=pm), flush=True)
 del os.environ["PCC_KNN3_TC"]
 
+# many clouds: the grids of the xyz kernels (query splits per cloud, resident-CTA fill) and of the tcgen05 kernels depend on b
+for it in range(8):
+    b = int(rng.choice([17, 33, 40, 64, 100]))
+    c = int(rng.choice([3, 3, 64, 32]))
+    n = int(rng.integers(260, 2049)) if c == 3 else int(rng.integers(64, 1200))
+    k = int(rng.integers(1, 33))
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    x = torch.randn(b, c, n, generator=g)
+    if c == 3 and it % 2:
+        os.environ["PCC_KNN3_TC"] = "1"
+    try:
+        idx, dist = neighbour_ops.knn_indices(x.to(dev), k, return_dist=True)
+    except RuntimeError as exc:  # forced filter outside its shapes
+        idx = None
+        if "unsupported" not in str(exc):
+            raise
+    os.environ.pop("PCC_KNN3_TC", None)
+    if idx is None:
+        idx, dist = neighbour_ops.knn_indices(x.to(dev), k, return_dist=True)
+    eidx, edist = oracle.knn(x.numpy(), k, return_dist=True)
+    cases += 1
+    if not (np.array_equal(idx.cpu().numpy(), eidx) and np.array_equal(dist.cpu().numpy(), edist)):
+        fails += 1
+        print("MANY-CLOUD KNN MISMATCH", dict(b=b, c=c, n=n, k=k, forced_tc=bool(c == 3 and it % 2)), flush=True)
+
 # point-major feature kNN through the KeOps expression of the reference's pykeops_knn (knn_tc2 / knn_tc / SIMT with pm = true)
 from pointcloudcounterfactual_b200.keops import LazyTensor as _LT  # noqa: E402
 for it in range(16):
