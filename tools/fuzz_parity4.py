@@ -77,4 +77,22 @@ for it in range(iters):
     if e[0] > 1e-6 or max(e[1:]) > 1e-5:
         fails += 1
         print("APPROXMATCH vs reference CUDA MISMATCH", dict(b=b, n=int(ta.shape[1]), m=int(tc.shape[1])), e, flush=True)
+# many clouds (the generate loop runs B = 256): small clouds, large batch
+for it in range(max(2, iters // 3)):
+    b, n, m = int(rng.choice([33, 64, 100, 256])), int(rng.integers(2, 300)), int(rng.integers(2, 300))
+    a, c = synthetic.s2_far(b, n, m)
+    ta, tc = a.to(dev), c.to(dev)
+    rd1, ri1, rd2, ri2 = ref.NNDistance(ta, tc)
+    d1, i1, d2, i2 = NNDistance(ta, tc)
+    rmatch, _ = ref.ApproxMatch(ta, tc)
+    rcost = ref.MatchCost(ta, tc, rmatch)
+    rg1, rg2 = ref.MatchCostGrad(ta, tc, rmatch)
+    torch.cuda.synchronize()
+    fc, f1, f2 = MatchCostFused(ta, tc)
+    cases += 1
+    ok = torch.equal(i1, ri1) and torch.equal(i2, ri2) and torch.equal(d1, rd1) and torch.equal(d2, rd2)
+    e = (rel(fc, rcost), rel(f1, rg1), rel(f2, rg2))
+    if not ok or max(e) > 1e-5:
+        fails += 1
+        print("MANY-CLOUD vs reference CUDA MISMATCH", dict(b=b, n=n, m=m), ok, e, flush=True)
 print(f"fuzz4 seed {seed}: {cases} cases, {fails} failures")
