@@ -130,10 +130,18 @@ int pcc_argkmin(int b, int nq, int nr, int c, int k, const float *q, const float
  * Indices outside [0,n) are clamped (torch.gather raises).  PCC_ENOTSUP for k > 32 or n > 8192 (caller composes). */
 int pcc_graph_gather(int b, int c, int n, int k, const float *x, const int64_t *idx, int mode, float *out,
                      pcc_stream_t stream);
-/* Its backward w.r.t. x: grad_x (b,c,n) is fully written; scatter-add by shared-memory float atomics (summation order
- * not fixed, like the backward of torch.gather). */
+/* Its backward w.r.t. x: grad_x (b,c,n) is fully written.  While one (point, neighbour) plane fits shared memory (n*k floats,
+ * n*k % 4 == 0, n <= 4096, k <= 32) the edges are sorted by target and summed in list order: no atomics, bitwise reproducible;
+ * other shapes scatter-add with shared-memory float atomics (summation order not fixed, like the backward of torch.gather). */
 int pcc_graph_gather_grad(int b, int c, int n, int k, const int64_t *idx, int mode, const float *grad_out,
                           float *grad_x, pcc_stream_t stream);
+/* The same backward with the edge sort hoisted: pcc_graph_edge_sort_bytes = size of the buffer the sort fills (0: the sorted
+ * backward does not cover this shape); pcc_graph_edge_sort depends on idx alone and may run early / on another stream;
+ * pcc_graph_gather_grad_presorted consumes the buffer (same results as pcc_graph_gather_grad, bit for bit). */
+long long pcc_graph_edge_sort_bytes(int b, int n, int k);
+int pcc_graph_edge_sort(int b, int n, int k, const int64_t *idx, void *ws, pcc_stream_t stream);
+int pcc_graph_gather_grad_presorted(int b, int c, int n, int k, int mode, const void *ws, const float *grad_out,
+                                    float *grad_x, pcc_stream_t stream);
 
 /* ---- Fused EdgeConv layer ----------------------------------------------------------------
  * Replaces get_graph_features (src/utils/neighbour_ops.py:113-119) -> EdgeConvLayer.forward (src/module/layers.py:

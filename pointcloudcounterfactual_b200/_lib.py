@@ -40,6 +40,9 @@ _SIGNATURES = {
     "pcc_argkmin": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pcc_graph_gather": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "pcc_graph_gather_grad": (_i, [_i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "pcc_graph_edge_sort_bytes": (ctypes.c_longlong, [_i, _i, _i]),
+    "pcc_graph_edge_sort": (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    "pcc_graph_gather_grad_presorted": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pcc_edgeconv_forward": (_i, [_i, _i, _i, _i] + [_vp] * 6 + [_i, ctypes.c_float, ctypes.c_float, _i, ctypes.c_float]
                              + [_vp] * 7),
     "pcc_edgeconv_backward": (_i, [_i, _i, _i, _i] + [_vp] * 6 + [_i, _i, ctypes.c_float] + [_vp] * 8),

@@ -177,6 +177,7 @@ size_t edge_sort_ws_bytes(int b, int n, int k, int pieces);
 bool edge_sort_ok(int b, int n, int k, int pieces);
 void edge_sort_launch(int b, int n, int k, int pieces, const int64_t *idx, char *ws, bool interleave, const int **off,
                       const unsigned int **rev, int *stride, cudaStream_t st);
+void edge_sort_views(int b, int n, int k, int pieces, const char *ws, const int **off, const unsigned int **rev, int *stride);
 __host__ __device__ inline int edge_pos(int p) {
   const int r = p & 511, l = r >> 4, q = r & 15;
   return (p & ~511) | ((q >> 2) << 7) | (l << 2) | (q & 3);

@@ -763,6 +763,16 @@ bool edge_sort_ok(int b, int n, int k, int pieces) {
   return b > 0 && n > 0 && n <= EC_MAX_N && k > 0 && k <= EC_MAX_K && pieces > 0 && n % pieces == 0 &&
          (long long)b * pieces <= 65535;
 }
+// the views of a workspace edge_sort_launch has filled (same carve-up)
+void edge_sort_views(int b, int n, int k, int pieces, const char *ws, const int **off_out, const unsigned int **rev_out,
+                     int *stride) {
+  const int subs = b * pieces, total = n / pieces * k, estride = es_stride(total);
+  const size_t cnt_bytes = es_up(sizeof(int) * (size_t)subs * EC_PARTS * n), rev_bytes = es_up(sizeof(int) * (size_t)subs * estride);
+  *off_out = reinterpret_cast<const int *>(ws);
+  const char *w = ws + es_up(sizeof(int) * (size_t)subs * (n + 1));
+  *rev_out = reinterpret_cast<const unsigned int *>(w + 2 * cnt_bytes + rev_bytes);
+  *stride = estride;
+}
 void edge_sort_launch(int b, int n, int k, int pieces, const int64_t *idx, char *ws, bool interleave, const int **off_out,
                       const unsigned int **rev_out, int *stride, cudaStream_t st) {
   const int subs = b * pieces, total = n / pieces * k, estride = es_stride(total);

@@ -303,32 +303,44 @@ static int launch_gather(int b, int c, int n, int k, const float *x, const int64
   return finish_launch(1);
 }
 
+// does the deterministic sorted backward cover this shape?
+static bool gather_sorted_ok(int b, int n, int k) {
+  static const bool force_atomic = getenv("PCC_GATHER_GRAD_ATOMIC") != nullptr;  // measurement switch
+  return !force_atomic && k <= 32 && (n * k) % 4 == 0 && gs_smem_bytes(n, k) <= 227 * 1024 && n <= GS_MAXN && edge_sort_ok(b, n, k, 1);
+}
+
+template <int MODE>
+static int launch_gather_grad_sorted(int b, int c, int n, int k, const int *off, const unsigned int *rev, int estride,
+                                     const float *gout, float *gx, cudaStream_t st) {
+  const size_t sorted_smem = gs_smem_bytes(n, k);
+  // planes of up to ~100 KB: two 512-thread CTAs per SM, one sums while the other's plane loads
+  const bool half = sorted_smem <= 110 * 1024 && n <= GS_MAXN / 2;
+  static size_t attr[64], attr_h[64];
+  if (cudaError_t e = half ? smem_optin(graph_gather_grad_sorted_kernel<MODE, 512>, sorted_smem, attr_h)
+                           : smem_optin(graph_gather_grad_sorted_kernel<MODE, 1024>, sorted_smem, attr);
+      e != cudaSuccess)
+    return (int)e;
+  if (half)
+    graph_gather_grad_sorted_kernel<MODE, 512><<<dim3(c, b), 512, sorted_smem, st>>>(c, n, k, estride, off, rev, gout, gx);
+  else
+    graph_gather_grad_sorted_kernel<MODE, 1024><<<dim3(c, b), 1024, sorted_smem, st>>>(c, n, k, estride, off, rev, gout, gx);
+  return finish_launch(1);
+}
+
 template <int MODE>
 static int launch_gather_grad(int b, int c, int n, int k, const int64_t *idx, const float *gout, float *gx,
                               cudaStream_t st) {
-  const size_t sorted_smem = gs_smem_bytes(n, k);
-  static const bool force_atomic = getenv("PCC_GATHER_GRAD_ATOMIC") != nullptr;  // measurement switch
-  if (!force_atomic && k <= 32 && (n * k) % 4 == 0 && sorted_smem <= 227 * 1024 && n <= GS_MAXN && edge_sort_ok(b, n, k, 1) &&
-      (reinterpret_cast<uintptr_t>(gout) & 15) == 0) {
-    // planes of up to ~100 KB: two 512-thread CTAs per SM, one sums while the other's plane loads
-    const bool half = sorted_smem <= 110 * 1024 && n <= GS_MAXN / 2;
-    static size_t attr[64], attr_h[64];
-    if (cudaError_t e = half ? smem_optin(graph_gather_grad_sorted_kernel<MODE, 512>, sorted_smem, attr_h)
-                             : smem_optin(graph_gather_grad_sorted_kernel<MODE, 1024>, sorted_smem, attr);
-        e != cudaSuccess)
-      return (int)e;
+  if (gather_sorted_ok(b, n, k) && (reinterpret_cast<uintptr_t>(gout) & 15) == 0) {
     char *ws = nullptr;
     if (cudaError_t e = ws_alloc((void **)&ws, edge_sort_ws_bytes(b, n, k, 1), st); e != cudaSuccess) return (int)e;
     const int *off;
     const unsigned int *rev;
     int estride;
     edge_sort_launch(b, n, k, 1, idx, ws, true, &off, &rev, &estride, st);
-    if (half)
-      graph_gather_grad_sorted_kernel<MODE, 512><<<dim3(c, b), 512, sorted_smem, st>>>(c, n, k, estride, off, rev, gout, gx);
-    else
-      graph_gather_grad_sorted_kernel<MODE, 1024><<<dim3(c, b), 1024, sorted_smem, st>>>(c, n, k, estride, off, rev, gout, gx);
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    const int rc = launch_gather_grad_sorted<MODE>(b, c, n, k, off, rev, estride, gout, gx, st);
     cudaFreeAsync(ws, st);
-    return finish_launch(5);
+    return rc;
   }
   const size_t smem = sizeof(float) * n;
   graph_gather_grad_kernel<MODE><<<dim3(c, b), GG_THREADS, smem, st>>>(c, n, k, idx, gout, gx);
@@ -479,6 +491,36 @@ extern "C" __attribute__((visibility("default"))) int pcc_graph_gather_grad(int 
   cudaStream_t st = (cudaStream_t)stream;
   return mode ? launch_gather_grad<1>(b, c, n, k, idx, grad_out, grad_x, st)
               : launch_gather_grad<0>(b, c, n, k, idx, grad_out, grad_x, st);
+}
+
+// The edge sort of the backward depends on idx alone: a caller that knows a backward will follow can run it early (e.g. on a
+// side stream under the forward gather) into its own buffer and hand it to pcc_graph_gather_grad_presorted.
+extern "C" __attribute__((visibility("default"))) long long pcc_graph_edge_sort_bytes(int b, int n, int k) {
+  if (b <= 0 || n <= 0 || k <= 0 || n > GG_MAXN || b > 65535 || !gather_sorted_ok(b, n, k)) return 0;
+  return (long long)edge_sort_ws_bytes(b, n, k, 1);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_graph_edge_sort(int b, int n, int k, const int64_t *idx, void *ws, pcc_stream_t stream) {
+  if (pcc_graph_edge_sort_bytes(b, n, k) == 0) return PCC_ENOTSUP;
+  const int *off;
+  const unsigned int *rev;
+  int estride;
+  edge_sort_launch(b, n, k, 1, idx, reinterpret_cast<char *>(ws), true, &off, &rev, &estride, (cudaStream_t)stream);
+  return finish_launch(4);
+}
+
+extern "C" __attribute__((visibility("default"))) int pcc_graph_gather_grad_presorted(int b, int c, int n, int k, int mode, const void *ws,
+                                                                                       const float *grad_out, float *grad_x,
+                                                                                       pcc_stream_t stream) {
+  if (b <= 0 || c <= 0 || n <= 0 || k <= 0 || (mode != 0 && mode != 1)) return PCC_EINVAL;
+  if (c > 65535 || pcc_graph_edge_sort_bytes(b, n, k) == 0 || (reinterpret_cast<uintptr_t>(grad_out) & 15) != 0) return PCC_ENOTSUP;
+  const int *off;
+  const unsigned int *rev;
+  int estride;
+  edge_sort_views(b, n, k, 1, reinterpret_cast<const char *>(ws), &off, &rev, &estride);
+  cudaStream_t st = (cudaStream_t)stream;
+  return mode ? launch_gather_grad_sorted<1>(b, c, n, k, off, rev, estride, grad_out, grad_x, st)
+              : launch_gather_grad_sorted<0>(b, c, n, k, off, rev, estride, grad_out, grad_x, st);
 }
 
 extern "C" __attribute__((visibility("default"))) int pcc_graph_filtering(int b, int n, int k, const float *x, const int64_t *idx, float *out,

@@ -94,31 +94,64 @@ def torch_knn(x: torch.Tensor, k: int) -> torch.Tensor:
     return self_square_distance(x).topk(k=k, largest=False)[1]
 
 
+_SIDE: dict[int, torch.cuda.Stream] = {}
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    i = device.index if device.index is not None else torch.cuda.current_device()
+    if i not in _SIDE:
+        _SIDE[i] = torch.cuda.Stream(device)
+    return _SIDE[i]
+
+
 class _GraphGather(Function):
     """x (B,C,N), idx (B,N,k) int64 -> neighbours (B,C,N,k) [mode 0] or graph features (B,2C,N,k) [mode 1] in ONE
-    kernel that writes the result once (pcc_graph_gather); backward = one scatter-add kernel (pcc_graph_gather_grad)."""
+    kernel that writes the result once (pcc_graph_gather).  Backward: sums over the edge list sorted by target, no atomics,
+    bitwise reproducible (pcc_graph_gather_grad).  When a backward will follow, the sort -- it depends on idx alone -- runs
+    during the forward on a side stream, under the HBM-bound gather, and is joined before the forward returns (so the fork
+    is safe inside a CUDA graph capture); the backward then consumes it (pcc_graph_gather_grad_presorted, same bits)."""
 
     @staticmethod
     def forward(ctx: Any, x: torch.Tensor, idx: torch.Tensor, mode: int) -> torch.Tensor:
         b, c, n = x.shape
         k = idx.shape[2]
+        lib = L.load()
+        ws = None
         with torch.cuda.device(x.device):
+            cur = torch.cuda.current_stream(x.device)
+            nbytes = int(lib.pcc_graph_edge_sort_bytes(b, n, k)) if x.requires_grad and idx.is_contiguous() else 0
+            if nbytes:
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                side = _side_stream(x.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    L.check(lib.pcc_graph_edge_sort(b, n, k, L.ptr(idx), L.ptr(ws), side.cuda_stream), "graph_edge_sort")
             out = torch.empty((b, (2 * c) if mode else c, n, k), dtype=torch.float32, device=x.device)
-            L.check(L.load().pcc_graph_gather(b, c, n, k, L.ptr(x), L.ptr(idx), mode, L.ptr(out), L.stream_of(x)),
-                    "graph_gather")
-        ctx.save_for_backward(idx)
+            L.check(lib.pcc_graph_gather(b, c, n, k, L.ptr(x), L.ptr(idx), mode, L.ptr(out), L.stream_of(x)), "graph_gather")
+            if nbytes:
+                cur.wait_stream(side)
+        if ws is None:
+            ctx.save_for_backward(idx)
+        else:
+            ctx.save_for_backward(idx, ws)
         ctx.dims = (b, c, n, k, mode)
         return out
 
     @staticmethod
     def backward(ctx: Any, grad_out: torch.Tensor):
-        (idx,) = ctx.saved_tensors
+        idx = ctx.saved_tensors[0]
+        ws = ctx.saved_tensors[1] if len(ctx.saved_tensors) > 1 else None
         b, c, n, k, mode = ctx.dims
         g = grad_out.contiguous()
+        lib = L.load()
         with torch.cuda.device(g.device):
             gx = torch.empty((b, c, n), dtype=torch.float32, device=g.device)
-            L.check(L.load().pcc_graph_gather_grad(b, c, n, k, L.ptr(idx), mode, L.ptr(g), L.ptr(gx), L.stream_of(g)),
-                    "graph_gather_grad")
+            if ws is not None and g.data_ptr() % 16 == 0:
+                L.check(lib.pcc_graph_gather_grad_presorted(b, c, n, k, mode, L.ptr(ws), L.ptr(g), L.ptr(gx), L.stream_of(g)),
+                        "graph_gather_grad_presorted")
+            else:
+                L.check(lib.pcc_graph_gather_grad(b, c, n, k, L.ptr(idx), mode, L.ptr(g), L.ptr(gx), L.stream_of(g)),
+                        "graph_gather_grad")
         return gx, None, None
 
 
