@@ -16,8 +16,9 @@
 //     bitwise reproducible (torch.gather's own backward is not).
 //   * atomic (planes that do not fit, or n*k not a multiple of 4): scatter-add into a shared-memory row with float
 //     atomics -- 511 us at C=64, N=2048, k=25, B=32, bound by the 105 M shared-memory atomics (1.4 cycles per lane).
-// Measured at that shape: forward 195 us (66 % of the HBM copy peak); sorted backward 279 us (50 us of it the sort), i.e.
-// 3.0 TB/s of gradient read; N=1024, k=20: 124 us.  Measured and dropped: (a) segmented sums with warp shuffles per 32
+// Measured at that shape: forward 195 us (66 % of the HBM copy peak); sorted backward 271 us (50 us of it the sort), i.e.
+// 3.1 TB/s of gradient read -- 256 us when the caller runs the sort early (pcc_graph_edge_sort on a side stream under the
+// forward, then pcc_graph_gather_grad_presorted); N=1024, k=20: 124 us.  Measured and dropped: (a) segmented sums with warp shuffles per 32
 // edges before one atomic per run, 795 us; (b) the sorted kernel with the source range cut into four pieces and two
 // alternating shared-memory stages so that copies overlap sums inside one CTA, 335 us -- the loads disappear from the
 // stall profile but four times the run boundaries, eight barriers and the per-piece continuation pass cost more
