@@ -119,7 +119,7 @@ class _GraphGather(Function):
         ws = None
         with torch.cuda.device(x.device):
             cur = torch.cuda.current_stream(x.device)
-            nbytes = int(lib.pcc_graph_edge_sort_bytes(b, n, k)) if x.requires_grad and idx.is_contiguous() else 0
+            nbytes = int(lib.pcc_graph_edge_sort_bytes(b, n, k)) if ctx.needs_input_grad[0] and idx.is_contiguous() else 0
             if nbytes:
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
                 side = _side_stream(x.device)
