@@ -14,6 +14,8 @@
 //            (5 exponentials per pair: levels j+1 are obtained from level j by two squarings) and either written
 //            to the (b,m,n) matrix (pcc_approxmatch; one 0.5 GiB write instead of nine read-modify-writes) or
 //            consumed on the fly into cost and gradients (pcc_matchcost_fused; the matrix never exists).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pcc {
@@ -242,6 +244,416 @@ am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__r
       rem[p] = r;
       ratB[p] = r / s1[e];                          // approxmatch.cu:60-61   (level B)
     }
+  }
+}
+
+// ---- exact-zero culling for the steep levels --------------------------------------------------------------------
+// E = ex2.approx.ftz(a) is EXACTLY +0 once a = d2 * level * log2e < -126 (the result would be subnormal), and
+// fma(+0 [* rl], w, acc) == acc bit for bit for finite w: a partner further than R_j = sqrt(126 / (4^j log2e)) from an
+// own point contributes NOTHING to that point's sequential sum, so dropping it leaves every rounding of the
+// reference's chain untouched.  At levels j = 7, 6, 5 (R = 0.073, 0.146, 0.29 on unit-sphere clouds) that is most pairs.
+//   am_group_kernel      per cloud and side, a permutation that makes consecutive blocks of 64 points spatially
+//                        tight (median splits by rank: counting sort by x, then by y inside every quarter, then by z
+//                        inside every sixteenth).  Which thread owns which point is free: only the partner ORDER is fixed.
+//   am_sweep*_cull       a warp owns one block of 64 points (two per lane).  It tests every staged partner against
+//                        the block's bounding box with a conservative cutoff (130 instead of 126: the box distance
+//                        is a lower bound of the computed d2 up to rounding) and appends the survivors' tile slots to
+//                        its own list -- in ascending partner index, i.e. the reference's summation order -- then runs
+//                        the unchanged inner loop over the list.  Lists are padded to the unroll width with a
+//                        zero-weight dummy partner (fma(E, 0, acc) == acc).  Non-finite own points or weights switch
+//                        the cull off for that warp / partner (NaN must keep propagating as in the full sweep).
+// Results are bit-identical to the full sweeps (tests/test_gpu_emd.py: culled == PCC_AM_NOCULL=1 on S1/S2/S3,
+// collapsed and NaN clouds).  S1 clouds, blocks of 64: 12 % / 26 % / 56 % of the partners survive at j = 7 / 6 / 5.
+constexpr int AMG_THREADS = 1024;
+constexpr int AMC_MAXPTS = 4096;    // clouds up to this size take the culled sweeps (u16 permutation, sort in smem)
+constexpr int AMC_LEVELS = 2;       // levels t = 0, 1 (j = 7, 6) are culled; at j = 5 the lists are 56 % full and do not pay
+constexpr float AMC_CUT = 130.f;    // cull when boxdist2 * |level * log2e| > AMC_CUT
+constexpr int AMC_PAD = 16;         // list padding granularity (>= both unroll widths) and spare tile entries
+
+// exclusive scan of cnt[0 .. nb) in place (nb <= AMG_THREADS * per), one contiguous chunk per thread
+__device__ __forceinline__ void amg_scan(int *cnt, int nb, int *warp_tot) {
+  const int per = (nb + AMG_THREADS - 1) / AMG_THREADS;
+  const int b0 = min((int)threadIdx.x * per, nb), b1 = min(b0 + per, nb);
+  int local = 0;
+  for (int i = b0; i < b1; ++i) local += cnt[i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    const int t = lane < AMG_THREADS / 32 ? warp_tot[lane] : 0;
+    int sc = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, sc, o);
+      if (lane >= o) sc += u;
+    }
+    if (lane < AMG_THREADS / 32) warp_tot[lane] = sc - t;
+  }
+  __syncthreads();
+  int off = warp_tot[w] + inc - local;
+  for (int i = b0; i < b1; ++i) {
+    const int d = cnt[i];
+    cnt[i] = off;
+    off += d;
+  }
+  __syncthreads();
+}
+
+// Three counting sorts: by x over the whole cloud (256 bins), by y inside every quarter of that order (64 bins each), by z
+// inside every sixteenth (32 bins each) -- median splits by RANK, so the blocks stay balanced whatever the density.  The order inside
+// a bin (shared-memory atomics) is arbitrary: nothing downstream depends on which thread owns which point.
+// The cloud is staged in shared memory once (every pass gathers coordinates through the current order).  Also
+// initialises this side's remain vector (am_init_kernel's job, approxmatch.cu:19-21) so the solve starts one launch earlier.
+__global__ void __launch_bounds__(AMG_THREADS)
+am_group_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                unsigned short *__restrict__ perm1, unsigned short *__restrict__ perm2, float *__restrict__ temp,
+                float multiL, float multiR) {
+  extern __shared__ __align__(16) float gx[];  // [cnt][3]
+  __shared__ unsigned short ord[2][AMC_MAXPTS];
+  __shared__ int hist[16 * 32];
+  __shared__ int warp_tot[AMG_THREADS / 32];
+  __shared__ float red[6][AMG_THREADS / 32];
+  __shared__ float ext[6];
+  const size_t cloud = blockIdx.x;
+  const int side = blockIdx.y;
+  const int cnt = side ? m : n;
+  const float *__restrict__ x = (side ? xyz2 : xyz1) + cloud * (size_t)cnt * 3;
+  unsigned short *__restrict__ perm = (side ? perm2 : perm1) + cloud * (size_t)cnt;
+  const float INF = __int_as_float(0x7f800000);
+  {  // temp per cloud: [remainL(n) | remainR(m) | ratioL(n) | ratioR(m)]
+    float *t = temp + cloud * (size_t)(n + m) * 2 + (side ? n : 0);
+    const float v = side ? multiR : multiL;
+    for (int i = threadIdx.x; i < cnt; i += AMG_THREADS) t[i] = v;
+  }
+  // stage the coordinates; extents per axis (non-finite coordinates are ignored; they land in bin 0)
+  float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
+  for (int i = threadIdx.x; i < cnt * 3; i += AMG_THREADS) {
+    const float v = x[i];
+    gx[i] = v;
+    const int ax = i % 3;
+    if (fabsf(v) <= 3.0e38f) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        if (a == ax) {
+          lo[a] = fminf(lo[a], v);
+          hi[a] = fmaxf(hi[a], v);
+        }
+    }
+  }
+  for (int i = threadIdx.x; i < cnt; i += AMG_THREADS) ord[0][i] = (unsigned short)i;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[a][threadIdx.x >> 5] = lo[a];
+      red[3 + a][threadIdx.x >> 5] = hi[a];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = red[threadIdx.x][0];
+    for (int w = 1; w < AMG_THREADS / 32; ++w) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
+    ext[threadIdx.x] = v;
+  }
+  int cur = 0;
+  for (int axis = 0; axis < 3; ++axis) {
+    const int nseg = axis == 0 ? 1 : (axis == 1 ? 4 : 16);
+    const int nbin = axis == 0 ? 256 : (axis == 1 ? 64 : 32);
+    const int seg_len = (cnt + nseg - 1) / nseg;
+    const float inv_len = 1.f / (float)seg_len;  // (pos + 0.5) / seg_len is never within 1e-4 of an integer: exact floor
+    for (int i = threadIdx.x; i < nseg * nbin; i += AMG_THREADS) hist[i] = 0;
+    __syncthreads();
+    const float l = ext[axis], h = ext[3 + axis];
+    const float scale = (h > l) ? (float)nbin / (h - l) : 0.f;
+    auto key_of = [&](int pos) {
+      const float v = gx[ord[cur][pos] * 3 + axis];
+      int bin = (fabsf(v) <= 3.0e38f) ? (int)((v - l) * scale) : 0;
+      bin = min(max(bin, 0), nbin - 1);
+      return (int)(((float)pos + 0.5f) * inv_len) * nbin + bin;
+    };
+    for (int pos = threadIdx.x; pos < cnt; pos += AMG_THREADS) atomicAdd(&hist[key_of(pos)], 1);
+    __syncthreads();
+    amg_scan(hist, nseg * nbin, warp_tot);
+    for (int pos = threadIdx.x; pos < cnt; pos += AMG_THREADS)
+      ord[cur ^ 1][atomicAdd(&hist[key_of(pos)], 1)] = ord[cur][pos];
+    __syncthreads();
+    cur ^= 1;
+  }
+  for (int i = threadIdx.x; i < cnt; i += AMG_THREADS) perm[i] = ord[cur][i];
+}
+
+struct AmBox {
+  float lx, hx, ly, hy, lz, hz;
+  bool ok;  // every own coordinate finite: the cull may be applied
+};
+
+// bounding box of the warp's 64 own points (a, b per lane; both valid point indices)
+__device__ __forceinline__ AmBox am_warp_box(float ax, float ay, float az, float bx, float by, float bz, float fa = 0.f,
+                                             float fb = 0.f) {  // fa, fb: own factors that must be finite as well
+  AmBox r;
+  r.lx = fminf(ax, bx); r.hx = fmaxf(ax, bx);
+  r.ly = fminf(ay, by); r.hy = fmaxf(ay, by);
+  r.lz = fminf(az, bz); r.hz = fmaxf(az, bz);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    r.lx = fminf(r.lx, __shfl_xor_sync(0xffffffffu, r.lx, o));
+    r.hx = fmaxf(r.hx, __shfl_xor_sync(0xffffffffu, r.hx, o));
+    r.ly = fminf(r.ly, __shfl_xor_sync(0xffffffffu, r.ly, o));
+    r.hy = fmaxf(r.hy, __shfl_xor_sync(0xffffffffu, r.hy, o));
+    r.lz = fminf(r.lz, __shfl_xor_sync(0xffffffffu, r.lz, o));
+    r.hz = fmaxf(r.hz, __shfl_xor_sync(0xffffffffu, r.hz, o));
+  }
+  const float big = 3.0e38f;
+  const bool fin = fabsf(ax) <= big && fabsf(ay) <= big && fabsf(az) <= big && fabsf(bx) <= big && fabsf(by) <= big &&
+                   fabsf(bz) <= big && fabsf(fa) <= big && fabsf(fb) <= big;  // false for NaN / inf
+  r.ok = __all_sync(0xffffffffu, fin);
+  return r;
+}
+
+// Appends, in ascending order, the byte offsets (slot * 16) of the staged partners [0, cnt) that may reach the box;
+// pads the list to a multiple of AMC_PAD with the dummy slot `cnt`.  Returns the padded length.  `cull` is false when
+// an own point or factor of this warp, or any staged weight, is not finite (0 * inf must stay NaN): every partner is
+// kept then.  Two partners per lane and step (64 per step): their tests are independent work.
+__device__ __forceinline__ int am_build_list(const float4 *tile, int cnt, const AmBox &bx, float cut, bool cull,
+                                             unsigned short *list, int lane) {
+  int len = 0;
+  const unsigned int below = (1u << lane) - 1u;
+  for (int i0 = 0; i0 < cnt; i0 += 64) {
+    const int ia = i0 + lane, ib = i0 + 32 + lane;
+    bool ka = false, kb = false;
+    if (ia < cnt) {
+      const float4 q = tile[ia];
+      const float dx = fmaxf(fmaxf(bx.lx - q.x, q.x - bx.hx), 0.f);
+      const float dy = fmaxf(fmaxf(bx.ly - q.y, q.y - bx.hy), 0.f);
+      const float dz = fmaxf(fmaxf(bx.lz - q.z, q.z - bx.hz), 0.f);
+      ka = !(fmaf(dz, dz, fmaf(dx, dx, dy * dy)) > cut) || !cull;  // NaN partner coordinates give 0 or NaN: kept
+    }
+    if (ib < cnt) {
+      const float4 q = tile[ib];
+      const float dx = fmaxf(fmaxf(bx.lx - q.x, q.x - bx.hx), 0.f);
+      const float dy = fmaxf(fmaxf(bx.ly - q.y, q.y - bx.hy), 0.f);
+      const float dz = fmaxf(fmaxf(bx.lz - q.z, q.z - bx.hz), 0.f);
+      kb = !(fmaf(dz, dz, fmaf(dx, dx, dy * dy)) > cut) || !cull;
+    }
+    const unsigned int ba = __ballot_sync(0xffffffffu, ka), bb = __ballot_sync(0xffffffffu, kb);
+    const int na = __popc(ba);
+    if (ka) list[len + __popc(ba & below)] = (unsigned short)(ia * 16);
+    if (kb) list[len + na + __popc(bb & below)] = (unsigned short)(ib * 16);
+    len += na + __popc(bb);
+  }
+  const int lenp = (len + AMC_PAD - 1) / AMC_PAD * AMC_PAD;
+  for (int i = len + lane; i < lenp; i += 32) list[i] = (unsigned short)(cnt * 16);
+  __syncwarp();
+  return lenp;
+}
+
+// dynamic shared memory of the culled sweeps: partner tile (+ spare entries), optional second weights, four lists
+constexpr size_t AMC_TILE_BYTES = (size_t)(AM_QTILE + AMC_PAD) * 16;
+constexpr size_t AMC_W_BYTES = (size_t)(AM_QTILE + AMC_PAD) * 4;
+constexpr size_t AMC_LIST_BYTES = (size_t)(AM_QTILE + AMC_PAD) * 2;
+constexpr size_t AMC_SMEM1 = AMC_TILE_BYTES + (AM_THREADS / 32) * AMC_LIST_BYTES;
+constexpr size_t AMC_SMEM31 = AMC_TILE_BYTES + AMC_W_BYTES + (AM_THREADS / 32) * AMC_LIST_BYTES;
+
+// am_sweep_kernel<EPI, 2, 16> over the culled partner lists; own points through `perm`.
+template <int EPI>
+__global__ void __launch_bounds__(AM_THREADS, 4)  // states the register budget: ptxas otherwise serialises the loop (44 regs)
+am_sweep_cull_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
+                     const float *__restrict__ wQ, size_t wQ_stride, float level, float cut,
+                     const unsigned short *__restrict__ permP, float *__restrict__ remainP, size_t remain_stride,
+                     float *__restrict__ ratioP, size_t ratio_stride) {
+  constexpr int U = 16;
+  extern __shared__ __align__(16) unsigned char csm[];
+  float4 *tile = reinterpret_cast<float4 *>(csm);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned short *list = reinterpret_cast<unsigned short *>(csm + AMC_TILE_BYTES + warp * AMC_LIST_BYTES);
+  const size_t cloud = blockIdx.y;
+  xP += cloud * (size_t)nP * 3;
+  xQ += cloud * (size_t)nQ * 3;
+  wQ += cloud * wQ_stride;
+  permP += cloud * (size_t)nP;
+  float *rem = remainP + cloud * remain_stride;
+  float *rat = ratioP + cloud * ratio_stride;
+  // warp w of block bx owns the permuted slots g0 + lane and g0 + 32 + lane
+  const int g0 = blockIdx.x * (AM_THREADS * 2) + warp * 64;
+  const int sa = g0 + lane, sb = g0 + 32 + lane;
+  const int a = permP[min(sa, nP - 1)], b = permP[min(sb, nP - 1)];
+  const float ax = xP[a * 3], ay = xP[a * 3 + 1], az = xP[a * 3 + 2];
+  const float bx_ = xP[b * 3], by_ = xP[b * 3 + 1], bz_ = xP[b * 3 + 2];
+  const f32x2 npx = pack2(-ax, -bx_), npy = pack2(-ay, -by_), npz = pack2(-az, -bz_);
+  const float init = (EPI == EPI_RATIO_L) ? 1e-9f : 0.f;
+  f32x2 acc = pack2(init, init);
+  const float rla = (EPI == EPI_REMAIN_L) ? rat[a] : 0.f, rlb = (EPI == EPI_REMAIN_L) ? rat[b] : 0.f;
+  const f32x2 rl2 = pack2(rla, rlb);
+  const float lc = level * AM_LOG2E;
+  const f32x2 lc2 = pack2(lc, lc);
+  const AmBox box = am_warp_box(ax, ay, az, bx_, by_, bz_, rla, rlb);  // inf * 0 must stay NaN: no cull then
+  // the epilogue's operands, requested now (their latency would otherwise end the kernel)
+  const float rema = rem[a], remb = rem[b];
+
+  for (int base = 0; base < nQ; base += AM_QTILE) {
+    const int cnt = min(AM_QTILE, nQ - base);
+    __syncthreads();
+    bool wfin = true;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < cnt + 1; i += AM_THREADS) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // slot cnt: the zero-weight dummy partner
+      if (i < cnt) {
+        const float *q = xQ + (size_t)(base + i) * 3;
+        v = make_float4(q[0], q[1], q[2], wQ[base + i]);
+      }
+      wfin = wfin && fabsf(v.w) <= 3.0e38f;
+      tile[i] = v;
+    }
+    const bool cull = __syncthreads_and(wfin) && box.ok;
+    const int len = am_build_list(tile, cnt, box, cut, cull, list, lane);
+    const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
+#pragma unroll 1
+    for (int l = 0; l < len; l += U) {
+      f32x2 E[U];
+      float w[U];
+      const uint4 o0 = *reinterpret_cast<const uint4 *>(list + l), o1 = *reinterpret_cast<const uint4 *>(list + l + 8);
+      const unsigned int ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+      float4 q[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned int off = (u & 1) ? (ow[u >> 1] >> 16) : (ow[u >> 1] & 0xffffu);
+        q[u] = *reinterpret_cast<const float4 *>(tb + off);
+      }
+      asm volatile("" ::: "memory");  // all gathers are issued before the first use (the compiler sank them otherwise)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        w[u] = q[u].w;
+        am_exp_terms<1>(q[u], &npx, &npy, &npz, lc2, &E[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        f32x2 e = E[u];
+        if (EPI == EPI_REMAIN_L) e = mul2(rl2, e);
+        acc = fma2(e, pack2(w[u], w[u]), acc);
+      }
+    }
+  }
+  float s[2];
+  unpack2(acc, s[0], s[1]);
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if ((e ? sb : sa) >= nP) continue;
+    const int p = e ? b : a;
+    const float r = e ? remb : rema;
+    if (EPI == EPI_RATIO_L) {  // approxmatch.cu:60-61
+      rat[p] = r / s[e];
+    } else if (EPI == EPI_RATIO_R) {  // approxmatch.cu:104-109
+      const float sumr = s[e] * r;
+      const float consumption = fminf(r / (sumr + 1e-9f), 1.0f);
+      rat[p] = consumption * r;
+      rem[p] = fmaxf(0.0f, r - sumr);
+    } else {  // approxmatch.cu:161-162
+      rem[p] = fmaxf(0.0f, r - s[e]);
+    }
+  }
+}
+
+// am_sweep31_kernel<2> over the culled partner lists (the cutoff is level B's: E_B == 0 implies E_A == 0).
+__global__ void __launch_bounds__(AM_THREADS, 4)
+am_sweep31_cull_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__restrict__ xQ,
+                       const float *__restrict__ ratioR_A, size_t ratioR_stride, const float *__restrict__ remainR,
+                       size_t remainR_stride, float levelA, float levelB, float cut,
+                       const unsigned short *__restrict__ permP, float *__restrict__ remainL, size_t remainL_stride,
+                       const float *__restrict__ ratioL_A, float *__restrict__ ratioL_B, size_t ratioL_stride) {
+  constexpr int U = 8;
+  extern __shared__ __align__(16) unsigned char csm[];
+  float4 *tile = reinterpret_cast<float4 *>(csm);               // (x, y, z, ratioR_A) per partner
+  float *wB = reinterpret_cast<float *>(csm + AMC_TILE_BYTES);  // remainR per partner
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned short *list =
+      reinterpret_cast<unsigned short *>(csm + AMC_TILE_BYTES + AMC_W_BYTES + warp * AMC_LIST_BYTES);
+  const size_t cloud = blockIdx.y;
+  xP += cloud * (size_t)nP * 3;
+  xQ += cloud * (size_t)nQ * 3;
+  ratioR_A += cloud * ratioR_stride;
+  remainR += cloud * remainR_stride;
+  permP += cloud * (size_t)nP;
+  float *rem = remainL + cloud * remainL_stride;
+  const float *ratA = ratioL_A + cloud * ratioL_stride;
+  float *ratB = ratioL_B + cloud * ratioL_stride;
+  const int g0 = blockIdx.x * (AM_THREADS * 2) + warp * 64;
+  const int sa = g0 + lane, sb = g0 + 32 + lane;
+  const int a = permP[min(sa, nP - 1)], b = permP[min(sb, nP - 1)];
+  const float ax = xP[a * 3], ay = xP[a * 3 + 1], az = xP[a * 3 + 2];
+  const float bx_ = xP[b * 3], by_ = xP[b * 3 + 1], bz_ = xP[b * 3 + 2];
+  const f32x2 npx = pack2(-ax, -bx_), npy = pack2(-ay, -by_), npz = pack2(-az, -bz_);
+  f32x2 acc3 = 0ull, acc1 = pack2(1e-9f, 1e-9f);
+  const float rla = ratA[a], rlb = ratA[b];
+  const f32x2 rl2 = pack2(rla, rlb);
+  const float lcA = levelA * AM_LOG2E, lcB = levelB * AM_LOG2E;
+  const f32x2 lcA2 = pack2(lcA, lcA), lcB2 = pack2(lcB, lcB);
+  const AmBox box = am_warp_box(ax, ay, az, bx_, by_, bz_, rla, rlb);
+  const float rema = rem[a], remb = rem[b];  // the epilogue's operands, requested now
+
+  for (int base = 0; base < nQ; base += AM_QTILE) {
+    const int cnt = min(AM_QTILE, nQ - base);
+    __syncthreads();
+    bool wfin = true;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < cnt + 1; i += AM_THREADS) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      float w1 = 0.f;
+      if (i < cnt) {
+        const float *q = xQ + (size_t)(base + i) * 3;
+        v = make_float4(q[0], q[1], q[2], ratioR_A[base + i]);
+        w1 = remainR[base + i];
+      }
+      wfin = wfin && fabsf(v.w) <= 3.0e38f && fabsf(w1) <= 3.0e38f;
+      tile[i] = v;
+      wB[i] = w1;
+    }
+    const bool cull = __syncthreads_and(wfin) && box.ok;
+    const int len = am_build_list(tile, cnt, box, cut, cull, list, lane);
+    const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
+    const unsigned char *wb = reinterpret_cast<const unsigned char *>(wB);
+#pragma unroll 1
+    for (int l = 0; l < len; l += U) {
+      const uint4 o0 = *reinterpret_cast<const uint4 *>(list + l);
+      const unsigned int ow[4] = {o0.x, o0.y, o0.z, o0.w};
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned int off = (u & 1) ? (ow[u >> 1] >> 16) : (ow[u >> 1] & 0xffffu);
+        const float4 q = *reinterpret_cast<const float4 *>(tb + off);
+        const float w1 = *reinterpret_cast<const float *>(wb + (off >> 2));
+        const f32x2 qx = pack2(q.x, q.x), qy = pack2(q.y, q.y), qz = pack2(q.z, q.z), qw3 = pack2(q.w, q.w),
+                    qw1 = pack2(w1, w1);
+        const f32x2 dx = add2(qx, npx), dy = add2(qy, npy), dz = add2(qz, npz);
+        const f32x2 d2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+        float a0, a1, b0, b1;
+        unpack2(mul2(d2, lcA2), a0, a1);
+        unpack2(mul2(d2, lcB2), b0, b1);
+        const f32x2 EA = pack2(ex2_ftz(a0), ex2_ftz(a1));
+        const f32x2 EB = pack2(ex2_ftz(b0), ex2_ftz(b1));
+        acc3 = fma2(mul2(rl2, EA), qw3, acc3);
+        acc1 = fma2(EB, qw1, acc1);
+      }
+    }
+  }
+  float s3[2], s1[2];
+  unpack2(acc3, s3[0], s3[1]);
+  unpack2(acc1, s1[0], s1[1]);
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if ((e ? sb : sa) >= nP) continue;
+    const int p = e ? b : a;
+    const float r = fmaxf(0.0f, (e ? remb : rema) - s3[e]);  // approxmatch.cu:161-162 (level A)
+    rem[p] = r;
+    ratB[p] = r / s1[e];                                     // approxmatch.cu:60-61   (level B)
   }
 }
 
@@ -554,8 +966,17 @@ struct AmWorkspace {
   float *fL = nullptr;  // [9][b][n]
   float *fR = nullptr;  // [9][b][m]
   float *cost_part = nullptr;
+  unsigned short *perm1 = nullptr, *perm2 = nullptr;  // spatial grouping of either cloud (culled sweeps), or null
   size_t fL_level_stride = 0, fR_level_stride = 0;
 };
+
+// PCC_AM_NOCULL=1 (read at every call: the parity test toggles it) keeps every level on the full sweeps.
+static bool am_cull_enabled(int n, int m) {
+  if (n > AMC_MAXPTS || m > AMC_MAXPTS) return false;
+  const char *e = getenv("PCC_AM_NOCULL");
+  return !(e && e[0] && e[0] != '0');
+}
+
 
 // -4^j for j = 7..-1, evaluated ONCE per process by the device's own powf (the reference calls powf in the kernel,
 // approxmatch.cu:25).  Falls back to the host's powf when the first call happens under stream capture.
@@ -589,11 +1010,24 @@ static int am_levels(cudaStream_t st, AmLevels *out) {
 static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, float *temp, AmWorkspace &ws,
                     size_t extra_floats, const AmLevels &lv, cudaStream_t st, int *launches) {
   const size_t nfl = (size_t)AM_LEVELS * b * n, nfr = (size_t)AM_LEVELS * b * m;
-  cudaError_t e = ws_alloc((void **)&ws.base, sizeof(float) * (nfl + nfr + extra_floats), st);
+  const bool cull = am_cull_enabled(n, m);
+  const size_t perm_floats = cull ? ((size_t)b * (n + m) + 1) / 2 : 0;  // u16 entries
+  cudaError_t e = ws_alloc((void **)&ws.base, sizeof(float) * (nfl + nfr + extra_floats + perm_floats), st);
   if (e != cudaSuccess) return (int)e;
   ws.fL = ws.base;
   ws.fR = ws.base + nfl;
   ws.cost_part = ws.base + nfl + nfr;
+  if (cull) {
+    ws.perm1 = reinterpret_cast<unsigned short *>(ws.base + nfl + nfr + extra_floats);
+    ws.perm2 = ws.perm1 + (size_t)b * n;
+    static size_t a1[64], a2[64], a4[64];
+    if ((e = smem_optin(am_sweep_cull_kernel<EPI_RATIO_L>, AMC_SMEM1, a1)) != cudaSuccess ||
+        (e = smem_optin(am_sweep_cull_kernel<EPI_RATIO_R>, AMC_SMEM1, a2)) != cudaSuccess ||
+        (e = smem_optin(am_sweep31_cull_kernel, AMC_SMEM31, a4)) != cudaSuccess)
+      return (int)e;
+  }
+  // cutoff on the squared box distance for level t: E underflows to +0 beyond it (see the culled kernels)
+  auto cut = [&](int t) { return AMC_CUT / (-(lv.lv[t] * AM_LOG2E)); };
   ws.fL_level_stride = (size_t)b * n;
   ws.fR_level_stride = (size_t)b * m;
   float multiL, multiR;  // approxmatch.cu:6-12 (integer division)
@@ -606,7 +1040,14 @@ static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, f
   }
   const size_t tstride = (size_t)(n + m) * 2;
   float *remainL = temp, *remainR = temp + n;
-  PCC_LAUNCH(PDL_EMD_SMALL, am_init_kernel, dim3((n + m + 255) / 256, b), 256, 0, st, n, m, temp, multiL, multiR);
+  if (cull) {  // the grouping kernel also initialises remainL / remainR
+    const size_t gsm = sizeof(float) * 3 * (size_t)(n > m ? n : m);
+    static size_t ag[64];
+    if ((e = smem_optin(am_group_kernel, gsm + 20 * 1024, ag)) != cudaSuccess) return (int)e;  // static part counts
+    am_group_kernel<<<dim3(b, 2), AMG_THREADS, gsm, st>>>(n, m, xyz1, xyz2, ws.perm1, ws.perm2, temp, multiL, multiR);
+  } else {
+    PCC_LAUNCH(PDL_EMD_SMALL, am_init_kernel, dim3((n + m + 255) / 256, b), 256, 0, st, n, m, temp, multiL, multiR);
+  }
   constexpr int P = AM_P_DEFAULT;
   const int per_cta = AM_THREADS * P;
   const dim3 gk((n + per_cta - 1) / per_cta, b), gl((m + per_cta - 1) / per_cta, b);
@@ -615,15 +1056,29 @@ static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, f
   auto fL = [&](int t) { return ws.fL + (size_t)t * ws.fL_level_stride; };
   auto fR = [&](int t) { return ws.fR + (size_t)t * ws.fR_level_stride; };
   for (int t = 0; t < AM_LEVELS; ++t) {
-    if (t == 0) {
+    const bool cull_t = cull && t < AMC_LEVELS;
+    if (t == 0 && cull_t) {
+      am_sweep_cull_kernel<EPI_RATIO_L><<<gk, AM_THREADS, AMC_SMEM1, st>>>(n, m, xyz1, xyz2, remainR, tstride, lv.lv[0],
+                                                                           cut(0), ws.perm1, remainL, tstride, fL(0),
+                                                                           (size_t)n);
+    } else if (t == 0) {
       PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_RATIO_L, P>), gk, AM_THREADS, 0, st, n, m, xyz1, xyz2, remainR,
                  tstride, lv.lv[0], remainL, tstride, fL(0), (size_t)n);
+    } else if (cull_t) {
+      am_sweep31_cull_kernel<<<gk, AM_THREADS, AMC_SMEM31, st>>>(n, m, xyz1, xyz2, fR(t - 1), (size_t)m, remainR, tstride,
+                                                                 lv.lv[t - 1], lv.lv[t], cut(t), ws.perm1, remainL,
+                                                                 tstride, fL(t - 1), fL(t), (size_t)n);
     } else {
       PCC_LAUNCH(PDL_EMD_SWEEP, am_sweep31_kernel<P>, gk, AM_THREADS, 0, st, n, m, xyz1, xyz2, fR(t - 1), (size_t)m,
                  remainR, tstride, lv.lv[t - 1], lv.lv[t], remainL, tstride, fL(t - 1), fL(t), (size_t)n);
     }
-    PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_RATIO_R, P>), gl, AM_THREADS, 0, st, m, n, xyz2, xyz1, fL(t),
-               (size_t)n, lv.lv[t], remainR, tstride, fR(t), (size_t)m);
+    if (cull_t)
+      am_sweep_cull_kernel<EPI_RATIO_R><<<gl, AM_THREADS, AMC_SMEM1, st>>>(m, n, xyz2, xyz1, fL(t), (size_t)n, lv.lv[t],
+                                                                           cut(t), ws.perm2, remainR, tstride, fR(t),
+                                                                           (size_t)m);
+    else
+      PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_RATIO_R, P>), gl, AM_THREADS, 0, st, m, n, xyz2, xyz1, fL(t),
+                 (size_t)n, lv.lv[t], remainR, tstride, fR(t), (size_t)m);
   }
   PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_REMAIN_L, P>), gk, AM_THREADS, 0, st, n, m, xyz1, xyz2,
              fR(AM_LEVELS - 1), (size_t)m, lv.lv[AM_LEVELS - 1], remainL, tstride, fL(AM_LEVELS - 1), (size_t)n);

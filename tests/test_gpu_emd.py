@@ -107,6 +107,42 @@ def test_fused_is_deterministic(cuda):
     assert all(torch.equal(p, q) for p, q in zip(x, y))
 
 
+def _cull_cases():
+    a, c = synthetic.s1_near(3, 2048)
+    nan = a.clone()
+    nan[1, 17, 2] = float("nan")
+    nan[2, 5, 0] = float("inf")
+    return {
+        "s1": synthetic.s1_near(8, 2048), "s2": synthetic.s2_far(4, 2048, 2048), "s3_ties": synthetic.s3_ties(4, 2048),
+        "ragged": synthetic.s2_far(3, 1500, 700), "ragged_multi_tile": synthetic.s2_far(2, 100, 3000),
+        "two_tiles": synthetic.s1_near(2, 4096), "collapsed": (a * 1e-3, c), "scaled_x8": (a * 8, c * 8),
+        "nan_inf": (nan, c),
+    }
+
+
+@pytest.mark.parametrize("case", ["s1", "s2", "s3_ties", "ragged", "ragged_multi_tile", "two_tiles", "collapsed",
+                                  "scaled_x8", "nan_inf"])
+def test_culled_sweeps_bit_identical_to_full_sweeps(cuda, case, monkeypatch):
+    """Exact-zero culling (csrc/approxmatch.cu): the sweeps of the two steepest levels skip partners whose exponential
+    underflows to +0.  Nothing may change: every output bit equals the full sweeps' (PCC_AM_NOCULL=1 is read per call)."""
+    a, c = _cull_cases()[case]
+    a, c = a.to(cuda).contiguous(), c.to(cuda).contiguous()
+
+    def run():
+        out = list(MatchCostFused(a, c, True, True))
+        if a.shape[0] * a.shape[1] * c.shape[1] <= 4 * 2048 * 2048:
+            out += list(ApproxMatch(a, c))[:1]   # the materialised plan; `temp` is scratch
+        torch.cuda.synchronize()
+        return out
+
+    monkeypatch.setenv("PCC_AM_NOCULL", "1")
+    full = run()
+    monkeypatch.setenv("PCC_AM_NOCULL", "0")
+    culled = run()
+    for f, g in zip(full, culled):
+        assert torch.equal(f.view(torch.int32), g.view(torch.int32))
+
+
 @pytest.mark.parametrize("b,n,eps,iters", [(3, 1024, 0.005, 50), (2, 2048, 0.005, 50), (1, 1024, 0.002, 3000), (2, 1024, 0.01, 1),
                                            (2, 3072, 0.005, 30),   # exactly 48 KiB of dynamic shared memory + static words
                                            (1, 4096, 0.01, 20), (1, 5120, 0.005, 10)])
