@@ -97,7 +97,8 @@ int pcc_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2,
 /* Fused replacement for the ApproxMatch -> MatchCost -> MatchCostGrad chain behind
  * structural_losses.match_cost (structural_losses/match_cost.py:14-42): same cost and gradients, but the
  * (b,m,n) match matrix is never materialised (O(b(n+m)) memory).  grad1 / grad2 may be NULL.
- * temp: (b, 2(n+m)) floats of scratch, as for pcc_approxmatch. */
+ * temp: (b, 2(n+m)) floats of scratch; its contents are unspecified on return (the solver skips the last remainL
+ * update and the ratio export, which only pcc_approxmatch's temp receives). */
 int pcc_matchcost_fused(int b, int n, int m, const float *xyz1, const float *xyz2, float *cost, float *grad1,
                         float *grad2, float *temp, pcc_stream_t stream);
 

@@ -661,6 +661,7 @@ am_sweep31_cull_kernel(int nP, int nQ, const float *__restrict__ xP, const float
 // match(p,q) = sum_t E_t(p,q) * a_t[p] * b_t[q],  t = 0..8  <->  j = 7..-1,  E_t = exp2(c_t * d2)
 struct AmLevels {
   float lv[AM_LEVELS];  // -4^j as the device's powf returns it (am_levels_kernel)
+  float lc[AM_LEVELS];  // lv * log2e: (d2 * lv) * log2e == d2 * lc bit for bit, lv being a power of two (see am_sweep_kernel)
 };
 
 constexpr int AMF_QTILE = 256;                      // partner points per tile in the phase-B kernels
@@ -675,10 +676,9 @@ __device__ __forceinline__ f32x2 am_match_pair(f32x2 d2, const f32x2 *bq /*9*/, 
                                                const AmLevels &lv) {
   float lo, hi;
   f32x2 E[AM_LEVELS];
-  const f32x2 l2e2 = pack2(AM_LOG2E, AM_LOG2E);
 #pragma unroll
   for (int t = 0; t < AM_LEVELS; t += (EXACT ? 1 : 2)) {  // anchors j = 7, 5, 3, 1, -1 (t = 0, 2, 4, 6, 8)
-    const f32x2 a = mul2(mul2(d2, pack2(lv.lv[t], lv.lv[t])), l2e2);
+    const f32x2 a = mul2(d2, pack2(lv.lc[t], lv.lc[t]));
     unpack2(a, lo, hi);
     E[t] = pack2(ex2_ftz(lo), ex2_ftz(hi));
   }
@@ -1002,13 +1002,14 @@ static int am_levels(cudaStream_t st, AmLevels *out) {
       cudaGetLastError();
     }
   }
+  for (int t = 0; t < AM_LEVELS; ++t) cached.lc[t] = cached.lv[t] * AM_LOG2E;
   *out = cached;
   return 0;
 }
 
 // Phase A: runs the 27 sweeps; leaves remainL/remainR in temp and the per-level factors in ws.
 static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, float *temp, AmWorkspace &ws,
-                    size_t extra_floats, const AmLevels &lv, cudaStream_t st, int *launches) {
+                    size_t extra_floats, const AmLevels &lv, cudaStream_t st, int *launches, bool want_temp) {
   const size_t nfl = (size_t)AM_LEVELS * b * n, nfr = (size_t)AM_LEVELS * b * m;
   const bool cull = am_cull_enabled(n, m);
   const size_t perm_floats = cull ? ((size_t)b * (n + m) + 1) / 2 : 0;  // u16 entries
@@ -1080,12 +1081,18 @@ static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, f
       PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_RATIO_R, P>), gl, AM_THREADS, 0, st, m, n, xyz2, xyz1, fL(t),
                  (size_t)n, lv.lv[t], remainR, tstride, fR(t), (size_t)m);
   }
-  PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_REMAIN_L, P>), gk, AM_THREADS, 0, st, n, m, xyz1, xyz2,
-             fR(AM_LEVELS - 1), (size_t)m, lv.lv[AM_LEVELS - 1], remainL, tstride, fL(AM_LEVELS - 1), (size_t)n);
-  PCC_LAUNCH(PDL_EMD_SMALL, am_export_temp_kernel, dim3((n + m + 255) / 256, b), 256, 0, st, n, m,
-             ws.fL + (size_t)(AM_LEVELS - 1) * ws.fL_level_stride, ws.fR + (size_t)(AM_LEVELS - 1) * ws.fR_level_stride,
-             temp);
-  *launches += 2 + 2 * AM_LEVELS + 1;
+  // The last remainL update (sweep 3 of level j = -1, approxmatch.cu:130-163) and the export of the last level's ratio
+  // vectors only fill `temp`: match / cost / gradients are functions of the per-level ratio vectors alone.  The
+  // fused path treats temp as scratch (its Python caller drops it, match_cost.py:25), so it skips both.
+  if (want_temp) {
+    PCC_LAUNCH(PDL_EMD_SWEEP, PCC_K(am_sweep_kernel<EPI_REMAIN_L, P>), gk, AM_THREADS, 0, st, n, m, xyz1, xyz2,
+               fR(AM_LEVELS - 1), (size_t)m, lv.lv[AM_LEVELS - 1], remainL, tstride, fL(AM_LEVELS - 1), (size_t)n);
+    PCC_LAUNCH(PDL_EMD_SMALL, am_export_temp_kernel, dim3((n + m + 255) / 256, b), 256, 0, st, n, m,
+               ws.fL + (size_t)(AM_LEVELS - 1) * ws.fL_level_stride,
+               ws.fR + (size_t)(AM_LEVELS - 1) * ws.fR_level_stride, temp);
+    *launches += 2;
+  }
+  *launches += 2 * AM_LEVELS + 1;
   return (int)cudaGetLastError();
 }
 
@@ -1103,7 +1110,7 @@ extern "C" __attribute__((visibility("default"))) int pcc_approxmatch(int b, int
   AmLevels lv;
   am_levels(st, &lv);
   int launches = 0;
-  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, 0, lv, st, &launches);
+  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, 0, lv, st, &launches, true);
   if (rc == 0) {
     const int lslab = 256;
     dim3 grid((n + AM_THREADS - 1) / AM_THREADS, (m + lslab - 1) / lslab, b);
@@ -1134,7 +1141,7 @@ extern "C" __attribute__((visibility("default"))) int pcc_matchcost_fused(int b,
   am_levels(st, &sc);
   int launches = 0;
   const int parts = (n + AM_THREADS - 1) / AM_THREADS;
-  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, (size_t)b * parts, sc, st, &launches);
+  int rc = am_solve(b, n, m, xyz1, xyz2, temp, ws, (size_t)b * parts, sc, st, &launches, false);
   if (rc == 0) {
     PCC_LAUNCH(PDL_EMD_SWEEP, am_costgrad_kernel, dim3(parts, b), AM_THREADS, 0, st, n, m, xyz1, xyz2, ws.fL, ws.fR,
                ws.fL_level_stride, ws.fR_level_stride, sc, cost ? ws.cost_part : nullptr, grad1);
