@@ -266,7 +266,7 @@ am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__r
 // collapsed and NaN clouds).  S1 clouds, blocks of 64: 12 % / 26 % / 56 % of the partners survive at j = 7 / 6 / 5.
 constexpr int AMG_THREADS = 1024;
 constexpr int AMC_MAXPTS = 4096;    // clouds up to this size take the culled sweeps (u16 permutation, sort in smem)
-constexpr int AMC_LEVELS = 2;       // levels t = 0, 1 (j = 7, 6) are culled; at j = 5 the lists are 56 % full and do not pay
+constexpr int AMC_LEVELS = 3;       // levels t = 0, 1, 2 (j = 7, 6, 5) are culled (j = 5: break-even on S1, a gain on spread clouds)
 constexpr float AMC_CUT = 130.f;    // cull when boxdist2 * |level * log2e| > AMC_CUT
 constexpr int AMC_PAD = 16;         // list padding granularity (>= both unroll widths) and spare tile entries
 
@@ -392,6 +392,17 @@ am_group_kernel(int n, int m, const float *__restrict__ xyz1, const float *__res
   for (int i = threadIdx.x; i < cnt; i += AMG_THREADS) perm[i] = ord[cur][i];
 }
 
+// Which block of 64 grouped points warp w of CTA blockIdx.x takes.  Consecutive blocks are spatial neighbours (same
+// partner density, same list length), and all CTAs of a culled sweep are resident at once, so a CTA of four neighbours
+// would leave the dense regions' SMs running long after the sparse ones: instead the four warps of CTA bx take one
+// block from each quarter of the order (q * gridDim.x + bx), rotated so that the CTA sharing the SM with this one
+// (148 CTAs later: bx + 4 in a grid of 8 per cloud) puts the complementary quarter on every sub-partition.
+__device__ __forceinline__ int am_cull_block(int warp) {
+  const int bx = blockIdx.x;
+  const int q = (warp + bx + 2 * (bx >> 2)) & 3;
+  return q * gridDim.x + bx;
+}
+
 struct AmBox {
   float lx, hx, ly, hy, lz, hz;
   bool ok;  // every own coordinate finite: the cull may be applied
@@ -483,8 +494,8 @@ am_sweep_cull_kernel(int nP, int nQ, const float *__restrict__ xP, const float *
   permP += cloud * (size_t)nP;
   float *rem = remainP + cloud * remain_stride;
   float *rat = ratioP + cloud * ratio_stride;
-  // warp w of block bx owns the permuted slots g0 + lane and g0 + 32 + lane
-  const int g0 = blockIdx.x * (AM_THREADS * 2) + warp * 64;
+  // warp w of block bx owns block am_cull_block(w) of 64 permuted slots: g0 + lane and g0 + 32 + lane
+  const int g0 = am_cull_block(warp) * 64;
   const int sa = g0 + lane, sb = g0 + 32 + lane;
   const int a = permP[min(sa, nP - 1)], b = permP[min(sb, nP - 1)];
   const float ax = xP[a * 3], ay = xP[a * 3 + 1], az = xP[a * 3 + 2];
@@ -515,7 +526,7 @@ am_sweep_cull_kernel(int nP, int nQ, const float *__restrict__ xP, const float *
       tile[i] = v;
     }
     const bool cull = __syncthreads_and(wfin) && box.ok;
-    const int len = am_build_list(tile, cnt, box, cut, cull, list, lane);
+    const int len = g0 < nP ? am_build_list(tile, cnt, box, cut, cull, list, lane) : 0;  // warp-uniform
     const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
 #pragma unroll 1
     for (int l = 0; l < len; l += U) {
@@ -586,7 +597,7 @@ am_sweep31_cull_kernel(int nP, int nQ, const float *__restrict__ xP, const float
   float *rem = remainL + cloud * remainL_stride;
   const float *ratA = ratioL_A + cloud * ratioL_stride;
   float *ratB = ratioL_B + cloud * ratioL_stride;
-  const int g0 = blockIdx.x * (AM_THREADS * 2) + warp * 64;
+  const int g0 = am_cull_block(warp) * 64;
   const int sa = g0 + lane, sb = g0 + 32 + lane;
   const int a = permP[min(sa, nP - 1)], b = permP[min(sb, nP - 1)];
   const float ax = xP[a * 3], ay = xP[a * 3 + 1], az = xP[a * 3 + 2];
@@ -618,7 +629,7 @@ am_sweep31_cull_kernel(int nP, int nQ, const float *__restrict__ xP, const float
       wB[i] = w1;
     }
     const bool cull = __syncthreads_and(wfin) && box.ok;
-    const int len = am_build_list(tile, cnt, box, cut, cull, list, lane);
+    const int len = g0 < nP ? am_build_list(tile, cnt, box, cut, cull, list, lane) : 0;  // warp-uniform
     const unsigned char *tb = reinterpret_cast<const unsigned char *>(tile);
     const unsigned char *wb = reinterpret_cast<const unsigned char *>(wB);
 #pragma unroll 1
@@ -976,6 +987,12 @@ static bool am_cull_enabled(int n, int m) {
   const char *e = getenv("PCC_AM_NOCULL");
   return !(e && e[0] && e[0] != '0');
 }
+// number of culled levels (tuning knob for tools/emd_cull_probe.py; any value gives the same bits)
+static int am_cull_levels() {
+  const char *e = getenv("PCC_AM_CULL_LEVELS");
+  const int v = e && e[0] ? atoi(e) : AMC_LEVELS;
+  return v < 0 ? 0 : (v > AM_LEVELS ? AM_LEVELS : v);
+}
 
 
 // -4^j for j = 7..-1, evaluated ONCE per process by the device's own powf (the reference calls powf in the kernel,
@@ -1056,8 +1073,9 @@ static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, f
   // sweep 1 of level t share one fused launch.
   auto fL = [&](int t) { return ws.fL + (size_t)t * ws.fL_level_stride; };
   auto fR = [&](int t) { return ws.fR + (size_t)t * ws.fR_level_stride; };
+  const int ncull = am_cull_levels();
   for (int t = 0; t < AM_LEVELS; ++t) {
-    const bool cull_t = cull && t < AMC_LEVELS;
+    const bool cull_t = cull && t < ncull;
     if (t == 0 && cull_t) {
       am_sweep_cull_kernel<EPI_RATIO_L><<<gk, AM_THREADS, AMC_SMEM1, st>>>(n, m, xyz1, xyz2, remainR, tstride, lv.lv[0],
                                                                            cut(0), ws.perm1, remainL, tstride, fL(0),

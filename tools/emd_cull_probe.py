@@ -81,4 +81,8 @@ for name, gen in (("s1", lambda: synthetic.s1_near(32, 2048)), ("s2", lambda: sy
     t_full = timed(a, c, False)
     t_cull = timed(a, c, True)
     print(f"{name} B=32x2048 matchcost_fused fwd+bwd: full {t_full:.1f} us, culled {t_cull:.1f} us")
+    for lv in (1, 3, 4):
+        os.environ["PCC_AM_CULL_LEVELS"] = str(lv)
+        print(f"   culled levels = {lv}: {timed(a, c, True):.1f} us")
+    del os.environ["PCC_AM_CULL_LEVELS"]
 os.environ["PCC_AM_NOCULL"] = "0"
