@@ -264,18 +264,18 @@ am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__r
 //                        the cull off for that warp / partner (NaN must keep propagating as in the full sweep).
 // Results are bit-identical to the full sweeps (tests/test_gpu_emd.py: culled == PCC_AM_NOCULL=1 on S1/S2/S3,
 // collapsed and NaN clouds).  S1 clouds, blocks of 64: 12 % / 26 % / 56 % of the partners survive at j = 7 / 6 / 5.
-constexpr int AMG_THREADS = 1024;
+constexpr int AMG_THREADS = 256;
 constexpr int AMC_MAXPTS = 4096;    // clouds up to this size take the culled sweeps (u16 permutation, sort in smem)
+constexpr int AMG_PPT = AMC_MAXPTS / AMG_THREADS;  // points per thread of the grouping kernel (keys in registers)
 constexpr int AMC_LEVELS = 3;       // levels t = 0, 1, 2 (j = 7, 6, 5) are culled (j = 5: break-even on S1, a gain on spread clouds)
 constexpr float AMC_CUT = 130.f;    // cull when boxdist2 * |level * log2e| > AMC_CUT
 constexpr int AMC_PAD = 16;         // list padding granularity (>= both unroll widths) and spare tile entries
 
-// exclusive scan of cnt[0 .. nb) in place (nb <= AMG_THREADS * per), one contiguous chunk per thread
+// exclusive scan of cnt[0 .. nb) in place, nb <= 2 * AMG_THREADS: two adjacent bins per thread
 __device__ __forceinline__ void amg_scan(int *cnt, int nb, int *warp_tot) {
-  const int per = (nb + AMG_THREADS - 1) / AMG_THREADS;
-  const int b0 = min((int)threadIdx.x * per, nb), b1 = min(b0 + per, nb);
-  int local = 0;
-  for (int i = b0; i < b1; ++i) local += cnt[i];
+  const int b0 = 2 * threadIdx.x;
+  const int c0 = b0 < nb ? cnt[b0] : 0, c1 = b0 + 1 < nb ? cnt[b0 + 1] : 0;
+  const int local = c0 + c1;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int inc = local;
 #pragma unroll
@@ -285,31 +285,20 @@ __device__ __forceinline__ void amg_scan(int *cnt, int nb, int *warp_tot) {
   }
   if (lane == 31) warp_tot[w] = inc;
   __syncthreads();
-  if (w == 0) {
-    const int t = lane < AMG_THREADS / 32 ? warp_tot[lane] : 0;
-    int sc = t;
+  int off = inc - local;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, sc, o);
-      if (lane >= o) sc += u;
-    }
-    if (lane < AMG_THREADS / 32) warp_tot[lane] = sc - t;
-  }
-  __syncthreads();
-  int off = warp_tot[w] + inc - local;
-  for (int i = b0; i < b1; ++i) {
-    const int d = cnt[i];
-    cnt[i] = off;
-    off += d;
-  }
+  for (int u = 0; u < AMG_THREADS / 32; ++u) off += u < w ? warp_tot[u] : 0;
+  if (b0 < nb) cnt[b0] = off;
+  if (b0 + 1 < nb) cnt[b0 + 1] = off + c0;
   __syncthreads();
 }
 
 // Three counting sorts: by x over the whole cloud (256 bins), by y inside every quarter of that order (64 bins each), by z
-// inside every sixteenth (32 bins each) -- median splits by RANK, so the blocks stay balanced whatever the density.  The order inside
-// a bin (shared-memory atomics) is arbitrary: nothing downstream depends on which thread owns which point.
-// The cloud is staged in shared memory once (every pass gathers coordinates through the current order).  Also
-// initialises this side's remain vector (am_init_kernel's job, approxmatch.cu:19-21) so the solve starts one launch earlier.
+// inside every sixteenth (32 bins each) -- median splits by RANK, so the blocks stay balanced whatever the density.  The
+// order inside a bin (shared-memory atomics) is arbitrary: nothing downstream depends on which thread owns which point.
+// The cloud is staged in shared memory once (every pass gathers coordinates through the current order); a thread keeps
+// the keys of its positions in registers between the histogram and the scatter.  With `temp` it also initialises this
+// side's remain vector (am_init_kernel's job, approxmatch.cu:19-21) so the solve starts one launch earlier.
 __global__ void __launch_bounds__(AMG_THREADS)
 am_group_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                 unsigned short *__restrict__ perm1, unsigned short *__restrict__ perm2, float *__restrict__ temp,
@@ -319,34 +308,31 @@ am_group_kernel(int n, int m, const float *__restrict__ xyz1, const float *__res
   __shared__ int hist[16 * 32];
   __shared__ int warp_tot[AMG_THREADS / 32];
   __shared__ float red[6][AMG_THREADS / 32];
-  __shared__ float ext[6];
   const size_t cloud = blockIdx.x;
   const int side = blockIdx.y;
   const int cnt = side ? m : n;
   const float *__restrict__ x = (side ? xyz2 : xyz1) + cloud * (size_t)cnt * 3;
   unsigned short *__restrict__ perm = (side ? perm2 : perm1) + cloud * (size_t)cnt;
   const float INF = __int_as_float(0x7f800000);
-  {  // temp per cloud: [remainL(n) | remainR(m) | ratioL(n) | ratioR(m)]
+  if (temp) {  // temp per cloud: [remainL(n) | remainR(m) | ratioL(n) | ratioR(m)]
     float *t = temp + cloud * (size_t)(n + m) * 2 + (side ? n : 0);
     const float v = side ? multiR : multiL;
     for (int i = threadIdx.x; i < cnt; i += AMG_THREADS) t[i] = v;
   }
   // stage the coordinates; extents per axis (non-finite coordinates are ignored; they land in bin 0)
   float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
-  for (int i = threadIdx.x; i < cnt * 3; i += AMG_THREADS) {
-    const float v = x[i];
-    gx[i] = v;
-    const int ax = i % 3;
-    if (fabsf(v) <= 3.0e38f) {
+  for (int i = threadIdx.x; i < cnt; i += AMG_THREADS) {
+    ord[0][i] = (unsigned short)i;
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
-        if (a == ax) {
-          lo[a] = fminf(lo[a], v);
-          hi[a] = fmaxf(hi[a], v);
-        }
+    for (int a = 0; a < 3; ++a) {
+      const float v = x[i * 3 + a];
+      gx[i * 3 + a] = v;
+      if (fabsf(v) <= 3.0e38f) {
+        lo[a] = fminf(lo[a], v);
+        hi[a] = fmaxf(hi[a], v);
+      }
     }
   }
-  for (int i = threadIdx.x; i < cnt; i += AMG_THREADS) ord[0][i] = (unsigned short)i;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -360,11 +346,6 @@ am_group_kernel(int n, int m, const float *__restrict__ xyz1, const float *__res
     }
   }
   __syncthreads();
-  if (threadIdx.x < 6) {
-    float v = red[threadIdx.x][0];
-    for (int w = 1; w < AMG_THREADS / 32; ++w) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
-    ext[threadIdx.x] = v;
-  }
   int cur = 0;
   for (int axis = 0; axis < 3; ++axis) {
     const int nseg = axis == 0 ? 1 : (axis == 1 ? 4 : 16);
@@ -372,24 +353,50 @@ am_group_kernel(int n, int m, const float *__restrict__ xyz1, const float *__res
     const int seg_len = (cnt + nseg - 1) / nseg;
     const float inv_len = 1.f / (float)seg_len;  // (pos + 0.5) / seg_len is never within 1e-4 of an integer: exact floor
     for (int i = threadIdx.x; i < nseg * nbin; i += AMG_THREADS) hist[i] = 0;
-    __syncthreads();
-    const float l = ext[axis], h = ext[3 + axis];
+    float l = red[axis][0], h = red[3 + axis][0];
+#pragma unroll
+    for (int w = 1; w < AMG_THREADS / 32; ++w) {
+      l = fminf(l, red[axis][w]);
+      h = fmaxf(h, red[3 + axis][w]);
+    }
     const float scale = (h > l) ? (float)nbin / (h - l) : 0.f;
-    auto key_of = [&](int pos) {
-      const float v = gx[ord[cur][pos] * 3 + axis];
-      int bin = (fabsf(v) <= 3.0e38f) ? (int)((v - l) * scale) : 0;
-      bin = min(max(bin, 0), nbin - 1);
-      return (int)(((float)pos + 0.5f) * inv_len) * nbin + bin;
-    };
-    for (int pos = threadIdx.x; pos < cnt; pos += AMG_THREADS) atomicAdd(&hist[key_of(pos)], 1);
+    __syncthreads();
+    int key[AMG_PPT];
+#pragma unroll
+    for (int u = 0; u < AMG_PPT; ++u) {
+      const int pos = threadIdx.x + u * AMG_THREADS;
+      key[u] = -1;
+      if (pos < cnt) {
+        const float v = gx[ord[cur][pos] * 3 + axis];
+        int bin = (fabsf(v) <= 3.0e38f) ? (int)((v - l) * scale) : 0;
+        bin = min(max(bin, 0), nbin - 1);
+        key[u] = (int)(((float)pos + 0.5f) * inv_len) * nbin + bin;
+        atomicAdd(&hist[key[u]], 1);
+      }
+    }
     __syncthreads();
     amg_scan(hist, nseg * nbin, warp_tot);
-    for (int pos = threadIdx.x; pos < cnt; pos += AMG_THREADS)
-      ord[cur ^ 1][atomicAdd(&hist[key_of(pos)], 1)] = ord[cur][pos];
+#pragma unroll
+    for (int u = 0; u < AMG_PPT; ++u) {
+      const int pos = threadIdx.x + u * AMG_THREADS;
+      if (key[u] >= 0) ord[cur ^ 1][atomicAdd(&hist[key[u]], 1)] = ord[cur][pos];
+    }
     __syncthreads();
     cur ^= 1;
   }
   for (int i = threadIdx.x; i < cnt; i += AMG_THREADS) perm[i] = ord[cur][i];
+}
+
+// shared with the Chamfer forward (chamfer.cu): both clouds of every pair grouped in one launch
+int am_group_launch(int b, int n, int m, const float *xyz1, const float *xyz2, unsigned short *perm1,
+                    unsigned short *perm2, float *temp, float multiL, float multiR, cudaStream_t st) {
+  if (n > AMC_MAXPTS || m > AMC_MAXPTS) return PCC_ENOTSUP;
+  const size_t gsm = sizeof(float) * 3 * (size_t)(n > m ? n : m);
+  static size_t ag[64];
+  // the 48 KiB default limit counts the kernel's ~18 KiB of static shared memory too: opt in from 28 KiB of dynamic
+  if (cudaError_t e = smem_optin(am_group_kernel, gsm + 20 * 1024, ag, 48 * 1024); e != cudaSuccess) return (int)e;
+  am_group_kernel<<<dim3(b, 2), AMG_THREADS, gsm, st>>>(n, m, xyz1, xyz2, perm1, perm2, temp, multiL, multiR);
+  return (int)cudaGetLastError();
 }
 
 // Which block of 64 grouped points warp w of CTA blockIdx.x takes.  Consecutive blocks are spatial neighbours (same
@@ -1059,10 +1066,7 @@ static int am_solve(int b, int n, int m, const float *xyz1, const float *xyz2, f
   const size_t tstride = (size_t)(n + m) * 2;
   float *remainL = temp, *remainR = temp + n;
   if (cull) {  // the grouping kernel also initialises remainL / remainR
-    const size_t gsm = sizeof(float) * 3 * (size_t)(n > m ? n : m);
-    static size_t ag[64];
-    if ((e = smem_optin(am_group_kernel, gsm + 20 * 1024, ag)) != cudaSuccess) return (int)e;  // static part counts
-    am_group_kernel<<<dim3(b, 2), AMG_THREADS, gsm, st>>>(n, m, xyz1, xyz2, ws.perm1, ws.perm2, temp, multiL, multiR);
+    if (int rc = am_group_launch(b, n, m, xyz1, xyz2, ws.perm1, ws.perm2, temp, multiL, multiR, st); rc != 0) return rc;
   } else {
     PCC_LAUNCH(PDL_EMD_SMALL, am_init_kernel, dim3((n + m + 255) / 256, b), 256, 0, st, n, m, temp, multiL, multiR);
   }

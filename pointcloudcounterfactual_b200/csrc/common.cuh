@@ -43,6 +43,12 @@ inline void note_route(Route r) { g_routes[r].fetch_add(1, std::memory_order_rel
 // device's default pool that other libraries and captured graphs allocate from.  Release with cudaFreeAsync.
 cudaError_t ws_alloc(void **ptr, size_t bytes, cudaStream_t st);
 
+// Spatial grouping of both clouds of every pair (approxmatch.cu: am_group_kernel; declared here for other translation units): perm1 (b,n) / perm2 (b,m) list each
+// cloud's points so that consecutive blocks of 64 are spatially tight.  n, m <= 4096 (PCC_ENOTSUP beyond).  temp may
+// be null (otherwise the approxmatch remain vectors are initialised on the way).
+int am_group_launch(int b, int n, int m, const float *xyz1, const float *xyz2, unsigned short *perm1,
+                    unsigned short *perm2, float *temp, float multiL, float multiR, cudaStream_t st);
+
 // Opt-in to more than 48 KiB of dynamic shared memory.  The attribute is PER DEVICE: one process may drive several GPUs
 // (the Python wrappers take tensors on any device), so the high-water mark is kept per device ordinal.
 // The 48 KiB limit without opt-in counts STATIC shared memory too, so the opt-in starts well below it (at exactly 48 KiB of
