@@ -183,7 +183,10 @@ struct NnPart {
   int loc;
 };
 
-__global__ void __launch_bounds__(NS_THREADS, 4)
+#ifndef PCC_NS_MINB
+#define PCC_NS_MINB 4
+#endif
+__global__ void __launch_bounds__(NS_THREADS, PCC_NS_MINB)
 nn_sym_kernel(int n, const float *__restrict__ xyz1, int m, const float *__restrict__ xyz2, int nrb, int ncc,
               NnPart *__restrict__ rowpart, NnPart *__restrict__ colpart) {
   pdl_enter();
