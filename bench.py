@@ -392,7 +392,13 @@ def run_b200(args) -> None:
                                   "roofline": {"bound": "fp32", "unit": "TFLOP/s", "achieved": flops / (ms * 1e-3) / 1e12,
                                                "peak": fp32_peak, "frac": flops / (ms * 1e-3) / 1e12 / fp32_peak}}
         ms, gr = graph_or_eager(emd_fb, reps=10)
-        sub["emd_fwd_bwd"] = {"ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr}
+        sub["emd_fwd_bwd"] = {
+            "ms": ms, "clouds_per_s": world * B_PER_GPU / (ms * 1e-3), "cuda_graph": gr,
+            # the reference's solver evaluates 27 sweeps x B*n*m exponentials; here 26 run (the last one only fills the
+            # scratch vector) and 8 of them skip the partners whose exponential is exactly zero
+            "algorithmic_gexp_per_s": 27 * pairs / (ms * 1e-3) / 1e9,
+            "note": "27*B*n*m exp-pair evaluations of the reference's solver / this time (cost+gradient kernel included in "
+                    "the time, its 6 special-function ops per pair not counted); MUFU.EX2 peak in roofline.peak"}
         tf32_peak = peaks["bf16_tflops"] / 2.0  # dense TF32 = half the bf16 tensor rate (nominal 1.1 vs 2.25 PFLOP/s)
         for name, x, k, c in (("knn_xyz_k20_n1024", x3, KNN_K, 3), ("knn_feat64_k20_n1024", xf, KNN_K, KNN_C),
                               ("knn_xyz_k25_n2048", x25, 25, 3), ("knn_xyz_k4_n2048", x25, 4, 3)):
