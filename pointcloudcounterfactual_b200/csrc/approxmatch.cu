@@ -9,7 +9,8 @@
 //            with a per-sweep epilogue (ratioL / ratioR+remainR / remainL update).  All clouds and all row blocks
 //            run in parallel over the 148 SMs (the reference runs one 512-thread CTA per cloud), two partner
 //            points per step with packed FADD2/FMUL2/FFMA2 and one MUFU.EX2 each.  The per-level scaling vectors
-//            ratioL_j, ratioR_j (9 x (n+m) floats per cloud) are kept.
+//            ratioL_j, ratioR_j (9 x (n+m) floats per cloud) are kept.  The sweeps of the three steepest levels skip
+//            the partners whose exponential is exactly +0 ("exact-zero culling" below: same bits, fewer pairs).
 //   phase B  "apply": match[l][k] = sum_j E_j(k,l) ratioL_j[k] ratioR_j[l] is evaluated ONCE per pair
 //            (5 exponentials per pair: levels j+1 are obtained from level j by two squarings) and either written
 //            to the (b,m,n) matrix (pcc_approxmatch; one 0.5 GiB write instead of nine read-modify-writes) or
@@ -260,8 +261,9 @@ am_sweep31_kernel(int nP, int nQ, const float *__restrict__ xP, const float *__r
 //                        is a lower bound of the computed d2 up to rounding) and appends the survivors' tile slots to
 //                        its own list -- in ascending partner index, i.e. the reference's summation order -- then runs
 //                        the unchanged inner loop over the list.  Lists are padded to the unroll width with a
-//                        zero-weight dummy partner (fma(E, 0, acc) == acc).  Non-finite own points or weights switch
-//                        the cull off for that warp / partner (NaN must keep propagating as in the full sweep).
+//                        zero-weight dummy partner (fma(E, 0, acc) == acc).  Non-finite own points / own factors switch
+//                        the cull off for the warp, a non-finite weight in the staged tile for the whole tile (0 * inf
+//                        and NaN must keep propagating exactly as in the full sweep).
 // Results are bit-identical to the full sweeps (tests/test_gpu_emd.py: culled == PCC_AM_NOCULL=1 on S1/S2/S3,
 // collapsed and NaN clouds).  S1 clouds, blocks of 64: 12 % / 26 % / 56 % of the partners survive at j = 7 / 6 / 5.
 constexpr int AMG_THREADS = 256;
