@@ -348,8 +348,11 @@ __device__ __forceinline__ void team_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+#ifndef PCC_KW_MINB
+#define PCC_KW_MINB 3
+#endif
 template <int S>
-__global__ void __launch_bounds__(KW_THREADS, 3)
+__global__ void __launch_bounds__(KW_THREADS, PCC_KW_MINB)
 knn3w_kernel(int n, int k, int qper, int ps, int cs, const float *__restrict__ x, int64_t *__restrict__ idx_out,
              float *__restrict__ dist_out, int *__restrict__ hard) {
   constexpr int T = KW_THREADS / 32 / S;  // teams per CTA
