@@ -336,8 +336,8 @@ knn3_kernel(int n, int k, int groups8, int ps, int cs, const float *__restrict__
 //      compacts the ~1.5 k candidates of the team into shared memory;
 //   4  each candidate's (distance bits, index) key is ranked by counting smaller keys; rank r < k is output slot r.
 // No thread ever loops over the references: a query costs ~400 warp instructions instead of ~10^4 thread
-// instructions.  Clouds whose candidate count exceeds KW_CAP (massive exact ties) are flagged in `hard` and redone by
-// knn3_kernel, which prunes in place.
+// instructions.  A query whose candidate count exceeds KW_CAP (massive exact ties) is answered in place by
+// knn3w_overflow: no flag array to clear and no repair launch behind the kernel.
 constexpr int KW_THREADS = 128;
 constexpr int KW_CAP = 128;  // candidate slots per team
 
@@ -348,13 +348,77 @@ __device__ __forceinline__ void team_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// A query with more than KW_CAP candidates (massive exact ties): selection by k rounds of "next smallest key" over the
+// team's references, key = (distance bits, index) -- d >= 0, so the bit patterns order like the values; NaN and padding
+// never qualify.  A round is a lane-local scan of 32 distances (recomputed from the staged cloud with the arithmetic of
+// the key pass: the same bits), two warp reductions and, for S > 1, a merge through shared memory: ~350 warp
+// instructions per round, slower than the ranked path but without a flag array to clear and a repair launch behind the
+// kernel (3 us of the 44 us at B=32, N=1024).  Not inlined: its registers must not weigh on the fast path.
+template <int S>
+__device__ __noinline__ void knn3w_overflow(const float *xs, const float *ys, const float *zs, int n, int k, int slice,
+                                            int lane, int team, float qx, float qy, float qz, int64_t *o, float *od,
+                                            int *tot_team, unsigned int *lmin_team) {
+  const float INF = __int_as_float(0x7f800000);
+  const int tl = slice * 32 + lane;
+  unsigned int last_d = 0u, last_j = 0u;
+  bool have_last = false;
+  for (int i = 0; i < k; ++i) {  // team-uniform trip count
+    unsigned int bd = 0xffffffffu, bj = 0xffffffffu;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const int j = slice * 1024 + r * 32 + lane;
+      const float dx = xs[j] - qx, dy = ys[j] - qy, dz = zs[j] - qz;
+      const unsigned int db = __float_as_uint(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+      const unsigned int uj = (unsigned int)j;
+      const bool ok = j < n && db <= 0x7f800000u &&                                      // a real, non-NaN distance
+                      (!have_last || db > last_d || (db == last_d && uj > last_j)) &&   // beyond the previous winner
+                      (db < bd || (db == bd && uj < bj));                               // below the best so far
+      bd = ok ? db : bd;
+      bj = ok ? uj : bj;
+    }
+    unsigned int md = __reduce_min_sync(0xffffffffu, bd);
+    unsigned int mj = __reduce_min_sync(0xffffffffu, bd == md ? bj : 0xffffffffu);
+    if (S > 1) {
+      team_sync(1 + team, S * 32);  // previous readers of tot / lmin are done
+      if (lane == 0) {
+        tot_team[slice] = (int)md;
+        lmin_team[slice] = mj;
+      }
+      team_sync(1 + team, S * 32);
+#pragma unroll
+      for (int s2 = 0; s2 < S; ++s2) {
+        const unsigned int od2 = (unsigned int)tot_team[s2], oj2 = lmin_team[s2];
+        if (od2 < md || (od2 == md && oj2 < mj)) {
+          md = od2;
+          mj = oj2;
+        }
+      }
+    }
+    const bool found = md <= 0x7f800000u;
+    if (tl == 0) {
+      o[i] = found ? (int64_t)mj : 0;  // fewer than k real distances only with NaN / inf inputs
+      if (od) od[i] = found ? __uint_as_float(md) : INF;
+    }
+    last_d = md;
+    last_j = mj;
+    have_last = true;
+    if (!found) {  // team-uniform: nothing left, the remaining slots get the same filler
+      for (int t = i + 1 + tl; t < k; t += S * 32) {
+        o[t] = 0;
+        if (od) od[t] = INF;
+      }
+      break;
+    }
+  }
+}
+
 #ifndef PCC_KW_MINB
 #define PCC_KW_MINB 3
 #endif
 template <int S>
 __global__ void __launch_bounds__(KW_THREADS, PCC_KW_MINB)
 knn3w_kernel(int n, int k, int qper, int ps, int cs, const float *__restrict__ x, int64_t *__restrict__ idx_out,
-             float *__restrict__ dist_out, int *__restrict__ hard) {
+             float *__restrict__ dist_out) {
   constexpr int T = KW_THREADS / 32 / S;  // teams per CTA
   constexpr int NP = 1024 * S;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -467,8 +531,9 @@ knn3w_kernel(int n, int k, int qper, int ps, int cs, const float *__restrict__ x
         total += t;
       }
     }
-    if (total > KW_CAP) {  // team-uniform
-      if (tl == 0) hard[cloud] = 1;
+    if (total > KW_CAP) {  // team-uniform, rare (massive exact ties): answered in place, see knn3w_overflow
+      knn3w_overflow<S>(xs, ys, zs, n, k, slice, lane, team, qx, qy, qz, idx_out + (cloud * (size_t)n + q) * k,
+                        dist_out ? dist_out + (cloud * (size_t)n + q) * k : nullptr, tot[team], lmin[team]);
       team_sync(1 + team, S * 32);
       continue;
     }
@@ -558,13 +623,13 @@ knn3w_kernel(int n, int k, int qper, int ps, int cs, const float *__restrict__ x
 }
 
 template <int S>
-static int launch_knn3w_s(int b, int n, int k, int parts, bool pm, const float *x, int64_t *idx, float *dist, int *hard,
+static int launch_knn3w_s(int b, int n, int k, int parts, bool pm, const float *x, int64_t *idx, float *dist,
                           cudaStream_t st) {
   const size_t smem = sizeof(float) * 3 * 1024 * S;
   static size_t attr[64];  // static + dynamic shared memory exceeds the 48 KiB default at S = 4: opt in at any size
   if (cudaError_t e = smem_optin(knn3w_kernel<S>, smem, attr, 0); e != cudaSuccess) return (int)e;
   const int qper = (n + parts - 1) / parts;
-  knn3w_kernel<S><<<dim3((n + qper - 1) / qper, b), KW_THREADS, smem, st>>>(n, k, qper, pm ? 3 : 1, pm ? 1 : n, x, idx, dist, hard);
+  knn3w_kernel<S><<<dim3((n + qper - 1) / qper, b), KW_THREADS, smem, st>>>(n, k, qper, pm ? 3 : 1, pm ? 1 : n, x, idx, dist);
   return (int)cudaGetLastError();
 }
 
@@ -628,19 +693,11 @@ static int launch_knn3(int b, int n, int k, bool pm, const float *x, int64_t *id
     return launch_knn3_thread(b, n, k, pm, x, idx, dist, nullptr, st);
   }
   note_route(R_KNN3W);
-  int *hard = nullptr;
-  cudaError_t e = ws_alloc((void **)&hard, sizeof(int) * b, st);
-  if (e != cudaSuccess) return (int)e;
-  cudaMemsetAsync(hard, 0, sizeof(int) * b, st);
   int rc;
-  if (n <= 1024) rc = launch_knn3w_s<1>(b, n, k, knn3w_parts(b, n, 4), pm, x, idx, dist, hard, st);
-  else if (n <= 2048) rc = launch_knn3w_s<2>(b, n, k, knn3w_parts(b, n, 2), pm, x, idx, dist, hard, st);
-  else rc = launch_knn3w_s<4>(b, n, k, knn3w_parts(b, n, 1), pm, x, idx, dist, hard, st);
-  if (rc == 0) {
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    rc = launch_knn3_thread(b, n, k, pm, x, idx, dist, hard, st);  // exits at once unless a cloud overflowed KW_CAP
-  }
-  cudaFreeAsync(hard, st);
+  if (n <= 1024) rc = launch_knn3w_s<1>(b, n, k, knn3w_parts(b, n, 4), pm, x, idx, dist, st);
+  else if (n <= 2048) rc = launch_knn3w_s<2>(b, n, k, knn3w_parts(b, n, 2), pm, x, idx, dist, st);
+  else rc = launch_knn3w_s<4>(b, n, k, knn3w_parts(b, n, 1), pm, x, idx, dist, st);
+  if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   return rc;
 }
 

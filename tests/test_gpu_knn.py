@@ -126,6 +126,26 @@ def test_knn_ties_lowest_index(cuda):
     assert np.array_equal(neighbour_ops.knn(x.to(cuda), 25).cpu().numpy(), oracle.knn(x.numpy(), 25))
 
 
+@pytest.mark.parametrize("n,k", [(1024, 20), (1000, 32), (2048, 25), (1500, 4), (3000, 20), (4096, 8)])
+def test_xyz_knn_candidate_overflow_answered_in_kernel(cuda, monkeypatch, n, k):
+    """More exact ties than the warp-cooperative kernel's candidate buffer (knn3w_overflow: k rounds of "next smallest
+    (distance, index)" inside the kernel, teams of 1, 2 and 4 warps): a collapsed cloud, a cloud of 16 distinct points,
+    a cloud with one NaN point, next to an ordinary cloud that must be left alone."""
+    monkeypatch.setenv("PCC_KNN3_SIMT", "1")  # read per call: the SIMT xyz kernels for every n
+    pool = synthetic.knn_xyz(1, 16)[0]                                  # (3, 16)
+    few = pool[:, torch.arange(n) % 16]                                 # every point 1/16 of the cloud
+    nanc = torch.zeros(3, n)
+    nanc[:, 7] = float("nan")
+    x = torch.stack([torch.zeros(3, n), few, synthetic.knn_xyz(1, n)[0], nanc]).contiguous()
+    got = neighbour_ops.knn(x.to(cuda), k).cpu().numpy()
+    want = oracle.knn(x[:3].numpy(), k)
+    assert np.array_equal(got[:3], want)
+    # the NaN point is never a neighbour of the others; rows of the real points: the lowest k indices except 7
+    real = np.array([i for i in range(n) if i != 7][:k])
+    rows = np.array([i for i in range(n) if i != 7])
+    assert np.array_equal(got[3][rows], np.broadcast_to(real, (n - 1, k)))
+
+
 @pytest.mark.parametrize("case", ["xyz_k20", "xyz_k4", "feat64_k20", "feat128_k25"])
 def test_knn_golden_reference(cuda, golden, case):
     g = golden["knn"]
