@@ -25,7 +25,7 @@ NVCC_FLAGS = [
 # finalize -> loss reduction (measured on B200, tools/pdl_probe.py: NNDistance 58.7 -> 56.7 us, bit-identical; on the EMD
 # solver sweeps it is a loss).  PCC_PDL_MASK=0 in the environment switches it off at run time.
 PDL_FLAGS = ["-DPCC_PDL", "-DPCC_PDL_DEFAULT_MASK=1"]
-EXTRA_FLAGS = {"lib.cu": PDL_FLAGS, "chamfer.cu": PDL_FLAGS}
+EXTRA_FLAGS = {"lib.cu": PDL_FLAGS, "chamfer.cu": PDL_FLAGS, "knn_tc2.cu": PDL_FLAGS}
 
 
 def nvcc() -> str:

@@ -115,6 +115,10 @@ knn_tc2_prep_kernel(int c, int n, bool pm, const float *__restrict__ x, float *_
       bt[2 * R] = real ? T2_C1 * sqrtf(s) : 0.f;
     }
   }
+  // the main kernel may become resident (barriers, TMEM allocation) while the last CTAs of this one drain; it executes
+  // griddepcontrol.wait before it reads anything written here.  Triggered at the END: a main-kernel CTA takes a whole SM's
+  // shared memory, so an early trigger would starve the CTAs of this kernel that are still queued.
+  pdl_trigger();
 }
 
 struct T2Ctl {
@@ -194,6 +198,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  pdl_wait();  // everything above overlapped the prep kernel; its outputs (xT, norms, bounds) are read from here on
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -578,7 +583,8 @@ static int launch_tc2(int b, int c, int n, int k, int npad, bool pm, const float
   if (rc == 0) rc = tc_make_map(&mr, xT, b, n, Cfg::C, R);
   if (rc != 0) return rc;
   dim3 grid((n + Cfg::QUERIES - 1) / Cfg::QUERIES, b);
-  knn_tc2_kernel<KB, HALVES, R><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mq, mr, n, k, npad, xT, norms, bounds, idx, dist);
+  PCC_LAUNCH(PDL_CHAMFER, PCC_K(knn_tc2_kernel<KB, HALVES, R>), grid, Cfg::THREADS, Cfg::SMEM, st, mq, mr, n, k, npad,
+             xT, (const float *)norms, (const float *)bounds, idx, dist);
   return (int)cudaGetLastError();
 }
 
