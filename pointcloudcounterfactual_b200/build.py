@@ -21,9 +21,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
-# Programmatic dependent launch (csrc/common.cuh) is compiled into the Chamfer forward chain only: symmetric kernel ->
-# finalize -> loss reduction (measured on B200, tools/pdl_probe.py: NNDistance 58.7 -> 56.7 us, bit-identical; on the EMD
-# solver sweeps it is a loss).  PCC_PDL_MASK=0 in the environment switches it off at run time.
+# Programmatic dependent launch (csrc/common.cuh) is compiled into the Chamfer forward chain: symmetric kernel ->
+# finalize -> loss reduction (measured on B200, tools/pdl_probe.py: NNDistance 58.7 -> 56.7 us, bit-identical) and the
+# feature kNN's prep -> main pair (79.3 -> 78.6 us with the trigger at the end of the prep kernel); on the EMD solver
+# sweeps it is a loss.  PCC_PDL_MASK=0 in the environment switches it off at run time.
 PDL_FLAGS = ["-DPCC_PDL", "-DPCC_PDL_DEFAULT_MASK=1"]
 EXTRA_FLAGS = {"lib.cu": PDL_FLAGS, "chamfer.cu": PDL_FLAGS, "knn_tc2.cu": PDL_FLAGS}
 
